@@ -1,0 +1,113 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED Python reference at /root/reference.
+
+Run in the build container only:  python -m oracle.gen_golden
+Each fixture stores the input planes, the parameters, and the outputs of the reference's own
+encode_video() run with the defined fp64 DCT monkeypatched in (oracle/ref_harness.py):
+container bytes, reconstructed planes, quantised level planes, mv.txt, plus per-frame details from
+the in-memory frame loop (MVs, modes, avg_mae, comparison counts, bits per row, bit strings).
+TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh  # noqa: E402
+from tests import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (generator, kwargs for the generator, encoder parameters)
+    "fs_i8_r4_qp3": ("moving", dict(seed=11, height=64, width=96, nframes=10, step=3, clamp=16),
+                     dict(block=8, search_range=4, qp=3, i_period=8, nref=1)),
+    "fs_i16_r2_nref4": ("moving", dict(seed=12, height=64, width=96, nframes=7, step=2, clamp=16),
+                        dict(block=16, search_range=2, qp=2, i_period=8, nref=4)),
+    "fastme_i16_nref4": ("moving", dict(seed=13, height=64, width=96, nframes=8, step=2, clamp=24),
+                         dict(block=16, search_range=4, qp=3, i_period=8, nref=4, fastme=True)),
+    "frac_fs_i8_r2_nref2": ("moving", dict(seed=14, height=48, width=64, nframes=6, step=2, clamp=16),
+                            dict(block=8, search_range=2, qp=1, i_period=4, nref=2, frac=True)),
+    "frac_fastme_i8_nref3": ("moving", dict(seed=15, height=48, width=64, nframes=7, step=2, clamp=16),
+                             dict(block=8, search_range=2, qp=4, i_period=5, nref=3, frac=True, fastme=True)),
+    "fs_i4_r3_nref2": ("moving", dict(seed=16, height=32, width=48, nframes=5, step=2, clamp=16),
+                       dict(block=4, search_range=3, qp=1, i_period=3, nref=2)),
+    "ties_i8_r4": ("poster", dict(seed=17, height=64, width=96, nframes=5),
+                   dict(block=8, search_range=4, qp=2, i_period=5, nref=2)),
+    "ties_fastme_i16": ("poster", dict(seed=18, height=64, width=96, nframes=5),
+                        dict(block=16, search_range=4, qp=5, i_period=5, nref=2, fastme=True)),
+    "fs_i16_r8_qp6": ("moving", dict(seed=19, height=96, width=128, nframes=4, step=6, clamp=32),
+                      dict(block=16, search_range=8, qp=6, i_period=4, nref=1)),
+}
+
+
+def frame_details(frames, enc):
+    objs = rh.ref_encode_frames(frames, **enc)
+    det = []
+    for fr in objs:
+        d = {"intra": int(fr.prediction_mode.value), "avg_mae": float(fr.avg_mae),
+             "mae_comparisons": int(fr.total_mae_comparisons),
+             "bits_per_row": [int(b) for b in fr.bits_per_row],
+             "pred_nbits": len(fr.entropy_encoded_prediction_data),
+             "coef_nbits": len(fr.entropy_encoded_DCT_coffs),
+             "pred_sha": hashlib.sha256(fr.entropy_encoded_prediction_data.tobytes()).hexdigest(),
+             "coef_sha": hashlib.sha256(fr.entropy_encoded_DCT_coffs.tobytes()).hexdigest()}
+        if d["intra"]:
+            d["modes"] = [int(m) for m in fr.intra_modes]
+        else:
+            keys = sorted(fr.mv_field.keys(), key=lambda k: (k[1], k[0]))
+            d["mv"] = [[int(v) for v in fr.mv_field[k]] for k in keys]
+        det.append(d)
+    return det
+
+
+def main(only=None):
+    os.makedirs(GOLD, exist_ok=True)
+    for name, (gen, gk, enc) in CASES.items():
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        frames = synth.moving_clip(**gk) if gen == "moving" else synth.posterised_clip(**gk)
+        out = rh.ref_encode_video(frames, **enc)
+        det = frame_details(frames, enc)
+        meta = {"generator": gen, "gen_kwargs": gk, "enc": enc, "frames": det,
+                "dct_mode": "fp64_defined", "encoded_sha256": hashlib.sha256(out["encoded"]).hexdigest()}
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"),
+                            frames=frames, encoded=np.frombuffer(out["encoded"], dtype=np.uint8),
+                            recon=out["recon"], levels=out["levels"], resid_mc=out["resid_mc"],
+                            resid_nomc=out["resid_nomc"], mv_txt=np.array(out["mv_txt"]),
+                            meta=np.array(json.dumps(meta)))
+        print(f"{name}: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
+
+    # CIF stand-in for BASELINE config 1 (Foreman is an LFS pointer): the reference's own synthetic
+    # generator tests/y_generator.py, 10 frames, i=8 r=4 qp=3 I_Period=8.
+    if not only or "cif_c1" in only:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_y_generator",
+                                                      os.path.join(rh.REFERENCE_ROOT, "tests", "y_generator.py"))
+        yg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(yg)
+        raw = yg.generate_yuv_bytestream(352, 288, 10)
+        frames = np.frombuffer(raw, dtype=np.uint8).reshape(10, 288, 352)
+        enc = dict(block=8, search_range=4, qp=3, i_period=8, nref=1)
+        t0 = time.time()
+        out = rh.ref_encode_video(frames, **enc)
+        meta = {"generator": "reference tests/y_generator.py generate_yuv_bytestream(352,288,10)", "enc": enc,
+                "dct_mode": "fp64_defined", "encoded_sha256": hashlib.sha256(out["encoded"]).hexdigest(),
+                "recon_sha256": hashlib.sha256(out["recon"].tobytes()).hexdigest(),
+                "levels_sha256": hashlib.sha256(out["levels"].tobytes()).hexdigest()}
+        np.savez_compressed(os.path.join(GOLD, "cif_c1.npz"), frames=frames,
+                            encoded=np.frombuffer(out["encoded"], dtype=np.uint8),
+                            mv_txt=np.array(out["mv_txt"]), meta=np.array(json.dumps(meta)))
+        print(f"cif_c1: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
