@@ -1,0 +1,247 @@
+"""ctypes binding of libbvc_b200.so (include/bvc.h).  Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
+    "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_me_time", "bvc_me_work_per_frame",
+]
+
+
+class BvcError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "block_size", "search_range", "qp", "nref_frames",
+                                       "fast_me", "frac_me", "i_period")]
+
+
+class FrameOut(C.Structure):
+    _fields_ = [("recon", C.c_void_p), ("levels", C.c_void_p), ("mv", C.c_void_p), ("sad", C.c_void_p),
+                ("modes", C.c_void_p), ("resid_mc", C.c_void_p), ("resid_nomc", C.c_void_p),
+                ("pred_bytes", C.c_void_p), ("pred_cap", C.c_size_t), ("coef_bytes", C.c_void_p),
+                ("coef_cap", C.c_size_t), ("bits_per_row", C.c_void_p),
+                ("pred_nbits", C.c_int64), ("coef_nbits", C.c_int64), ("avg_mae", C.c_double),
+                ("mae_comparisons", C.c_int64)]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libbvc_b200.so")
+
+
+def load_library():
+    """Load libbvc_b200.so.  No fallback: a missing library is an error, not a slow path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise BvcError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"or `make -C basic_video_codec_b200/csrc` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(path)
+    L.bvc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_int]
+    L.bvc_create.restype = C.c_int
+    L.bvc_destroy.argtypes = [C.c_void_p]
+    L.bvc_destroy.restype = None
+    L.bvc_last_error.argtypes = [C.c_void_p]
+    L.bvc_last_error.restype = C.c_char_p
+    L.bvc_set_qp.argtypes = [C.c_void_p, C.c_int]
+    L.bvc_encode_iframe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FrameOut)]
+    L.bvc_encode_pframe.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(FrameOut)]
+    L.bvc_me_search.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_int64)]
+    L.bvc_interp_halfpel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bvc_dct_quant_recon.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    L.bvc_encode_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+    L.bvc_clip_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+    L.bvc_launch_count.argtypes = [C.c_void_p]
+    L.bvc_launch_count.restype = C.c_int64
+    L.bvc_last_me_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.bvc_me_work_per_frame.argtypes = [C.c_void_p, C.c_int]
+    L.bvc_me_work_per_frame.restype = C.c_int64
+    _LIB = L
+    return L
+
+
+def _raise(code: int, msg: str):
+    """Map C status codes onto the exception types the reference raises."""
+    if code == BVC_ERR_INVALID:
+        raise ValueError(msg)
+    if code == BVC_ERR_OVERFLOW:
+        raise OverflowError(msg)
+    if code == BVC_ERR_NOMEM:
+        raise MemoryError(msg)
+    if code == BVC_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise BvcError(msg)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class FrameResult:
+    """Plain record of one encoded frame (numpy arrays + bit strings)."""
+    __slots__ = ("recon", "levels", "mv", "sad", "modes", "resid_mc", "resid_nomc", "pred_bytes", "pred_nbits",
+                 "coef_bytes", "coef_nbits", "bits_per_row", "avg_mae", "mae_comparisons")
+
+
+class Context:
+    """One encoder context = one GPU + one geometry/parameter set (bvc_ctx)."""
+
+    def __init__(self, width, height, block_size, search_range, qp, nref_frames=1, fast_me=False, frac_me=False,
+                 i_period=1, device=0, max_lanes=1):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        self.params = Params(int(width), int(height), int(block_size), int(max(search_range, 0)), int(qp),
+                             int(nref_frames), int(bool(fast_me)), int(bool(frac_me)), int(i_period))
+        rc = self._L.bvc_create(C.byref(self._h), int(device), C.byref(self.params), int(max_lanes))
+        if rc != BVC_OK:
+            msg = self._L.bvc_last_error(None).decode()
+            self._h = C.c_void_p()
+            _raise(rc, msg)
+        self.W, self.H, self.bs = int(width), int(height), int(block_size)
+        self.nblk = (self.W // self.bs) * (self.H // self.bs)
+        self.rows = self.H // self.bs
+        self.max_lanes = int(max_lanes)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.bvc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != BVC_OK:
+            _raise(rc, self._L.bvc_last_error(self._h).decode())
+
+    # ---- frame level -------------------------------------------------------------------------
+    def _frame(self, cur, refs, qp_rows, intra, debug_planes=True):
+        H, W = self.H, self.W
+        cur = np.ascontiguousarray(cur, dtype=np.uint8)
+        if cur.shape != (H, W):
+            raise ValueError(f"frame shape {cur.shape} != {(H, W)}")
+        r = FrameResult()
+        r.recon = np.empty((H, W), np.uint8)
+        r.levels = np.empty((H, W), np.int16)
+        r.mv = np.zeros((self.nblk, 3), np.int32)
+        r.sad = np.empty(self.nblk, np.int32)
+        r.modes = np.zeros(self.nblk, np.int32)
+        r.resid_mc = np.empty((H, W), np.int8) if debug_planes else None
+        r.resid_nomc = np.zeros((H, W), np.int8) if debug_planes else None
+        r.bits_per_row = np.empty(self.rows, np.int64)
+        coef_cap = self.nblk * (832 if self.bs == 16 else 192 if self.bs == 8 else 48) + 64
+        pred_cap = self.nblk * 12 + self.rows * 8 + 64
+        pred = np.empty(pred_cap, np.uint8)
+        coef = np.empty(coef_cap, np.uint8)
+        fo = FrameOut()
+        fo.recon, fo.levels, fo.mv, fo.sad, fo.modes = _p(r.recon), _p(r.levels), _p(r.mv), _p(r.sad), _p(r.modes)
+        fo.resid_mc, fo.resid_nomc = _p(r.resid_mc), _p(r.resid_nomc)
+        fo.pred_bytes, fo.pred_cap, fo.coef_bytes, fo.coef_cap = _p(pred), pred_cap, _p(coef), coef_cap
+        fo.bits_per_row = _p(r.bits_per_row)
+        qp = np.ascontiguousarray(qp_rows, dtype=np.int32) if qp_rows is not None else None
+        if intra:
+            self._check(self._L.bvc_encode_iframe(self._h, _p(cur), _p(qp), C.byref(fo)))
+        else:
+            keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+            arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+            self._check(self._L.bvc_encode_pframe(self._h, _p(cur), arr, len(keep), _p(qp), C.byref(fo)))
+        r.pred_nbits, r.coef_nbits = int(fo.pred_nbits), int(fo.coef_nbits)
+        r.pred_bytes = pred[: (r.pred_nbits + 7) // 8].tobytes()
+        r.coef_bytes = coef[: (r.coef_nbits + 7) // 8].tobytes()
+        r.avg_mae, r.mae_comparisons = float(fo.avg_mae), int(fo.mae_comparisons)
+        return r
+
+    def encode_iframe(self, cur, qp_rows=None, debug_planes=True):
+        return self._frame(cur, None, qp_rows, True, debug_planes)
+
+    def encode_pframe(self, cur, refs, qp_rows=None, debug_planes=True):
+        return self._frame(cur, list(refs), qp_rows, False, debug_planes)
+
+    # ---- hooks ---------------------------------------------------------------------------------
+    def me_search(self, cur, refs):
+        cur = np.ascontiguousarray(cur, dtype=np.uint8)
+        keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+        arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+        mv = np.zeros((self.nblk, 3), np.int32)
+        sad = np.zeros(self.nblk, np.int32)
+        cmp_ = C.c_int64(0)
+        self._check(self._L.bvc_me_search(self._h, _p(cur), arr, len(keep), _p(mv), _p(sad), C.byref(cmp_)))
+        return mv, sad, int(cmp_.value)
+
+    def interp_halfpel(self, ref):
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        out = np.empty((2 * self.H, 2 * self.W), np.uint8)
+        self._check(self._L.bvc_interp_halfpel(self._h, _p(ref), _p(out)))
+        return out
+
+    # ---- clip level ------------------------------------------------------------------------------
+    def encode_clip(self, frames, want_recon=False, out_capacity=None):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = frames.shape[0]
+        cap = int(out_capacity or (n * self.W * self.H + (1 << 20)))
+        out = np.empty(cap, np.uint8)
+        ln = C.c_size_t(0)
+        recon = np.empty_like(frames) if want_recon else None
+        self._check(self._L.bvc_encode_clip(self._h, _p(frames), n, _p(out), cap, C.byref(ln), _p(recon)))
+        return out[: ln.value].tobytes(), recon
+
+    def clip_upload(self, frames):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        self._check(self._L.bvc_clip_upload(self._h, _p(frames), frames.shape[0]))
+
+    def encode_clip_resident(self, nframes, out=None):
+        cap = nframes * self.W * self.H + (1 << 20)
+        if out is None:
+            out = np.empty(cap, np.uint8)
+        ln = C.c_size_t(0)
+        self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
+        return out, int(ln.value)
+
+    # ---- instrumentation -----------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._L.bvc_launch_count(self._h))
+
+    def last_me_time(self):
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._L.bvc_last_me_time(self._h, C.byref(ms), C.byref(n))
+        return float(ms.value), int(n.value)
+
+    def me_work_per_frame(self, nref_avail=1):
+        return int(self._L.bvc_me_work_per_frame(self._h, int(nref_avail)))
+
+
+def dct_quant_recon(residual, pred, qp, device=0):
+    """apply_dct_and_quantization + reconstruct_block on a batch of blocks (n, bs, bs)."""
+    L = load_library()
+    residual = np.ascontiguousarray(residual, dtype=np.int16)
+    pred = np.ascontiguousarray(pred, dtype=np.int16)
+    n, bs, _ = residual.shape
+    level = np.empty((n, bs, bs), np.int16)
+    recon = np.empty((n, bs, bs), np.uint8)
+    idct = np.empty((n, bs, bs), np.float64)
+    coef = np.empty((n, bs, bs), np.float64)
+    rc = L.bvc_dct_quant_recon(int(device), _p(residual), _p(pred), n, bs, int(qp), _p(level), _p(recon), _p(idct), _p(coef))
+    if rc != BVC_OK:
+        _raise(rc, L.bvc_last_error(None).decode())
+    return level, recon, idct, coef

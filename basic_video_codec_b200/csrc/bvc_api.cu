@@ -1,0 +1,769 @@
+// bvc_api.cu -- the C ABI (include/bvc.h): context, device memory layout, per-step kernel sequencing,
+// GOP-lane scheduling and host-side container assembly.
+//
+// Device layout (one context = one GPU, one geometry):
+//   in_pool   [nframes][H][pitch]            input luma planes (whole clip resident; 1.25 GB for 600 x 1080p)
+//   ref_pool  [lanes][nref+1][pps][H][pitch] reconstruction ring per GOP lane; pps = 4 phase planes when
+//                                            half-pel ME is on (phase 0 = the reconstruction itself), else 1.
+//                                            One 3-D TMA tensor map (x, y, plane) covers the whole pool.
+//   per lane  mv int4[nblk] | modes | levels (frame API only) | blk_bits[nblk][blk_words] | blk_nbits |
+//             coef/pred streams (double buffered so the D2H of step s overlaps step s+1)
+// A "step" encodes frame k of every active GOP lane with one launch per kernel:
+//   I step: tq_iframe (wavefront)            -> pack_scan -> pack_emit [-> halfpel]
+//   P step: me (full search | fastme) -> tq_pframe -> pack_scan -> pack_emit [-> halfpel]
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bvc.h"
+#include "bvc_kernels.h"
+
+namespace bvc {
+cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                          long long* cmp_out, cudaStream_t st);
+}
+
+using namespace bvc;
+
+static std::string g_create_error;
+
+struct bvc_ctx {
+    int device = 0;
+    bvc_params p{};
+    Geom g{};
+    int max_lanes = 1;
+    int pps = 1;          // planes per ring slot
+    int slots = 2;        // ring slots per lane (nref + 1)
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    uint8_t* in_pool = nullptr;
+    size_t in_planes = 0;
+    uint8_t* ref_pool = nullptr;
+    size_t ref_planes = 0;
+    CUtensorMap ref_map{};
+    bool have_map = false;
+
+    int4* d_mv = nullptr;
+    int32_t *d_modes = nullptr, *d_isad = nullptr, *d_qp_rows = nullptr, *d_blk_nbits = nullptr;
+    int16_t* d_levels = nullptr;       // lane 0 only (frame API)
+    int8_t *d_resid_mc = nullptr, *d_resid_nomc = nullptr;
+    uint32_t* d_blk_bits = nullptr;
+    int blk_words = 0;
+    long long *d_coef_off = nullptr, *d_frame_bits[2] = {nullptr, nullptr}, *d_row_bits = nullptr, *d_pred_row_off = nullptr,
+              *d_cmp = nullptr;
+    uint32_t *d_coef_stream[2] = {nullptr, nullptr}, *d_pred_stream[2] = {nullptr, nullptr};
+    size_t coef_cap_words = 0, pred_cap_words = 0;
+    int* d_progress = nullptr;
+    MeLane* d_me_lanes = nullptr;
+    FrameLane* d_fr_lanes = nullptr;
+    size_t lane_desc_cap = 0;
+    const uint8_t** d_hp_src = nullptr;
+    uint8_t** d_hp_dst = nullptr;
+    size_t hp_desc_cap = 0;
+
+    // host staging
+    uint8_t* h_stage = nullptr;  // pinned arena for stream downloads
+    size_t h_stage_cap = 0;
+    long long* h_bits = nullptr;  // pinned [steps][lanes][2]
+    size_t h_bits_cap = 0;
+    void* h_desc = nullptr;       // pinned descriptor staging
+    size_t h_desc_cap = 0;
+
+    // instrumentation of the last clip call
+    double last_me_ms = 0;
+    int64_t last_me_launches = 0;
+    int resident_frames = 0;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[512];                                                                               \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            c->err = b__;                                                                                \
+            return BVC_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+static int fail(bvc_ctx* c, int code, const char* msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_ref_map(bvc_ctx* c) {
+    c->have_map = false;
+    if (c->p.fast_me) return BVC_OK;
+    const int R = c->p.search_range;
+    MeTileCfg cfg = me_tile_config(c->g.bs, R);
+    if (!cfg.tiled) return BVC_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, BVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)c->g.W, (cuuint64_t)c->g.H, (cuuint64_t)c->ref_planes};
+    cuuint64_t strides[2] = {(cuuint64_t)c->g.pitch, (cuuint64_t)c->g.plane_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)cfg.win_pitch, (cuuint32_t)cfg.rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((EncodeTiledFn)fn)(&c->ref_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->ref_pool, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(c, BVC_ERR_CUDA, b);
+    }
+    c->have_map = true;
+    return BVC_OK;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int max_lanes) {
+    if (!out || !p) return fail(nullptr, BVC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const int bs = p->block_size;
+    if (!(bs == 4 || bs == 8 || bs == 16)) return fail(nullptr, BVC_ERR_UNSUPPORTED, "block_size must be 4, 8 or 16");
+    if (p->width < bs || p->height < bs)  // block_predictor.py:70-71
+        return fail(nullptr, BVC_ERR_INVALID, "frame smaller than block_size");
+    if (p->width % bs || p->height % bs) return fail(nullptr, BVC_ERR_UNSUPPORTED, "width/height must be multiples of block_size (pad first)");
+    int lg = 0; while ((1 << lg) < bs) lg++;
+    if (p->qp < 0 || p->qp > lg + 7) return fail(nullptr, BVC_ERR_INVALID, "qp > log2(block_size) + 7");  // params.py:29-30
+    if (p->nref_frames < 1 || p->nref_frames > BVC_MAX_REFS) return fail(nullptr, BVC_ERR_UNSUPPORTED, "nref_frames must be 1..8");
+    if (!p->fast_me && (p->search_range < 0 || p->search_range * (p->frac_me ? 2 : 1) > 255))
+        return fail(nullptr, BVC_ERR_UNSUPPORTED, "search_range out of supported range");
+    if (p->i_period < 1) return fail(nullptr, BVC_ERR_INVALID, "i_period must be >= 1");
+    if (max_lanes < 1) max_lanes = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, BVC_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        return fail(nullptr, BVC_ERR_CUDA, "device is not sm_100 class (kernels are built for sm_100a only)");
+
+    bvc_ctx* c = new bvc_ctx();
+    c->device = device;
+    c->p = *p;
+    c->max_lanes = max_lanes;
+    Geom& g = c->g;
+    g.W = p->width; g.H = p->height; g.bs = bs;
+    g.pitch = (g.W + 15) / 16 * 16;
+    g.bw = g.W / bs; g.bh = g.H / bs; g.nblk = g.bw * g.bh;
+    g.plane_bytes = ((size_t)g.pitch * g.H + 255) / 256 * 256;
+    c->pps = p->frac_me ? 4 : 1;
+    c->slots = p->nref_frames + 1;
+    c->blk_words = tq_blk_words(bs);
+    auto boot = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+        const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
+        c->ref_planes = L * c->slots * c->pps;
+        CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
+        CK(cudaMemset(c->ref_pool, 0, c->ref_planes * g.plane_bytes + 4096));
+        CK(dalloc(&c->d_mv, L * nb));
+        CK(dalloc(&c->d_modes, L * nb));
+        CK(dalloc(&c->d_isad, L * nb));
+        CK(dalloc(&c->d_qp_rows, L * g.bh));
+        CK(dalloc(&c->d_blk_nbits, L * nb));
+        CK(dalloc(&c->d_blk_bits, L * nb * c->blk_words));
+        CK(dalloc(&c->d_levels, (size_t)g.W * g.H));
+        CK(dalloc(&c->d_resid_mc, (size_t)g.W * g.H));
+        CK(dalloc(&c->d_resid_nomc, (size_t)g.W * g.H));
+        CK(dalloc(&c->d_coef_off, L * (nb + 1)));
+        CK(dalloc(&c->d_row_bits, L * g.bh));
+        CK(dalloc(&c->d_pred_row_off, L * (g.bh + 1)));
+        CK(dalloc(&c->d_cmp, L));
+        CK(dalloc(&c->d_progress, L * g.bh));
+        c->coef_cap_words = nb * c->blk_words + 8;
+        c->pred_cap_words = nb * 3 + g.bh + 8;
+        for (int i = 0; i < 2; i++) {
+            CK(dalloc(&c->d_coef_stream[i], L * c->coef_cap_words));
+            CK(dalloc(&c->d_pred_stream[i], L * c->pred_cap_words));
+            CK(dalloc(&c->d_frame_bits[i], L * 2));
+        }
+        std::vector<int32_t> q(L * g.bh, p->qp);
+        CK(cudaMemcpy(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+        int rc = make_ref_map(c);
+        if (rc != BVC_OK) return rc;
+        return BVC_OK;
+    };
+    int rc = boot();
+    if (rc != BVC_OK) {
+        g_create_error = c->err;
+        bvc_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return BVC_OK;
+}
+
+extern "C" void bvc_destroy(bvc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+    cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
+    cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
+    cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
+    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_progress); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_coef_stream[i]); cudaFree(c->d_pred_stream[i]); cudaFree(c->d_frame_bits[i]); }
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_bits) cudaFreeHost(c->h_bits);
+    if (c->h_desc) cudaFreeHost(c->h_desc);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    delete c;
+}
+
+extern "C" const char* bvc_last_error(const bvc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+extern "C" int64_t bvc_launch_count(const bvc_ctx* c) { return c ? c->launches : 0; }
+extern "C" int bvc_last_me_time(const bvc_ctx* c, double* ms, int64_t* launches) {
+    if (!c) return BVC_ERR_INVALID;
+    if (ms) *ms = c->last_me_ms;
+    if (launches) *launches = c->last_me_launches;
+    return BVC_OK;
+}
+
+extern "C" int bvc_set_qp(bvc_ctx* c, int qp) {
+    if (!c) return BVC_ERR_INVALID;
+    int lg = 0; while ((1 << lg) < c->g.bs) lg++;
+    if (qp < 0 || qp > lg + 7) return fail(c, BVC_ERR_INVALID, "qp > log2(block_size) + 7");
+    CK(cudaSetDevice(c->device));
+    c->p.qp = qp;
+    std::vector<int32_t> q((size_t)c->max_lanes * c->g.bh, qp);
+    CK(cudaMemcpyAsync(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return BVC_OK;
+}
+
+extern "C" int64_t bvc_me_work_per_frame(const bvc_ctx* c, int nref_avail) {
+    if (!c || c->p.fast_me) return 0;
+    const Geom& g = c->g;
+    const int sc = c->p.frac_me ? 2 : 1, R = c->p.search_range * sc;
+    // valid candidates per block factorise into x and y counts (block_predictor.py:116-143)
+    auto count = [&](int o, int n, int size) {  // positions m in [-R,R] with 0 <= sc*o+m and sc*o+m+sc*n <= sc*size
+        int lo = std::max(-R, -sc * o), hi = std::min(R, sc * (size - n - o));
+        return std::max(0, hi - lo + 1);
+    };
+    int64_t tot = 0;
+    for (int by = 0; by < g.bh; by++)
+        for (int bx = 0; bx < g.bw; bx++) tot += (int64_t)count(bx * g.bs, g.bs, g.W) * count(by * g.bs, g.bs, g.H);
+    return tot * g.bs * g.bs * nref_avail;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_in_pool(bvc_ctx* c, size_t planes) {
+    if (planes <= c->in_planes) return BVC_OK;
+    if (c->in_pool) CK(cudaFree(c->in_pool));
+    c->in_pool = nullptr;
+    c->in_planes = 0;
+    CK(cudaMalloc((void**)&c->in_pool, planes * c->g.plane_bytes + 4096));
+    c->in_planes = planes;
+    return BVC_OK;
+}
+static int ensure_lane_desc(bvc_ctx* c, size_t n) {
+    if (n <= c->lane_desc_cap) return BVC_OK;
+    if (c->d_me_lanes) CK(cudaFree(c->d_me_lanes));
+    if (c->d_fr_lanes) CK(cudaFree(c->d_fr_lanes));
+    CK(dalloc(&c->d_me_lanes, n));
+    CK(dalloc(&c->d_fr_lanes, n));
+    if (c->d_hp_src) CK(cudaFree(c->d_hp_src));
+    if (c->d_hp_dst) CK(cudaFree(c->d_hp_dst));
+    CK(dalloc(&c->d_hp_src, n * BVC_MAX_REFS));
+    CK(dalloc(&c->d_hp_dst, n * BVC_MAX_REFS));
+    c->lane_desc_cap = n;
+    return BVC_OK;
+}
+static int ensure_pinned(bvc_ctx* c, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return BVC_OK;
+    if (*p) CK(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    size_t n = std::max(need, (size_t)1 << 20);
+    CK(cudaHostAlloc(p, n, cudaHostAllocDefault));
+    *cap = n;
+    return BVC_OK;
+}
+
+static inline int ring_plane(const bvc_ctx* c, int lane, int slot) { return (lane * c->slots + slot) * c->pps; }
+static inline uint8_t* plane_ptr(const bvc_ctx* c, int plane) { return c->ref_pool + (size_t)plane * c->g.plane_bytes; }
+
+static int upload_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src) {
+    CK(cudaMemcpy2DAsync(dst, c->g.pitch, src, c->g.W, c->g.W, c->g.H, cudaMemcpyHostToDevice, c->st));
+    return BVC_OK;
+}
+static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src) {
+    CK(cudaMemcpy2DAsync(dst, c->g.W, src, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToHost, c->st));
+    return BVC_OK;
+}
+
+struct StepPlan {
+    int nl = 0;
+    bool intra = false;
+    size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
+};
+
+// Enqueue the kernels of one step on c->st.  `parity` selects the stream double buffer.
+static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_api, cudaEvent_t me_start, cudaEvent_t me_stop) {
+    const Geom& g = c->g;
+    const int nl = sp.nl;
+    TqArgs t{};
+    t.cur_base = c->in_pool; t.cur_plane_bytes = g.plane_bytes; t.cur_pitch = g.pitch;
+    t.ref_base = c->ref_pool; t.ref_plane_bytes = g.plane_bytes; t.ref_pitch = g.pitch;
+    t.lanes = c->d_fr_lanes + sp.desc_off;
+    t.mv = c->d_mv; t.modes = c->d_modes; t.isad = c->d_isad; t.qp_rows = c->d_qp_rows;
+    t.levels = frame_api ? c->d_levels : nullptr;
+    t.resid_mc = frame_api ? c->d_resid_mc : nullptr;
+    t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
+    t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
+    t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
+    if (sp.intra) {
+        CK(cudaMemsetAsync(c->d_progress, 0, (size_t)nl * g.bh * sizeof(int), c->st));
+        CK(launch_tq_iframe(t, nl, c->st));
+        c->launches += 1;
+    } else {
+        MeArgs m{};
+        m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
+        m.lanes = c->d_me_lanes + sp.desc_off;
+        m.out = c->d_mv;
+        m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
+        m.sc = c->p.frac_me ? 2 : 1;
+        m.nphase = c->p.frac_me ? 4 : 1;
+        m.R = c->p.search_range;
+        m.Rh = c->p.search_range * m.sc;
+        if (me_start) CK(cudaEventRecord(me_start, c->st));
+        if (c->p.fast_me) {
+            CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
+        } else {
+            CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->st));
+        }
+        if (me_stop) CK(cudaEventRecord(me_stop, c->st));
+        CK(launch_tq_pframe(t, nl, c->st));
+        c->launches += 2;
+    }
+    PackArgs pk{};
+    pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
+    pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
+    pk.coef_off = c->d_coef_off;
+    pk.coef_stream = c->d_coef_stream[parity]; pk.pred_stream = c->d_pred_stream[parity];
+    pk.frame_bits = c->d_frame_bits[parity]; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
+    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
+    pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
+    pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
+    CK(launch_pack(pk, nl, c->st));
+    c->launches += 2;
+    return BVC_OK;
+}
+
+// half-pel phase planes (K2).  Descriptors (phase-0 plane pointers and the three destination planes
+// behind them) are uploaded ahead of time; the launch itself is asynchronous.
+static int upload_halfpel_desc(bvc_ctx* c, const std::vector<int>& planes, size_t desc_off) {
+    const size_t n = planes.size();
+    if (!n) return BVC_OK;
+    std::vector<const uint8_t*> src(n);
+    std::vector<uint8_t*> dst(n);
+    for (size_t i = 0; i < n; i++) { src[i] = plane_ptr(c, planes[i]); dst[i] = plane_ptr(c, planes[i] + 1); }
+    CK(cudaMemcpy(c->d_hp_src + desc_off, src.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_hp_dst + desc_off, dst.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
+    return BVC_OK;
+}
+static int enqueue_halfpel(bvc_ctx* c, size_t desc_off, int n) {
+    if (!c->p.frac_me || n <= 0) return BVC_OK;
+    const Geom& g = c->g;
+    CK(launch_halfpel(c->d_hp_src + desc_off, c->d_hp_dst + desc_off, n, g.W, g.H, g.pitch, g.plane_bytes, c->st));
+    c->launches += 1;
+    return BVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame-level API
+static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, const int32_t* qp_rows,
+                        bvc_frame_out* out, bool intra, bool me_only, int32_t* mv_out, int32_t* sad_out, int64_t* cmp_out) {
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->device));
+    if (!cur) return fail(c, BVC_ERR_INVALID, "cur is null");
+    if (!intra && (nref_avail < 1 || nref_avail > c->p.nref_frames || !refs))
+        return fail(c, BVC_ERR_INVALID, "nref_avail must be 1..nref_frames");
+    int rc;
+    if ((rc = ensure_in_pool(c, 1)) != BVC_OK) return rc;
+    if ((rc = ensure_lane_desc(c, 1)) != BVC_OK) return rc;
+    if ((rc = upload_plane(c, c->in_pool, cur)) != BVC_OK) return rc;
+    MeLane ml{};
+    FrameLane fl{};
+    ml.cur_plane = 0; fl.cur_plane = 0;
+    ml.nref = fl.nref = intra ? 0 : nref_avail;
+    std::vector<int> hp;
+    for (int k = 0; k < ml.nref; k++) {
+        ml.ref_plane[k] = fl.ref_plane[k] = ring_plane(c, 0, k);
+        if ((rc = upload_plane(c, plane_ptr(c, ml.ref_plane[k]), refs[k])) != BVC_OK) return rc;
+        hp.push_back(ml.ref_plane[k]);
+    }
+    fl.out_plane = ring_plane(c, 0, ml.nref);
+    CK(cudaMemcpyAsync(c->d_me_lanes, &ml, sizeof ml, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->d_fr_lanes, &fl, sizeof fl, cudaMemcpyHostToDevice, c->st));
+    std::vector<int32_t> q(g.bh, c->p.qp);
+    if (qp_rows) q.assign(qp_rows, qp_rows + g.bh);
+    CK(cudaMemcpyAsync(c->d_qp_rows, q.data(), g.bh * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (c->p.frac_me) {
+        if ((rc = upload_halfpel_desc(c, hp, 0)) != BVC_OK) return rc;
+        if ((rc = enqueue_halfpel(c, 0, (int)hp.size())) != BVC_OK) return rc;
+    }
+
+    StepPlan sp;
+    sp.nl = 1; sp.intra = intra; sp.desc_off = 0;
+    if (me_only) {
+        // run only the ME kernel
+        MeArgs m{};
+        m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
+        m.lanes = c->d_me_lanes; m.out = c->d_mv;
+        m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
+        m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
+        if (c->p.fast_me) CK(launch_fastme(m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
+        else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
+        c->launches += 1;
+    } else {
+        if ((rc = enqueue_step(c, sp, 0, true, nullptr, nullptr)) != BVC_OK) return rc;
+    }
+    // ---- downloads ----
+    std::vector<int4> hmv;
+    std::vector<int32_t> hsad(g.nblk);
+    long long hcmp = 0;
+    if (!intra) {
+        hmv.resize(g.nblk);
+        CK(cudaMemcpyAsync(hmv.data(), c->d_mv, (size_t)g.nblk * sizeof(int4), cudaMemcpyDeviceToHost, c->st));
+        if (c->p.fast_me) CK(cudaMemcpyAsync(&hcmp, c->d_cmp, sizeof hcmp, cudaMemcpyDeviceToHost, c->st));
+    } else {
+        CK(cudaMemcpyAsync(hsad.data(), c->d_isad, (size_t)g.nblk * 4, cudaMemcpyDeviceToHost, c->st));
+    }
+    long long fb[2] = {0, 0};
+    if (!me_only) {
+        CK(cudaMemcpyAsync(fb, c->d_frame_bits[0], sizeof fb, cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    if (!intra) {
+        for (int b = 0; b < g.nblk; b++) hsad[b] = hmv[b].w;
+        int32_t* mvd = me_only ? mv_out : (out ? out->mv : nullptr);
+        if (mvd) for (int b = 0; b < g.nblk; b++) { mvd[3 * b] = hmv[b].x; mvd[3 * b + 1] = hmv[b].y; mvd[3 * b + 2] = hmv[b].z; }
+    }
+    int64_t cmp = 0;
+    if (intra) cmp = 2LL * g.nblk;  // params.py:62
+    else if (c->p.fast_me) cmp = hcmp;
+    else {
+        const int64_t n1 = 2LL * c->p.search_range * (c->p.frac_me ? 2 : 1) + 1;
+        cmp = (int64_t)g.nblk * nref_avail * n1 * n1;  // nominal count, block_predictor.py:91
+    }
+    if (me_only) {
+        if (sad_out) memcpy(sad_out, hsad.data(), (size_t)g.nblk * 4);
+        if (cmp_out) *cmp_out = cmp;
+        return BVC_OK;
+    }
+    if (!out) return BVC_OK;
+    if (out->sad) memcpy(out->sad, hsad.data(), (size_t)g.nblk * 4);
+    // avg_mae: sum of per-block MAE in raster order / number of blocks (PFrame.py:67,88; IFrame.py:51,76)
+    double s = 0.0;
+    for (int b = 0; b < g.nblk; b++) s += (double)hsad[b] / (double)(g.bs * g.bs);
+    out->avg_mae = s / (double)g.nblk;
+    out->mae_comparisons = cmp;
+    out->pred_nbits = fb[0];
+    out->coef_nbits = fb[1];
+    const size_t pb = (size_t)((fb[0] + 7) / 8), cb = (size_t)((fb[1] + 7) / 8);
+    if ((out->pred_bytes && pb > out->pred_cap) || (out->coef_bytes && cb > out->coef_cap))
+        return fail(c, BVC_ERR_NOMEM, "output bit buffer too small");
+    if (out->pred_bytes && pb) CK(cudaMemcpyAsync(out->pred_bytes, c->d_pred_stream[0], pb, cudaMemcpyDeviceToHost, c->st));
+    if (out->coef_bytes && cb) CK(cudaMemcpyAsync(out->coef_bytes, c->d_coef_stream[0], cb, cudaMemcpyDeviceToHost, c->st));
+    if (out->recon && (rc = download_plane(c, out->recon, plane_ptr(c, fl.out_plane))) != BVC_OK) return rc;
+    if (out->levels) CK(cudaMemcpyAsync(out->levels, c->d_levels, (size_t)g.W * g.H * 2, cudaMemcpyDeviceToHost, c->st));
+    if (out->resid_mc) CK(cudaMemcpyAsync(out->resid_mc, c->d_resid_mc, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, c->st));
+    if (out->resid_nomc && !intra) CK(cudaMemcpyAsync(out->resid_nomc, c->d_resid_nomc, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, c->st));
+    if (out->modes && intra) CK(cudaMemcpyAsync(out->modes, c->d_modes, (size_t)g.nblk * 4, cudaMemcpyDeviceToHost, c->st));
+    std::vector<long long> rb(g.bh);
+    CK(cudaMemcpyAsync(rb.data(), c->d_row_bits, (size_t)g.bh * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (out->bits_per_row) for (int r = 0; r < g.bh; r++) out->bits_per_row[r] = rb[r];
+    // restore the base-QP rows for later clip calls
+    if (qp_rows) {
+        std::vector<int32_t> qb((size_t)c->max_lanes * g.bh, c->p.qp);
+        CK(cudaMemcpy(c->d_qp_rows, qb.data(), qb.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return BVC_OK;
+}
+
+extern "C" int bvc_encode_iframe(bvc_ctx* c, const uint8_t* cur, const int32_t* qp_rows, bvc_frame_out* out) {
+    if (!c) return BVC_ERR_INVALID;
+    return frame_common(c, cur, nullptr, 0, qp_rows, out, true, false, nullptr, nullptr, nullptr);
+}
+extern "C" int bvc_encode_pframe(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail,
+                                 const int32_t* qp_rows, bvc_frame_out* out) {
+    if (!c) return BVC_ERR_INVALID;
+    return frame_common(c, cur, refs, nref_avail, qp_rows, out, false, false, nullptr, nullptr, nullptr);
+}
+extern "C" int bvc_me_search(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, int32_t* mv,
+                             int32_t* sad, int64_t* comparisons) {
+    if (!c) return BVC_ERR_INVALID;
+    return frame_common(c, cur, refs, nref_avail, nullptr, nullptr, false, true, mv, sad, comparisons);
+}
+
+extern "C" int bvc_interp_halfpel(bvc_ctx* c, const uint8_t* ref, uint8_t* out2x) {
+    if (!c || !ref || !out2x) return BVC_ERR_INVALID;
+    if (!c->p.frac_me) return fail(c, BVC_ERR_INVALID, "context was created without frac_me");
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_lane_desc(c, 1)) != BVC_OK) return rc;
+    const int pl = ring_plane(c, 0, 0);
+    if ((rc = upload_plane(c, plane_ptr(c, pl), ref)) != BVC_OK) return rc;
+    std::vector<int> v{pl};
+    if ((rc = upload_halfpel_desc(c, v, 0)) != BVC_OK) return rc;
+    if ((rc = enqueue_halfpel(c, 0, 1)) != BVC_OK) return rc;
+    uint8_t* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, (size_t)4 * g.W * g.H));
+    CK(launch_halfpel_interleave(plane_ptr(c, pl), g.W, g.H, g.pitch, g.plane_bytes, tmp, c->st));
+    c->launches += 1;
+    CK(cudaMemcpyAsync(out2x, tmp, (size_t)4 * g.W * g.H, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(tmp);
+    return BVC_OK;
+}
+
+extern "C" int bvc_dct_quant_recon(int device, const int16_t* residual, const int16_t* pred, int nblocks, int bs, int qp,
+                                   int16_t* level, uint8_t* recon, double* idct, double* coef) {
+    bvc_ctx tmp;
+    bvc_ctx* c = &tmp;
+    if (!(bs == 4 || bs == 8 || bs == 16)) return fail(nullptr, BVC_ERR_UNSUPPORTED, "block size must be 4, 8 or 16");
+    if (!residual || !pred || !level || !recon || nblocks < 1) return fail(nullptr, BVC_ERR_INVALID, "bad arguments");
+    auto run = [&]() -> int {
+        CK(cudaSetDevice(device));
+        const size_t n = (size_t)nblocks * bs * bs;
+        int16_t *dr = nullptr, *dp = nullptr, *dl = nullptr;
+        uint8_t* dc = nullptr;
+        double *di = nullptr, *dco = nullptr;
+        CK(dalloc(&dr, n)); CK(dalloc(&dp, n)); CK(dalloc(&dl, n)); CK(dalloc(&dc, n));
+        if (idct) CK(dalloc(&di, n));
+        if (coef) CK(dalloc(&dco, n));
+        CK(cudaMemcpy(dr, residual, n * 2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dp, pred, n * 2, cudaMemcpyHostToDevice));
+        CK(launch_tq_blocks(dr, dp, nblocks, bs, qp, dl, dc, di, dco, 0));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(level, dl, n * 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(recon, dc, n, cudaMemcpyDeviceToHost));
+        if (idct) CK(cudaMemcpy(idct, di, n * 8, cudaMemcpyDeviceToHost));
+        if (coef) CK(cudaMemcpy(coef, dco, n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dr); cudaFree(dp); cudaFree(dl); cudaFree(dc); cudaFree(di); cudaFree(dco);
+        return BVC_OK;
+    };
+    int rc = run();
+    if (rc != BVC_OK) g_create_error = tmp.err;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip-level API
+extern "C" int bvc_clip_upload(bvc_ctx* c, const uint8_t* frames, int nframes) {
+    if (!c || !frames || nframes < 1) return BVC_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+    const Geom& g = c->g;
+    if (g.pitch == g.W && g.plane_bytes == (size_t)g.W * g.H) {
+        CK(cudaMemcpyAsync(c->in_pool, frames, (size_t)nframes * g.plane_bytes, cudaMemcpyHostToDevice, c->st));
+    } else {
+        for (int f = 0; f < nframes; f++)
+            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
+                                 cudaMemcpyHostToDevice, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    c->resident_frames = nframes;
+    return BVC_OK;
+}
+
+struct FrameRec {
+    size_t pred_off = 0, coef_off = 0;  // offsets into the pinned staging arena
+    long long pred_bits = 0, coef_bits = 0;
+};
+
+static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
+                            uint8_t* recon) {
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->device));
+    if (nframes < 1 || !out || !out_len) return fail(c, BVC_ERR_INVALID, "bad arguments");
+    const int IP = c->p.i_period, G = c->max_lanes;
+    const int ngop = (nframes + IP - 1) / IP;
+    const int nwaves = (ngop + G - 1) / G;
+    int rc;
+    if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+
+    // ---- plan: one step per (wave, k) ----
+    std::vector<StepPlan> steps;
+    std::vector<MeLane> mel;
+    std::vector<FrameLane> frl;
+    std::vector<std::vector<int>> step_frames;   // clip frame index of every lane of a step
+    std::vector<std::vector<int>> step_outplane;
+    for (int w = 0; w < nwaves; w++) {
+        const int g0 = w * G, g1 = std::min(ngop, g0 + G);
+        for (int k = 0; k < IP; k++) {
+            StepPlan sp;
+            sp.intra = (k == 0);
+            sp.desc_off = mel.size();
+            std::vector<int> fr, op;
+            for (int gi = g0; gi < g1; gi++) {
+                const int f = gi * IP + k;
+                if (f >= nframes) continue;
+                const int lane = gi - g0;
+                MeLane ml{};
+                FrameLane fl{};
+                ml.cur_plane = fl.cur_plane = f;
+                const int nav = std::min(k, c->p.nref_frames);  // deque(maxlen=nRef), cleared at the I frame
+                ml.nref = fl.nref = nav;
+                for (int j = 0; j < nav; j++) {
+                    const int src_k = k - nav + j;              // oldest first (encoder.py:33,154)
+                    ml.ref_plane[j] = fl.ref_plane[j] = ring_plane(c, lane, src_k % c->slots);
+                }
+                fl.out_plane = ring_plane(c, lane, k % c->slots);
+                mel.push_back(ml);
+                frl.push_back(fl);
+                fr.push_back(f);
+                op.push_back(fl.out_plane);
+            }
+            sp.nl = (int)fr.size();
+            if (sp.nl == 0) continue;
+            steps.push_back(sp);
+            step_frames.push_back(fr);
+            step_outplane.push_back(op);
+        }
+    }
+    const size_t nsteps = steps.size();
+    if ((rc = ensure_lane_desc(c, mel.size())) != BVC_OK) return rc;
+    if ((rc = ensure_pinned(c, &c->h_desc, &c->h_desc_cap, mel.size() * (sizeof(MeLane) + sizeof(FrameLane)))) != BVC_OK) return rc;
+    memcpy(c->h_desc, mel.data(), mel.size() * sizeof(MeLane));
+    memcpy((uint8_t*)c->h_desc + mel.size() * sizeof(MeLane), frl.data(), frl.size() * sizeof(FrameLane));
+    CK(cudaMemcpyAsync(c->d_me_lanes, c->h_desc, mel.size() * sizeof(MeLane), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->d_fr_lanes, (uint8_t*)c->h_desc + mel.size() * sizeof(MeLane), frl.size() * sizeof(FrameLane),
+                       cudaMemcpyHostToDevice, c->st));
+    if ((rc = ensure_pinned(c, (void**)&c->h_bits, &c->h_bits_cap, nsteps * (size_t)G * 2 * sizeof(long long))) != BVC_OK) return rc;
+    if (c->p.frac_me) {
+        for (size_t s = 0; s < nsteps; s++)
+            if ((rc = upload_halfpel_desc(c, step_outplane[s], steps[s].desc_off)) != BVC_OK) return rc;
+    }
+
+    // ---- input: whole-clip upload in GOP-wave order so step 0 can start after the first wave's I frames ----
+    if (host_frames) {
+        if (g.pitch == g.W && g.plane_bytes == (size_t)g.W * g.H) {
+            // chunked so that compute on early frames overlaps later copies (copy stream + events)
+            CK(cudaMemcpyAsync(c->in_pool, host_frames, (size_t)nframes * g.plane_bytes, cudaMemcpyHostToDevice, c->st));
+        } else {
+            for (int f = 0; f < nframes; f++)
+                CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W,
+                                     g.H, cudaMemcpyHostToDevice, c->st));
+        }
+    }
+
+    std::vector<cudaEvent_t> ev_bits(nsteps), ev_copy(nsteps), ev_me0(nsteps), ev_me1(nsteps);
+    for (size_t s = 0; s < nsteps; s++) {
+        CK(cudaEventCreateWithFlags(&ev_bits[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_copy[s], cudaEventDisableTiming));
+        CK(cudaEventCreate(&ev_me0[s]));
+        CK(cudaEventCreate(&ev_me1[s]));
+    }
+    std::vector<FrameRec> recs(nframes);
+    size_t stage_used = 0;
+    // staging arena: grow geometrically; streams are small next to the planes
+    if ((rc = ensure_pinned(c, (void**)&c->h_stage, &c->h_stage_cap, std::max((size_t)nframes * g.W * g.H, (size_t)8 << 20))) != BVC_OK)
+        return rc;
+
+    auto drain = [&](size_t s) -> int {  // host side of step s: learn sizes, enqueue the payload copies
+        CK(cudaEventSynchronize(ev_bits[s]));
+        const int par = (int)(s & 1);
+        const long long* hb = c->h_bits + s * (size_t)G * 2;
+        for (int l = 0; l < steps[s].nl; l++) {
+            FrameRec& r = recs[step_frames[s][l]];
+            r.pred_bits = hb[2 * l];
+            r.coef_bits = hb[2 * l + 1];
+            const size_t pb = (size_t)((r.pred_bits + 7) / 8), cb = (size_t)((r.coef_bits + 7) / 8);
+            if (stage_used + pb + cb + 16 > c->h_stage_cap) return fail(c, BVC_ERR_NOMEM, "stream staging arena exhausted");
+            r.pred_off = stage_used;
+            r.coef_off = stage_used + ((pb + 7) & ~(size_t)7);
+            stage_used = r.coef_off + ((cb + 7) & ~(size_t)7);
+            if (pb) CK(cudaMemcpyAsync(c->h_stage + r.pred_off, (uint8_t*)(c->d_pred_stream[par] + (size_t)l * c->pred_cap_words), pb,
+                                       cudaMemcpyDeviceToHost, c->st_copy));
+            if (cb) CK(cudaMemcpyAsync(c->h_stage + r.coef_off, (uint8_t*)(c->d_coef_stream[par] + (size_t)l * c->coef_cap_words), cb,
+                                       cudaMemcpyDeviceToHost, c->st_copy));
+        }
+        CK(cudaEventRecord(ev_copy[s], c->st_copy));
+        return BVC_OK;
+    };
+
+    for (size_t s = 0; s < nsteps; s++) {
+        const int par = (int)(s & 1);
+        // the stream buffers of this parity were last used by step s-2: its D2H must be done
+        if (s >= 2) CK(cudaStreamWaitEvent(c->st, ev_copy[s - 2], 0));
+        if ((rc = enqueue_step(c, steps[s], par, false, ev_me0[s], ev_me1[s])) != BVC_OK) return rc;
+        // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
+        if ((rc = enqueue_halfpel(c, steps[s].desc_off, steps[s].nl)) != BVC_OK) return rc;
+        CK(cudaMemcpyAsync(c->h_bits + s * (size_t)G * 2, c->d_frame_bits[par], (size_t)steps[s].nl * 2 * sizeof(long long),
+                           cudaMemcpyDeviceToHost, c->st));
+        CK(cudaEventRecord(ev_bits[s], c->st));
+        if (recon) {
+            for (int l = 0; l < steps[s].nl; l++)
+                if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]))) != BVC_OK)
+                    return rc;
+        }
+        CK(cudaStreamWaitEvent(c->st_copy, ev_bits[s], 0));
+        if (s >= 1 && (rc = drain(s - 1)) != BVC_OK) return rc;
+    }
+    if ((rc = drain(nsteps - 1)) != BVC_OK) return rc;
+    CK(cudaStreamSynchronize(c->st_copy));
+    CK(cudaStreamSynchronize(c->st));
+
+    // ---- instrumentation ----
+    c->last_me_ms = 0;
+    c->last_me_launches = 0;
+    for (size_t s = 0; s < nsteps; s++) {
+        if (!steps[s].intra) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_me0[s], ev_me1[s]) == cudaSuccess) { c->last_me_ms += ms; c->last_me_launches++; }
+        }
+        cudaEventDestroy(ev_bits[s]); cudaEventDestroy(ev_copy[s]); cudaEventDestroy(ev_me0[s]); cudaEventDestroy(ev_me1[s]);
+    }
+
+    // ---- container (encoder.py:104-121): host-side concatenation in frame order ----
+    size_t o = 0;
+    for (int f = 0; f < nframes; f++) {
+        const FrameRec& r = recs[f];
+        const size_t pb = (size_t)((r.pred_bits + 7) / 8), cb = (size_t)((r.coef_bits + 7) / 8);
+        if (pb > 0xFFFF || cb > 0xFFFFFF) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
+        if (o + 6 + pb + cb > out_cap) return fail(c, BVC_ERR_NOMEM, "output buffer too small");
+        out[o++] = (f % IP == 0) ? 1 : 0;  // PredictionMode: INTRA_FRAME = 1, INTER_FRAME = 0
+        out[o++] = (uint8_t)(pb >> 8); out[o++] = (uint8_t)pb;
+        memcpy(out + o, c->h_stage + r.pred_off, pb); o += pb;
+        out[o++] = (uint8_t)(cb >> 16); out[o++] = (uint8_t)(cb >> 8); out[o++] = (uint8_t)cb;
+        memcpy(out + o, c->h_stage + r.coef_off, cb); o += cb;
+    }
+    *out_len = o;
+    return BVC_OK;
+}
+
+extern "C" int bvc_encode_clip(bvc_ctx* c, const uint8_t* frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
+                               uint8_t* recon) {
+    if (!c || !frames) return BVC_ERR_INVALID;
+    return encode_clip_impl(c, frames, nframes, out, out_cap, out_len, recon);
+}
+extern "C" int bvc_encode_clip_resident(bvc_ctx* c, int nframes, uint8_t* out, size_t out_cap, size_t* out_len, uint8_t* recon) {
+    if (!c) return BVC_ERR_INVALID;
+    if (nframes > c->resident_frames) return fail(c, BVC_ERR_INVALID, "clip not resident: call bvc_clip_upload first");
+    return encode_clip_impl(c, nullptr, nframes, out, out_cap, out_len, recon);
+}

@@ -1,0 +1,114 @@
+// bvc_kernels.h -- host-visible launchers of the CUDA kernels (internal to libbvc_b200.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bvc_common.cuh"
+
+namespace bvc {
+
+// ---- K1/K3 motion estimation -----------------------------------------------------------------
+struct MeLane {
+    int cur_plane;                 // index of the current frame in the input pool
+    int nref;                      // references available (deque length), oldest first
+    int ref_plane[BVC_MAX_REFS];   // plane index in the reference pool (first phase plane when frac)
+};
+struct MeArgs {
+    const uint8_t* cur_base;
+    size_t cur_plane_bytes;
+    int cur_pitch;
+    const MeLane* lanes;           // device array [lanes]
+    int4* out;                     // device [lanes][nblk] = (mvx, mvy, ref, sad)
+    int W, H, bs, bw, bh, nblk;
+    int R;                         // integer search range on the (phase) planes
+    int sc;                        // 1 integer-pel, 2 half-pel MV units
+    int nphase;                    // 1 or 4
+    int Rh;                        // range in MV units (= R*sc)
+    int win_pitch, win_copy_bytes, win_lm; // filled by the launcher
+};
+struct MeTileCfg {
+    bool tiled;
+    int nb;         // blocks per CTA
+    int win_pitch;  // TMA box width in bytes
+    int rows;       // TMA box height
+    int win_lm;     // left margin: window column of x0-R inside the 16-byte aligned box
+};
+MeTileCfg me_tile_config(int bs, int R);
+cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
+                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st);
+
+// ---- K4 FastME ---------------------------------------------------------------------------------
+cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                          long long* cmp_out, cudaStream_t st);
+
+// ---- K2 half-pel phase planes ----------------------------------------------------------------
+// src: one W x H plane; dst: 4 consecutive phase planes (P00 = copy, P10 = horizontal, P01 = vertical,
+// P11 = diagonal), each W x H with the last column / row of the odd phases left 0.
+cudaError_t launch_halfpel(const uint8_t* const* src_planes, uint8_t* const* dst_planes, int nplanes, int W, int H,
+                           int pitch, size_t plane_bytes, cudaStream_t st);
+// interleave 4 phase planes into the reference's (2H x 2W) layout (drop-in / test hook)
+cudaError_t launch_halfpel_interleave(const uint8_t* phases, int W, int H, int pitch, size_t plane_bytes, uint8_t* out2x,
+                                      cudaStream_t st);
+
+// ---- K5 / K6 / K7: transform, reconstruction, intra wavefront, entropy ---------------------------
+struct FrameLane {
+    int cur_plane;                 // input pool index
+    int out_plane;                 // reference-pool plane receiving the reconstruction
+    int nref;
+    int ref_plane[BVC_MAX_REFS];
+};
+struct TqArgs {
+    const uint8_t* cur_base;
+    size_t cur_plane_bytes;
+    int cur_pitch;
+    uint8_t* ref_base;             // reference pool (pred is read from it, recon is written into it)
+    size_t ref_plane_bytes;
+    int ref_pitch;
+    const FrameLane* lanes;        // device [lanes]
+    const int4* mv;                // device [lanes][nblk] (P frames)
+    int32_t* modes;                // device [lanes][nblk] (I frames: out)
+    int32_t* isad;                 // device [lanes][nblk] (I frames: mode-decision SAD, out)
+    const int32_t* qp_rows;        // device [lanes][bh]
+    int16_t* levels;               // device [lanes][H][W] (frame layout), may be null
+    int8_t* resid_mc;              // debug planes [lanes][H][W], may be null
+    int8_t* resid_nomc;
+    uint32_t* blk_bits;            // device [lanes][nblk][blk_words] per-block coefficient bit strings
+    int32_t* blk_nbits;            // device [lanes][nblk]
+    int blk_words;                 // words reserved per block in blk_bits
+    int W, H, bs, bw, bh, nblk;
+    int frac;                      // MVs in half-pel units, pred from phase planes
+    int multi_ref;                 // nRefFrames > 1: pred from refs[mv.ref] else refs[0]
+    int* progress;                 // I frames: device [lanes][bh] wavefront progress counters (zeroed)
+};
+cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st);
+cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st);
+
+// Block-level hook: residual (int16) + pred (int16) -> level/recon/idct/coef, nblocks blocks of bs x bs
+int tq_blk_words(int bs);
+cudaError_t launch_tq_blocks(const int16_t* res, const int16_t* pred, int nblocks, int bs, int qp, int16_t* level,
+                             uint8_t* recon, double* idct, double* coef, cudaStream_t st);
+
+// ---- K7b: stream assembly ----------------------------------------------------------------------
+struct PackArgs {
+    const int4* mv;                // P
+    const int32_t* modes;          // I
+    const int32_t* qp_rows;        // [lanes][bh]
+    const uint32_t* blk_bits;
+    const int32_t* blk_nbits;
+    int blk_words;
+    long long* coef_off;             // device [lanes][nblk+1]  exclusive bit offsets (out)
+    uint32_t* coef_stream;         // device [lanes][coef_cap_words]
+    uint32_t* pred_stream;         // device [lanes][pred_cap_words]
+    long long* frame_bits;           // device [lanes][2] = (pred_bits, coef_bits) (out)
+    long long* row_bits;             // device [lanes][bh] (out) bits_per_row
+    long long* pred_row_off;         // device [lanes][bh+1] scratch: prediction-stream offset of every row start
+    size_t coef_cap_words, pred_cap_words;
+    int bw, bh, nblk;
+    int base_qp;
+    int intra;                     // 1: modes, 0: motion vectors
+    int with_ref;                  // nRefFrames > 1: code the reference index difference
+};
+cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
+
+}  // namespace bvc

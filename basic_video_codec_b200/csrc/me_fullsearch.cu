@@ -1,0 +1,355 @@
+// me_fullsearch.cu -- K1/K3: exhaustive block-matching motion estimation (integer-pel and half-pel),
+// multi-reference, with the reference's exact tie-break.
+//
+// Replaces find_lowest_mae_block + get_ref_block_at_mv + is_out_of_range + common.mae
+// (reference encoder/block_predictor.py:61-143, common.py:43-45).
+//
+// Winner rule (block_predictor.py:76-88): minimum SAD; among equal SAD the smaller |mvx|+|mvy|;
+// among those the first in scan order ref ascending, mv_y ascending, mv_x ascending.  Candidates whose
+// block leaves the plane are skipped (no clamping / padding).  With fracMeEnabled the search runs
+// over +-2r half-pel positions of the 2x interpolated plane, sampled with stride 2
+// (block_predictor.py:65-66,103-111): we keep the 2x plane as four W x H *phase planes*
+// (even/odd column x even/odd row), so a half-pel candidate (mvx,mvy) is the integer candidate
+// (mvx>>1, mvy>>1) on phase plane (mvx&1, mvy&1) and the same kernel serves both modes.
+//
+// Kernel design (sm_100a, HBM is irrelevant here: ~2000 byte-ops per byte read):
+//   * bound by the ALU pipe: VABSDIFF4.U8.ACC issues at 16 lanes/clk/SMSP (measured,
+//     profiles/microbench) => 256 pixel-absdiffs/clk/SM;  PRMT/SHF share that pipe, so byte
+//     re-alignment must not be in the inner loop.
+//   * one CTA = NB horizontally adjacent blocks.  The search window (NB*BS+2R) x (BS+2R) is staged
+//     in shared memory by one TMA tile load (out-of-frame bytes are zero-filled by the TMA unit; the
+//     box origin must be 16-byte aligned -- a byte-granular origin raises an illegal-instruction fault on
+//     sm_100a, profiles/microbench/tma_probe.cu -- so the box starts at the aligned column at or left of
+//     x0-R).  The CTA then derives three byte-shifted copies (+1,+2,+3) with funnel shifts, once per
+//     window, so every candidate column reads naturally aligned 32-bit words and the inner loop has
+//     no PRMT/SHF at all (they would steal VABSDIFF4 issue slots).
+//   * one thread = one candidate column mx of one block; it slides down all 2R+1 vertical offsets.
+//     The current block lives in registers (BS*BS/4 words); each window row is loaded once (BS/4
+//     LDS.32) and feeds BS candidates (BS*BS/4 VABSDIFF4) => LDS:VABSDIFF4 = 1:BS.  BS accumulators
+//     rotate through compile-time slots; the row loop is unrolled BS deep in three variants (ramp-up,
+//     steady, ramp-down) so no candidate outside [-R,R] is ever evaluated: executed VABSDIFF4 count
+//     equals the algorithmic count exactly.
+//   * argmin: per thread a strict-less scan on (SAD<<9 | L1); per pass merged with the full 64-bit
+//     key (SAD, L1, ref, mvy, mvx); per block a shared-memory 64-bit atomicMin.
+#include "bvc_common.cuh"
+#include "bvc_kernels.h"
+
+namespace bvc {
+
+namespace {
+
+struct PassInfo {
+    int R;        // integer range on the (phase) plane
+    int sc;       // 1 = integer-pel, 2 = half-pel units
+    int px, py;   // phase (0/1)
+    int Rh;       // range in output MV units (R*sc)
+};
+
+template <int BS>
+struct CurBlock {
+    static constexpr int WPR = BS / 4;  // words per row
+    uint32_t w[BS][WPR];
+};
+
+template <int BS>
+__device__ __forceinline__ void load_cur(CurBlock<BS>& c, const uint8_t* p, int pitch) {
+#pragma unroll
+    for (int r = 0; r < BS; r++) {
+        const uint8_t* row = p + (size_t)r * pitch;
+        if constexpr (BS == 16) {
+            uint4 v = *reinterpret_cast<const uint4*>(row);
+            c.w[r][0] = v.x; c.w[r][1] = v.y; c.w[r][2] = v.z; c.w[r][3] = v.w;
+        } else if constexpr (BS == 8) {
+            uint2 v = *reinterpret_cast<const uint2*>(row);
+            c.w[r][0] = v.x; c.w[r][1] = v.y;
+        } else {
+            c.w[r][0] = *reinterpret_cast<const uint32_t*>(row);
+        }
+    }
+}
+
+enum { BODY_FIRST = 0, BODY_MID = 1, BODY_LAST = 2, BODY_ONLY = 3 };
+
+// One unrolled body of BS window rows.  `rowp` points at this thread's first word of window row
+// body*BS; `wpitch` is the window pitch in words.  mb = m of the candidate completing at t = 0 minus..:
+// candidate completing after row t has m = mbase + t.
+template <int BS, int MODE>
+__device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp,
+                                        int wpitch, int mbase, int mlo, int mhi, int mvy0, int sc, uint32_t absmx,
+                                        uint32_t& best, uint32_t& bestm) {
+    constexpr int WPR = BS / 4;
+#pragma unroll
+    for (int t = 0; t < BS; t++) {
+        uint32_t w[WPR];
+#pragma unroll
+        for (int j = 0; j < WPR; j++) w[j] = rowp[t * wpitch + j];
+#pragma unroll
+        for (int wi = 0; wi < WPR; wi++) {
+#pragma unroll
+            for (int j = 0; j < BS; j++) {
+                // candidate offset m = y - j; FIRST body: m >= 0 <=> j <= t; LAST body: m <= 2R <=> j >= t
+                bool on = true;
+                if (MODE == BODY_FIRST) on = (j <= t);
+                if (MODE == BODY_LAST) on = (j >= t);
+                if (on) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int slot = (t - j) & (BS - 1);
+                    // first word of a fresh candidate (j == 0, wi == 0) starts from zero: no reset needed
+                    acc[slot] = sad4(w[wi], cur.w[j][wi], (j == 0 && wi == 0) ? 0u : acc[slot]);
+                }
+            }
+        }
+        // the candidate whose last row (j = BS-1) was just added is complete
+        const bool completes = (MODE != BODY_FIRST) || (t == BS - 1);
+        if (completes) {
+            const int slot = (t + 1) & (BS - 1);
+            const int m = mbase + t;
+            const int mvy = mvy0 + sc * m;
+            const uint32_t key = (acc[slot] << 9) + absmx + (uint32_t)abs(mvy);
+            if (m >= mlo && m <= mhi && key < best) { best = key; bestm = (uint32_t)m; }
+        }
+    }
+}
+
+// Tiled full-search kernel.  grid = (ceil(bw/NB), bh, lanes).  Dynamic smem: 4 shifted window copies.
+template <int BS, int NB>
+__global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ unsigned long long sbest[NB];
+
+    const int tid = threadIdx.x;
+    const int R = a.R;
+    const int ncx = 2 * R + 1;
+    const int rows = BS + 2 * R;
+    const int WW = a.win_pitch;               // bytes, multiple of 16
+    const int copy_bytes = a.win_copy_bytes;  // WW*rows rounded up to 128
+    const int bx0 = blockIdx.x * NB;
+    const int by = blockIdx.y;
+    const int lane = blockIdx.z;
+    const MeLane& L = a.lanes[lane];
+
+    const int b = tid / ncx;
+    const int cxi = tid - b * ncx;
+    const bool active = (b < NB) && (bx0 + b < a.bw);
+    const int ox = (bx0 + b) * BS, oy = by * BS;
+    const int dx = cxi - R;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < NB) sbest[tid] = ~0ull;
+
+    CurBlock<BS> cur;
+    if (active) load_cur<BS>(cur, a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)oy * a.cur_pitch + ox, a.cur_pitch);
+    __syncthreads();
+
+    // this thread's window column (left edge of the candidate) and the aligned copy it reads
+    const int X = a.win_lm + b * BS + cxi;
+    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_bytes) + (X >> 2);
+    const int wpitch = WW >> 2;
+
+    uint32_t best_hi = 0xFFFFFFFFu, best_lo = 0xFFFFFFFFu;
+    uint32_t parity = 0;
+    const int nmid = (2 * R) / BS - 1;
+
+    for (int r = 0; r < L.nref; r++) {
+        for (int ph = 0; ph < a.nphase; ph++) {
+            const int px = ph & 1, py = ph >> 1;
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
+                // box origin: 16-byte aligned column (bx0*BS - R - win_lm), rows <= 256
+                tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, oy - R, L.ref_plane[r] + ph);
+            }
+            mbar_wait(&bar, parity);
+            parity ^= 1u;
+            {   // byte-shifted copies 1..3 of the window
+                const uint32_t* c0 = reinterpret_cast<const uint32_t*>(smem);
+                uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_bytes);
+                uint32_t* c2 = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)copy_bytes);
+                uint32_t* c3 = reinterpret_cast<uint32_t*>(smem + 3 * (size_t)copy_bytes);
+                const int nw = (WW * rows) >> 2;
+                for (int w = tid; w < nw; w += blockDim.x) {
+                    const uint32_t lo = c0[w], hi = c0[w + 1];
+                    c1[w] = __funnelshift_r(lo, hi, 8);
+                    c2[w] = __funnelshift_r(lo, hi, 16);
+                    c3[w] = __funnelshift_r(lo, hi, 24);
+                }
+            }
+            __syncthreads();
+
+            if (active) {
+                // vertical validity interval in m = dy + R; horizontal validity is per thread
+                const int mlo = max(0, R - oy);
+                const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                const int mvx = a.sc * dx + px;
+                const bool xvalid = (ox + dx >= 0) && (ox + dx + BS <= a.W - px) && (dx <= R - px);
+                if (xvalid) {
+                    const uint32_t absmx = (uint32_t)abs(mvx);
+                    const int mvy0 = py - a.sc * R;  // mvy = mvy0 + sc*m
+                    uint32_t acc[BS];
+#pragma unroll
+                    for (int i = 0; i < BS; i++) acc[i] = 0;
+                    uint32_t best = 0xFFFFFFFFu, bestm = 0;
+                    const uint32_t* rowp = colp;
+                    if (nmid >= 0) {
+                        me_body<BS, BODY_FIRST>(cur, acc, rowp, wpitch, -(BS - 1), mlo, mhi, mvy0, a.sc, absmx, best, bestm);
+                        rowp += BS * wpitch;
+                        int mbase = 1;
+                        for (int i = 0; i < nmid; i++) {
+                            me_body<BS, BODY_MID>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, absmx, best, bestm);
+                            rowp += BS * wpitch;
+                            mbase += BS;
+                        }
+                        me_body<BS, BODY_LAST>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, absmx, best, bestm);
+                    }
+                    if (best != 0xFFFFFFFFu) {
+                        const int mvy = mvy0 + a.sc * (int)bestm;
+                        const uint32_t lo = ((uint32_t)r << 20) | ((uint32_t)(mvy + a.Rh) << 10) | (uint32_t)(mvx + a.Rh);
+                        if (best < best_hi || (best == best_hi && lo < best_lo)) { best_hi = best; best_lo = lo; }
+                    }
+                }
+            }
+            __syncthreads();  // everyone is done with the window before the next TMA overwrites it
+        }
+    }
+    if (active && best_hi != 0xFFFFFFFFu)
+        atomicMin(&sbest[b], ((unsigned long long)best_hi << 32) | best_lo);
+    __syncthreads();
+    if (tid < NB && bx0 + tid < a.bw) {
+        const unsigned long long k = sbest[tid];
+        const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+        int4 o;
+        o.x = (int)(lo & 1023u) - a.Rh;
+        o.y = (int)((lo >> 10) & 1023u) - a.Rh;
+        o.z = (int)(lo >> 20);
+        o.w = (int)(hi >> 9);
+        a.out[(size_t)lane * a.nblk + (size_t)by * a.bw + bx0 + tid] = o;
+    }
+}
+
+// Generic fallback for (block, range) pairs the tiled kernel does not cover (2R not a multiple of
+// BS, BS = 2/32, ...): one CTA per block, threads stride over candidates, bytes straight from L1/L2.
+// Same key and tie-break; correctness path, not a performance path.
+__global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch) {
+    __shared__ unsigned long long sbest;
+    const int bs = a.bs;
+    const int bx = blockIdx.x, by = blockIdx.y, lane = blockIdx.z;
+    const MeLane& L = a.lanes[lane];
+    const int ox = bx * bs, oy = by * bs;
+    if (threadIdx.x == 0) sbest = ~0ull;
+    __syncthreads();
+    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)oy * a.cur_pitch + ox;
+    const int R = a.R, n1 = 2 * R + 1;
+    unsigned long long best = ~0ull;
+    const int per_plane = n1 * n1;
+    const int total = L.nref * a.nphase * per_plane;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+        const int rp = c / per_plane, q = c - rp * per_plane;
+        const int r = rp / a.nphase, ph = rp - r * a.nphase;
+        const int px = ph & 1, py = ph >> 1;
+        const int dy = q / n1 - R, dx = q - (q / n1) * n1 - R;
+        if (ox + dx < 0 || oy + dy < 0 || ox + dx + bs > a.W - px || oy + dy + bs > a.H - py || dx > R - px || dy > R - py) continue;
+        const uint8_t* ref = ref_base + (size_t)(L.ref_plane[r] + ph) * ref_plane_bytes + (size_t)(oy + dy) * ref_pitch + (ox + dx);
+        uint32_t s = 0;
+        for (int y = 0; y < bs; y++)
+            for (int x = 0; x < bs; x++) s += (uint32_t)abs((int)cur[(size_t)y * a.cur_pitch + x] - (int)ref[(size_t)y * ref_pitch + x]);
+        const int mvx = a.sc * dx + px, mvy = a.sc * dy + py;
+        const uint32_t hi = (s << 9) + (uint32_t)(abs(mvx) + abs(mvy));
+        const uint32_t lo = ((uint32_t)r << 20) | ((uint32_t)(mvy + a.Rh) << 10) | (uint32_t)(mvx + a.Rh);
+        const unsigned long long k = ((unsigned long long)hi << 32) | lo;
+        if (k < best) best = k;
+    }
+    atomicMin(&sbest, best);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t hi = (uint32_t)(sbest >> 32), lo = (uint32_t)sbest;
+        int4 o;
+        o.x = (int)(lo & 1023u) - a.Rh;
+        o.y = (int)((lo >> 10) & 1023u) - a.Rh;
+        o.z = (int)(lo >> 20);
+        o.w = (int)(hi >> 9);
+        a.out[(size_t)lane * a.nblk + (size_t)by * a.bw + bx] = o;
+    }
+}
+
+template <int BS, int NB>
+cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+    const int R = a.R;
+    const int ncx = 2 * R + 1;
+    const int threads = ((NB * ncx + 31) / 32) * 32;
+    const MeTileCfg cfg = me_tile_config(BS, R);
+    a.win_pitch = cfg.win_pitch;
+    a.win_lm = cfg.win_lm;
+    a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
+    const size_t smem = 4 * (size_t)a.win_copy_bytes + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    dim3 grid((a.bw + NB - 1) / NB, a.bh, lanes);
+    me_tiled_kernel<BS, NB><<<grid, threads, smem, st>>>(map, a);
+    return cudaGetLastError();
+}
+
+int pick_nb(int bs, int R) {
+    const int ncx = 2 * R + 1;
+    // as many blocks per CTA as fit 544 threads / 256-byte TMA boxes / ~100 KB of windows, so that
+    // two CTAs are resident per SM and one CTA's TMA wait hides behind the other's arithmetic.
+    // NB*BS is kept a multiple of 16 so the left margin of the aligned TMA box is the same for every CTA
+    const int cand16[] = {4, 2, 1}, cand8[] = {8, 4, 2}, cand4[] = {8, 4, 4};
+    const int* c = bs == 16 ? cand16 : bs == 8 ? cand8 : cand4;
+    const int n = 3;
+    const int lm = (16 - R % 16) % 16;
+    for (int i = 0; i < n; i++) {
+        const int nb = c[i];
+        const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
+        if (nb * ncx <= 544 && pitch <= 256 && 4 * pitch * (bs + 2 * R) <= 110 * 1024) return nb;
+    }
+    return 0;
+}
+
+}  // namespace
+
+MeTileCfg me_tile_config(int bs, int R) {
+    MeTileCfg c{false, 0, 0, 0, 0};
+    if (!(bs == 4 || bs == 8 || bs == 16)) return c;
+    if (R < 1 || (2 * R) % bs != 0 || 2 * R < bs) return c;
+    if (bs + 2 * R > 256) return c;  // TMA box rows
+    const int nb = pick_nb(bs, R);
+    if (nb == 0) return c;
+    c.tiled = true;
+    c.nb = nb;
+    c.win_lm = (16 - R % 16) % 16;
+    c.win_pitch = ((c.win_lm + nb * bs + 2 * R + 15) / 16) * 16;
+    c.rows = bs + 2 * R;
+    return c;
+}
+
+cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
+                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st) {
+    MeArgs a = args;
+    const MeTileCfg cfg = me_tile_config(a.bs, a.R);
+    if (cfg.tiled && ref_map) {
+        if (a.bs == 16) {
+            if (cfg.nb == 4) return launch_tiled<16, 4>(*ref_map, a, lanes, st);
+            if (cfg.nb == 2) return launch_tiled<16, 2>(*ref_map, a, lanes, st);
+            return launch_tiled<16, 1>(*ref_map, a, lanes, st);
+        } else if (a.bs == 8) {
+            if (cfg.nb == 8) return launch_tiled<8, 8>(*ref_map, a, lanes, st);
+            if (cfg.nb == 4) return launch_tiled<8, 4>(*ref_map, a, lanes, st);
+            return launch_tiled<8, 2>(*ref_map, a, lanes, st);
+        } else {
+            if (cfg.nb == 8) return launch_tiled<4, 8>(*ref_map, a, lanes, st);
+            return launch_tiled<4, 4>(*ref_map, a, lanes, st);
+        }
+    }
+    dim3 grid(a.bw, a.bh, lanes);
+    me_generic_kernel<<<grid, 256, 0, st>>>(a, ref_base, ref_plane_bytes, ref_pitch);
+    return cudaGetLastError();
+}
+
+}  // namespace bvc

@@ -1,0 +1,189 @@
+// pack.cu -- K7b: assemble the two per-frame bit streams in raster order.
+//
+//   prediction stream: per block row EG(row_qp - base_qp), then per block the differential
+//       motion vector EG(dmvx) EG(dmvy) [EG(dref)] chained in raster order from (0,0,0)
+//       (reference encoder/PFrame.py:136-163) or EG(mode) (encoder/IFrame.py:116-130);
+//   coefficient stream: the per-block strings produced by the transform kernels, concatenated
+//       (encoder/Frame.py:61-75).
+// Streams are MSB-first bit strings, zero padded to whole bytes (bitarray.tobytes()).
+//
+// pack_scan_kernel: one CTA per frame.  Exclusive scans of the per-block bit counts (both streams),
+//   per-row bit totals (bits_per_row, PFrame.py:76-83), zeroing of the used part of the output
+//   streams and emission of the (small) prediction stream.
+// pack_emit_kernel: one warp per block, funnel-shifts the block's words to its bit offset and ORs
+//   them into the coefficient stream.
+#include "bvc_kernels.h"
+
+namespace bvc {
+namespace {
+
+constexpr int SCAN_THREADS = 1024;
+
+__device__ __forceinline__ void put_bits_global_be(uint32_t* stream, long long off, unsigned long long code, int len) {
+    const unsigned long long V = code << (64 - len);
+    const int sh = (int)(off & 31);
+    const long long wi = off >> 5;
+    const uint32_t hi = (uint32_t)(V >> 32), lo = (uint32_t)V;
+    const uint32_t w0 = hi >> sh;
+    const uint32_t w1 = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
+    const uint32_t w2 = sh ? (lo << (32 - sh)) : 0u;
+    // store byte-swapped so that memory order is the MSB-first byte stream
+    if (w0) atomicOr(&stream[wi], __byte_perm(w0, 0, 0x0123));
+    if (w1) atomicOr(&stream[wi + 1], __byte_perm(w1, 0, 0x0123));
+    if (w2) atomicOr(&stream[wi + 2], __byte_perm(w2, 0, 0x0123));
+}
+
+// block-wide exclusive scan of one 64-bit value per thread; returns the exclusive prefix, total in *tot
+__device__ __forceinline__ long long block_exscan(long long v, long long* warp_sums, long long* tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+        long long wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            long long o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        warp_sums[lane] = wi - w;  // exclusive
+        if (lane == 31) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    const long long res = warp_sums[warp] + incl - v;
+    *tot = warp_sums[32];
+    __syncthreads();
+    return res;
+}
+
+struct PredCode {
+    unsigned long long code;  // up to 57 bits of motion-vector / mode symbols
+    int len;
+    uint32_t qcode;           // row-start qp symbol
+    int qlen;
+};
+
+__device__ __forceinline__ PredCode pred_code(const PackArgs& a, int fl, int b) {
+    PredCode pc;
+    pc.qcode = 0;
+    pc.qlen = 0;
+    const int bx = b % a.bw, by = b / a.bw;
+    if (bx == 0) {  // EG(rc_qp - base qp) opens every block row (PFrame.py:146-147, IFrame.py:120-121)
+        pc.qcode = eg_code(a.qp_rows[(size_t)fl * a.bh + by] - a.base_qp);
+        pc.qlen = eg_len_of_code(pc.qcode);
+    }
+    if (a.intra) {
+        const uint32_t e = eg_code(a.modes[(size_t)fl * a.nblk + b]);
+        pc.code = e;
+        pc.len = eg_len_of_code(e);
+    } else {
+        const int4 m = a.mv[(size_t)fl * a.nblk + b];
+        int4 p = make_int4(0, 0, 0, 0);
+        if (b > 0) p = a.mv[(size_t)fl * a.nblk + b - 1];  // previous block in raster order (PFrame.py:140-144,163)
+        uint32_t e = eg_code(m.x - p.x);
+        int l = eg_len_of_code(e);
+        pc.code = e;
+        pc.len = l;
+        e = eg_code(m.y - p.y);
+        l = eg_len_of_code(e);
+        pc.code = (pc.code << l) | e;
+        pc.len += l;
+        if (a.with_ref) {
+            e = eg_code(m.z - p.z);
+            l = eg_len_of_code(e);
+            pc.code = (pc.code << l) | e;
+            pc.len += l;
+        }
+    }
+    return pc;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
+    __shared__ long long warp_sums[33];
+    const int fl = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int chunk = (a.nblk + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int b0 = tid * chunk, b1 = min(a.nblk, b0 + chunk);
+    const int32_t* nb = a.blk_nbits + (size_t)fl * a.nblk;
+    long long* coff = a.coef_off + (size_t)fl * (a.nblk + 1);
+    uint32_t* cstream = a.coef_stream + (size_t)fl * a.coef_cap_words;
+    uint32_t* pstream = a.pred_stream + (size_t)fl * a.pred_cap_words;
+
+    // ---- coefficient stream offsets ----
+    long long csum = 0;
+    for (int b = b0; b < b1; b++) csum += nb[b];
+    long long ctot;
+    long long cpre = block_exscan(csum, warp_sums, &ctot);
+    for (int b = b0; b < b1; b++) { coff[b] = cpre; cpre += nb[b]; }
+    if (tid == 0) coff[a.nblk] = ctot;
+
+    // ---- prediction stream lengths ----
+    long long psum = 0;
+    for (int b = b0; b < b1; b++) { PredCode pc = pred_code(a, fl, b); psum += pc.len + pc.qlen; }
+    long long ptot;
+    long long ppre = block_exscan(psum, warp_sums, &ptot);
+    if (tid == 0) { a.frame_bits[2 * fl] = ptot; a.frame_bits[2 * fl + 1] = ctot; }
+
+    // ---- zero the used part of both streams (+2 words of slack for the 3-word OR window) ----
+    const long long cw = min((long long)a.coef_cap_words, ((ctot + 31) >> 5) + 2);
+    const long long pw = min((long long)a.pred_cap_words, ((ptot + 31) >> 5) + 2);
+    for (long long w = tid; w < cw; w += SCAN_THREADS) cstream[w] = 0;
+    for (long long w = tid; w < pw; w += SCAN_THREADS) pstream[w] = 0;
+    __syncthreads();
+
+    // ---- emit prediction stream; remember where every block row starts ----
+    long long* prow = a.pred_row_off + (size_t)fl * (a.bh + 1);
+    long long off = ppre;
+    for (int b = b0; b < b1; b++) {
+        PredCode pc = pred_code(a, fl, b);
+        if (b % a.bw == 0) prow[b / a.bw] = off;
+        if (pc.qlen) { put_bits_global_be(pstream, off, pc.qcode, pc.qlen); off += pc.qlen; }
+        put_bits_global_be(pstream, off, pc.code, pc.len);
+        off += pc.len;
+    }
+    if (tid == 0) prow[a.bh] = ptot;
+    __syncthreads();
+    // bits_per_row (PFrame.py:76-83): growth of both streams while the row was coded
+    for (int r = tid; r < a.bh; r += SCAN_THREADS)
+        a.row_bits[(size_t)fl * a.bh + r] = (prow[r + 1] - prow[r]) + (coff[(size_t)(r + 1) * a.bw] - coff[(size_t)r * a.bw]);
+}
+
+constexpr int EMIT_WARPS = 8;
+__global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) {
+    const int fl = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * EMIT_WARPS + warp;
+    if (b >= a.nblk) return;
+    const int nbits = a.blk_nbits[(size_t)fl * a.nblk + b];
+    const long long D = a.coef_off[(size_t)fl * (a.nblk + 1) + b];
+    const uint32_t* src = a.blk_bits + ((size_t)fl * a.nblk + b) * a.blk_words;
+    uint32_t* dst = a.coef_stream + (size_t)fl * a.coef_cap_words;
+    const int n = (nbits + 31) >> 5;
+    const int sh = (int)(D & 31);
+    const long long w0 = D >> 5;
+    for (int j = lane; j <= n; j += 32) {
+        const uint32_t lo = (j < n) ? src[j] : 0u;
+        const uint32_t hi = (j > 0) ? src[j - 1] : 0u;
+        const uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
+        if (v) atomicOr(&dst[w0 + j], __byte_perm(v, 0, 0x0123));
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st) {
+    pack_scan_kernel<<<lanes, SCAN_THREADS, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.nblk + EMIT_WARPS - 1) / EMIT_WARPS, lanes);
+    pack_emit_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace bvc

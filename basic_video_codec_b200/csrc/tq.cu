@@ -1,0 +1,289 @@
+// tq.cu -- K5 (P-frame residual/transform/reconstruct), K6 (I-frame intra wavefront) and the per-block
+// half of K7 (entropy coding of the quantised levels), fused so a block's residual, coefficients and
+// levels never round-trip HBM before they are coded.
+//
+// Replaces PFrame.process_block / generate_residual_block / find_mv_predicted_block
+// (reference encoder/PFrame.py:99-125,230-249), IFrame.process_block + intra predictors
+// (encoder/IFrame.py:184-231), apply_dct_and_quantization / reconstruct_block (encoder/Frame.py:190-202)
+// and the per-block part of entropy_encode_dct_coffs_row (encoder/Frame.py:61-75).
+#include "bvc_kernels.h"
+#include "tq_device.cuh"
+
+namespace bvc {
+namespace {
+
+constexpr int TQ_WARPS = 4;
+
+template <int BS>
+struct TqCtaSmem {
+    WarpTile<BS> w[TQ_WARPS];
+    uint8_t zz[BS * BS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// P frames: every block independent.  grid = (ceil(nblk / (TQ_WARPS*NBW)), lanes)
+template <int BS>
+__global__ void __launch_bounds__(TQ_WARPS * 32) tq_pframe_kernel(TqArgs a) {
+    constexpr int NBW = 32 / BS;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    build_zigzag<BS>(sm.zz, threadIdx.x, blockDim.x);
+    __syncthreads();
+    WarpTile<BS>& t = sm.w[warp];
+    const int fl = blockIdx.y;
+    const FrameLane& L = a.lanes[fl];
+    const int q = lane / BS, x = lane % BS;
+    const int b = (blockIdx.x * TQ_WARPS + warp) * NBW + q;
+    const bool valid = b < a.nblk;
+    const int bb = valid ? b : a.nblk - 1;
+    const int bx = bb % a.bw, by = bb / a.bw;
+    const int ox = bx * BS, oy = by * BS;
+
+    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(oy + x) * a.cur_pitch + ox;
+    const int4 mv = a.mv[(size_t)fl * a.nblk + bb];
+    // find_mv_predicted_block PFrame.py:230-244: refs[mv[2]] only when more than one reference is present
+    const int k = (L.nref > 1) ? mv.z : 0;
+    int plane = L.ref_plane[k];
+    int dx = mv.x, dy = mv.y;
+    if (a.frac) {  // half-pel MV = integer offset on one of the four phase planes
+        plane += (mv.x & 1) | ((mv.y & 1) << 1);
+        dx = mv.x >> 1;
+        dy = mv.y >> 1;
+    }
+    const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(oy + dy + x) * a.ref_pitch + (ox + dx);
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+        t.cur[q][x][i] = cur[i];
+        t.pred[q][x][i] = pr[i];
+    }
+    if (a.resid_nomc && valid) {
+        // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
+        const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(oy + x) * a.ref_pitch + ox;
+        int8_t* d = a.resid_nomc + ((size_t)fl * a.H + oy + x) * a.W + ox;
+#pragma unroll
+        for (int i = 0; i < BS; i++) d[i] = (int8_t)((int)cur[i] - (int)r0[i]);
+    }
+    __syncwarp();
+
+    TqOut o;
+    o.levels = a.levels ? a.levels + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+    o.lev_pitch = a.W;
+    o.recon = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes + (size_t)oy * a.ref_pitch + ox;
+    o.rec_pitch = a.ref_pitch;
+    o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+    o.resid_pitch = a.W;
+    o.idct_out = nullptr;
+    o.coef_out = nullptr;
+    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
+    tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, false);
+
+    // entropy-code the warp's blocks one after the other
+    for (int qq = 0; qq < NBW; qq++) {
+        const int b2 = (blockIdx.x * TQ_WARPS + warp) * NBW + qq;
+        if (b2 >= a.nblk) break;
+        uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b2) * a.blk_words;
+        const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], sm.zz, t.bits, lane, gout);
+        if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b2] = nb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// I frames: block (bx,by) needs the reconstructed right column of (bx-1,by) and bottom row of
+// (bx,by-1) (IFrame.py:184-213) => anti-diagonal wavefront.  One warp (= one CTA) walks one block row
+// of NBW *different frames* (lanes) left to right; rows are chained through per-row progress counters
+// in global memory (release/acquire), row r trailing row r-1 by one block.
+// grid = (bh * ceil(lanes/NBW)), ordered row-major so producers are dispatched before consumers.
+template <int BS>
+__global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
+    constexpr int NBW = 32 / BS;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    struct ISmem {
+        WarpTile<BS> t;
+        uint8_t zz[BS * BS];
+        uint8_t left[NBW][BS];
+        uint8_t top[NBW][BS];
+    };
+    ISmem& sm = *reinterpret_cast<ISmem*>(smraw);
+    const int lane = threadIdx.x;
+    build_zigzag<BS>(sm.zz, lane, 32);
+    __syncwarp();
+    const int ngrp = (lanes + NBW - 1) / NBW;
+    const int by = blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
+    const int q = lane / BS, x = lane % BS;
+    const int fl_raw = grp * NBW + q;
+    const bool valid = fl_raw < lanes;
+    const int fl = valid ? fl_raw : lanes - 1;
+    const FrameLane& L = a.lanes[fl];
+    const int oy = by * BS;
+    WarpTile<BS>& t = sm.t;
+    uint8_t* recon_plane = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes;
+    const uint8_t* cur_plane = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
+    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
+    volatile int* prog_up = (by > 0) ? a.progress + (size_t)fl * a.bh + (by - 1) : nullptr;
+    int* prog_me = a.progress + (size_t)fl * a.bh + by;
+
+    for (int bx = 0; bx < a.bw; bx++) {
+        const int ox = bx * BS;
+        // wait until the block above is reconstructed
+        if (by > 0 && valid && x == 0) {
+            while (*prog_up < bx + 1) { __nanosleep(20); }
+        }
+        __syncwarp();
+        __threadfence();
+        // neighbours (bypass L1: lines of the plane are being written by other SMs)
+        const int lv = (ox > 0) ? (int)__ldcg(recon_plane + (size_t)(oy + x) * a.ref_pitch + ox - 1) : 128;
+        const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
+        sm.left[q][x] = (uint8_t)lv;
+        sm.top[q][x] = (uint8_t)tv;
+        const uint8_t* cur = cur_plane + (size_t)(oy + x) * a.cur_pitch + ox;
+#pragma unroll
+        for (int i = 0; i < BS; i++) t.cur[q][x][i] = cur[i];
+        __syncwarp();
+        // mode decision, IFrame.py:184-195.  In-frame predictors are uint8, so cur - pred wraps mod 256
+        // (:189-190); border predictors are int64 128, a true absolute difference.
+        int sh = 0, sv = 0;
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+            const int ch = t.cur[q][i][x];  // column x against left[x]  (mode 0: pred[r][c] = left[c])
+            sh += (ox > 0) ? ((ch - lv) & 255) : abs(ch - 128);
+            const int cv = t.cur[q][x][i];  // row x against top[x]      (mode 1: pred[r][c] = top[r])
+            sv += (oy > 0) ? ((cv - tv) & 255) : abs(cv - 128);
+        }
+#pragma unroll
+        for (int d = 1; d < BS; d <<= 1) {
+            sh += __shfl_xor_sync(0xffffffffu, sh, d);
+            sv += __shfl_xor_sync(0xffffffffu, sv, d);
+        }
+        const int mode = (sh < sv) ? 0 : 1;  // tie -> vertical, IFrame.py:192-195
+#pragma unroll
+        for (int i = 0; i < BS; i++) t.pred[q][x][i] = mode == 0 ? sm.left[q][i] : (uint8_t)tv;
+        if (valid && x == 0) {
+            a.modes[(size_t)fl * a.nblk + by * a.bw + bx] = mode;
+            a.isad[(size_t)fl * a.nblk + by * a.bw + bx] = mode == 0 ? sh : sv;
+        }
+        __syncwarp();
+
+        TqOut o;
+        o.levels = a.levels ? a.levels + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+        o.lev_pitch = a.W;
+        o.recon = recon_plane + (size_t)oy * a.ref_pitch + ox;
+        o.rec_pitch = a.ref_pitch;
+        o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+        o.resid_pitch = a.W;
+        o.idct_out = nullptr;
+        o.coef_out = nullptr;
+        tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, true);
+        // publish: reconstruction of (bx,by) is visible before the counter moves
+        __threadfence();
+        __syncwarp();
+        if (valid && x == 0) atomicExch(prog_me, bx + 1);
+
+        for (int qq = 0; qq < NBW; qq++) {
+            const int f2 = grp * NBW + qq;
+            if (f2 >= lanes) break;
+            const int b2 = by * a.bw + bx;
+            uint32_t* gout = a.blk_bits + ((size_t)f2 * a.nblk + b2) * a.blk_words;
+            const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], sm.zz, t.bits, lane, gout);
+            if (lane == 0) a.blk_nbits[(size_t)f2 * a.nblk + b2] = nb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-level test hook: dense int16 residual / pred blocks.
+template <int BS>
+__global__ void __launch_bounds__(TQ_WARPS * 32) tq_blocks_kernel(const int16_t* res, const int16_t* pred, int nblocks, int qp,
+                                                                 int16_t* level, uint8_t* recon, double* idct, double* coef) {
+    constexpr int NBW = 32 / BS;
+    extern __shared__ __align__(16) uint8_t smraw[];
+    TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpTile<BS>& t = sm.w[warp];
+    const int q = lane / BS;
+    const int b = (blockIdx.x * TQ_WARPS + warp) * NBW + q;
+    const bool valid = b < nblocks;
+    const int bb = valid ? b : nblocks - 1;
+    TqOut o;
+    o.levels = level + (size_t)bb * BS * BS;
+    o.lev_pitch = BS;
+    o.recon = recon + (size_t)bb * BS * BS;
+    o.rec_pitch = BS;
+    o.resid_mc = nullptr;
+    o.resid_pitch = 0;
+    o.idct_out = idct ? idct + (size_t)bb * BS * BS : nullptr;
+    o.coef_out = coef ? coef + (size_t)bb * BS * BS : nullptr;
+    tq_warp<BS>(t, lane, valid, qp, o, res + (size_t)bb * BS * BS, pred + (size_t)bb * BS * BS, false);
+}
+
+template <int BS>
+cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
+    constexpr int NBW = 32 / BS;
+    const size_t smem = sizeof(TqCtaSmem<BS>);
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
+    dim3 grid((a.nblk + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), lanes);
+    tq_pframe_kernel<BS><<<grid, TQ_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int BS>
+cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
+    constexpr int NBW = 32 / BS;
+    const size_t smem = sizeof(WarpTile<BS>) + BS * BS + 2 * NBW * BS + 64;
+    const int ngrp = (lanes + NBW - 1) / NBW;
+    tq_iframe_kernel<BS><<<a.bh * ngrp, 32, smem, st>>>(a, lanes);
+    return cudaGetLastError();
+}
+
+template <int BS>
+cudaError_t launch_b(const int16_t* res, const int16_t* pred, int nblocks, int qp, int16_t* level, uint8_t* recon,
+                     double* idct, double* coef, cudaStream_t st) {
+    constexpr int NBW = 32 / BS;
+    const size_t smem = sizeof(TqCtaSmem<BS>);
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(tq_blocks_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
+    const int grid = (nblocks + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW);
+    tq_blocks_kernel<BS><<<grid, TQ_WARPS * 32, smem, st>>>(res, pred, nblocks, qp, level, recon, idct, coef);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int tq_blk_words(int bs) { return bs == 16 ? blk_words_for<16>() : bs == 8 ? blk_words_for<8>() : blk_words_for<4>(); }
+
+cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st) {
+    switch (a.bs) {
+        case 16: return launch_p<16>(a, lanes, st);
+        case 8: return launch_p<8>(a, lanes, st);
+        case 4: return launch_p<4>(a, lanes, st);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st) {
+    switch (a.bs) {
+        case 16: return launch_i<16>(a, lanes, st);
+        case 8: return launch_i<8>(a, lanes, st);
+        case 4: return launch_i<4>(a, lanes, st);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_tq_blocks(const int16_t* res, const int16_t* pred, int nblocks, int bs, int qp, int16_t* level,
+                             uint8_t* recon, double* idct, double* coef, cudaStream_t st) {
+    switch (bs) {
+        case 16: return launch_b<16>(res, pred, nblocks, qp, level, recon, idct, coef, st);
+        case 8: return launch_b<8>(res, pred, nblocks, qp, level, recon, idct, coef, st);
+        case 4: return launch_b<4>(res, pred, nblocks, qp, level, recon, idct, coef, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace bvc

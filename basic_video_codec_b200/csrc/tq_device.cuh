@@ -1,0 +1,295 @@
+// tq_device.cuh -- warp-level device code shared by the P-frame and I-frame kernels:
+//   K5  residual -> defined fp64 DCT -> quantise -> rescale -> IDCT -> reconstruct
+//       (reference encoder/Frame.py:190-202, encoder/dct.py:9-42; arithmetic defined in DESIGN.md §DCT
+//        and restated on the CPU in oracle/bvc_oracle.c -- the two must agree bit for bit)
+//   K7a zig-zag -> RLE -> signed exp-Golomb of one block's levels + end-of-block marker
+//       (reference encoder/Frame.py:61-75, encoder/entropy_encoder.py:8-29,65-88,115-135)
+//
+// One warp owns NBW = 32/BS blocks side by side: lane = (q = block in warp, x = column/row index).
+// Every 1-D pass gives each lane one line of BS values and all BS outputs of it, BS/2 DFMA each with
+// compile-time table indices (operands come from the constant bank, no shared-memory traffic for the
+// cosines).  Lines are exchanged through a padded fp64 shared-memory tile between passes.
+#pragma once
+#include "bvc_common.cuh"
+#include "bvc_dct_tables.h"
+
+namespace bvc {
+
+__constant__ double c_ct4[16] = BVC_CT4_INIT;
+__constant__ double c_ct8[64] = BVC_CT8_INIT;
+__constant__ double c_ct16[256] = BVC_CT16_INIT;
+__constant__ double c_w4[3] = BVC_W4_INIT;
+__constant__ double c_w8[3] = BVC_W8_INIT;
+__constant__ double c_w16[3] = BVC_W16_INIT;
+
+template <int BS> struct DctC;
+template <> struct DctC<4>  { static __device__ __forceinline__ double ct(int i) { return c_ct4[i]; }  static __device__ __forceinline__ double w(int i) { return c_w4[i]; } };
+template <> struct DctC<8>  { static __device__ __forceinline__ double ct(int i) { return c_ct8[i]; }  static __device__ __forceinline__ double w(int i) { return c_w8[i]; } };
+template <> struct DctC<16> { static __device__ __forceinline__ double ct(int i) { return c_ct16[i]; } static __device__ __forceinline__ double w(int i) { return c_w16[i]; } };
+
+template <int BS>
+constexpr int blk_words_for() {
+    // worst case: every coefficient non-zero with the largest magnitude 255*BS
+    return BS == 16 ? 208 : BS == 8 ? 48 : 12;
+}
+
+// Shared-memory working set of one warp.
+template <int BS>
+struct WarpTile {
+    static constexpr int NBW = 32 / BS;
+    double buf[NBW][BS][BS + 1];
+    int16_t lev[NBW][BS][BS];
+    uint8_t cur[NBW][BS][BS];
+    uint8_t pred[NBW][BS][BS];
+    uint32_t bits[blk_words_for<BS>() + 4];
+};
+
+// out[u] = sum_{x<BS/2} ct[u][x] * (u even ? a[x]+a[BS-1-x] : a[x]-a[BS-1-x])
+template <int BS>
+__device__ __forceinline__ void fold_fwd(const double (&a)[BS], double (&out)[BS]) {
+    constexpr int Hh = BS / 2;
+    double s[Hh], d[Hh];
+#pragma unroll
+    for (int x = 0; x < Hh; x++) { s[x] = __dadd_rn(a[x], a[BS - 1 - x]); d[x] = __dsub_rn(a[x], a[BS - 1 - x]); }
+#pragma unroll
+    for (int u = 0; u < BS; u++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int x = 0; x < Hh; x++) acc = __fma_rn(DctC<BS>::ct(u * BS + x), (u & 1) ? d[x] : s[x], acc);
+        out[u] = acc;
+    }
+}
+// out[y] = E+O, out[BS-1-y] = E-O with E/O the even/odd-u fma chains
+template <int BS>
+__device__ __forceinline__ void fold_inv(const double (&v)[BS], double (&out)[BS]) {
+    constexpr int Hh = BS / 2;
+#pragma unroll
+    for (int y = 0; y < Hh; y++) {
+        double e = 0.0, o = 0.0;
+#pragma unroll
+        for (int u = 0; u < BS; u += 2) e = __fma_rn(DctC<BS>::ct(u * BS + y), v[u], e);
+#pragma unroll
+        for (int u = 1; u < BS; u += 2) o = __fma_rn(DctC<BS>::ct(u * BS + y), v[u], o);
+        out[y] = __dadd_rn(e, o);
+        out[BS - 1 - y] = __dsub_rn(e, o);
+    }
+}
+
+__device__ __forceinline__ double pow2_neg(int s) { return __hiloint2double((1023 - s) << 20, 0); }
+__device__ __forceinline__ double pow2_pos(int s) { return __hiloint2double((1023 + s) << 20, 0); }
+
+struct TqOut {
+    int16_t* levels;   // global, frame layout, pitch W (elements) -- may be null
+    int lev_pitch;
+    uint8_t* recon;    // global plane base for this block row/col, pitch
+    int rec_pitch;
+    int8_t* resid_mc;  // may be null; pitch W
+    int resid_pitch;
+    double* idct_out;  // block hook only (dense bs*bs), may be null
+    double* coef_out;  // block hook only
+};
+
+// Transform + quantise + reconstruct the NBW blocks held in `t` (cur/pred filled, or residual given by
+// res_override for the block hook).  lane -> (q, x).  `valid` masks warps' trailing blocks.
+// qp: quantisation parameter of this block row.  Writes lev tile (smem) and the outputs in `o[q]`.
+// intra_u8_resid: I frames store the raw int16 residual as uint8 in the debug plane (IFrame.py:30,57-58).
+template <int BS>
+__device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, int qp, const TqOut& o,
+                                        const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid) {
+    const int q = lane / BS, x = lane % BS;
+    double a[BS], r[BS];
+    // ---- forward pass 1: columns (apply_dct_2d transforms columns first, dct.py:12) ----
+#pragma unroll
+    for (int y = 0; y < BS; y++) {
+        if (res_override) a[y] = (double)res_override[y * BS + x];
+        else a[y] = (double)((int)t.cur[q][y][x] - (int)t.pred[q][y][x]);  // PFrame.py:248 / IFrame.py:222
+    }
+    if (intra_u8_resid && o.resid_mc && valid) {
+#pragma unroll
+        for (int y = 0; y < BS; y++) o.resid_mc[(size_t)y * o.resid_pitch + x] = (int8_t)(uint8_t)(int)a[y];
+    }
+    fold_fwd<BS>(a, r);
+#pragma unroll
+    for (int u = 0; u < BS; u++) t.buf[q][u][x] = r[u];
+    __syncwarp();
+    // ---- forward pass 2: rows; this lane owns row u = x ----
+    const int u = x;
+#pragma unroll
+    for (int i = 0; i < BS; i++) a[i] = t.buf[q][u][i];
+    fold_fwd<BS>(a, r);
+    const bool su = (u == 0) || (2 * u == BS);
+    const double w_sp = su ? DctC<BS>::w(0) : DctC<BS>::w(1);  // for v in {0, BS/2}
+    const double w_nm = su ? DctC<BS>::w(1) : DctC<BS>::w(2);
+    const double inv0 = pow2_neg(qp), inv1 = pow2_neg(qp + 1), inv2 = pow2_neg(qp + 2);
+    const double q0 = pow2_pos(qp), q1 = pow2_pos(qp + 1), q2 = pow2_pos(qp + 2);
+    short lv[BS];
+#pragma unroll
+    for (int v = 0; v < BS; v++) {
+        const bool sv = (v == 0) || (2 * v == BS);
+        const double w = sv ? w_sp : w_nm;
+        const double coef = __dmul_rn(r[v], w);
+        if (o.coef_out && valid) o.coef_out[u * BS + v] = coef;
+        // generate_quantization_matrix dct.py:21-32 ; quantize_block :35-37 (round half to even)
+        const int d = u + v - (BS - 1);
+        const double inv = d < 0 ? inv0 : (d == 0 ? inv1 : inv2);
+        const double qs = d < 0 ? q0 : (d == 0 ? q1 : q2);
+        const double lq = rint(__dmul_rn(coef, inv));
+        lv[v] = (short)(int)lq;
+        // rescale_block dct.py:40-42 (exact) then the inverse transform's input scaling
+        a[v] = __dmul_rn(__dmul_rn(lq, qs), w);
+    }
+#pragma unroll
+    for (int v = 0; v < BS; v++) { t.lev[q][u][v] = lv[v]; t.buf[q][u][v] = a[v]; }
+    if (o.levels && valid) {
+        int16_t* lp = o.levels + (size_t)u * o.lev_pitch;
+#pragma unroll
+        for (int v = 0; v < BS; v++) lp[v] = lv[v];
+    }
+    __syncwarp();
+    // ---- inverse pass 1: over u for column v = x ----
+#pragma unroll
+    for (int i = 0; i < BS; i++) a[i] = t.buf[q][i][x];
+    fold_inv<BS>(a, r);
+    __syncwarp();
+#pragma unroll
+    for (int y = 0; y < BS; y++) t.buf[q][y][x] = r[y];
+    __syncwarp();
+    // ---- inverse pass 2: over v for row y = x ----
+    const int y = x;
+#pragma unroll
+    for (int i = 0; i < BS; i++) a[i] = t.buf[q][y][i];
+    fold_inv<BS>(a, r);
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+            const double p = pred_override ? (double)pred_override[y * BS + i] : (double)t.pred[q][y][i];
+            // reconstruct_block Frame.py:197-202: round(idct + pred) -> int16 -> clip -> uint8
+            const int v = (int)(short)(int)rint(__dadd_rn(r[i], p));
+            o.recon[(size_t)y * o.rec_pitch + i] = (uint8_t)min(max(v, 0), 255);
+            if (o.idct_out) o.idct_out[y * BS + i] = r[i];
+            // PFrame.py:39,63: float64 idct residual stored into an int8 plane (C cast: truncate, wrap)
+            if (!intra_u8_resid && o.resid_mc) o.resid_mc[(size_t)y * o.resid_pitch + i] = (int8_t)(int)r[i];
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// zig-zag position table: zz[p] = row*BS + col (entropy_encoder.py:115-135):
+// even diagonals run (row=i, col=s-i) with i ascending, odd ones (row=s-i, col=i).
+template <int BS>
+__device__ __forceinline__ void build_zigzag(uint8_t* zz, int tid, int nthreads) {
+    for (int e = tid; e < BS * BS; e += nthreads) {
+        const int r = e / BS, c = e % BS, s = r + c;
+        int before = (s < BS) ? s * (s + 1) / 2 : BS * BS - (2 * BS - 1 - s) * (2 * BS - s) / 2;
+        const int i0 = max(0, s - BS + 1);
+        const int idx = (s & 1) ? (c - i0) : (r - i0);
+        zz[before + idx] = (uint8_t)e;
+    }
+}
+
+// OR `len` bits of `code` (right aligned) into the big-endian word stream `buf` at bit offset `off`.
+__device__ __forceinline__ void put_bits_smem(uint32_t* buf, int off, unsigned long long code, int len) {
+    const unsigned long long V = code << (64 - len);
+    const int sh = off & 31, wi = off >> 5;
+    const uint32_t hi = (uint32_t)(V >> 32), lo = (uint32_t)V;
+    const uint32_t w0 = hi >> sh;
+    const uint32_t w1 = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
+    const uint32_t w2 = sh ? (lo << (32 - sh)) : 0u;
+    if (w0) atomicOr(&buf[wi], w0);
+    if (w1) atomicOr(&buf[wi + 1], w1);
+    if (w2) atomicOr(&buf[wi + 2], w2);
+}
+
+// Entropy-code one block (levels in smem tile `lev`, BS x BS) cooperatively by one warp.
+// Returns the number of bits; the bits are left in t.bits (big-endian words) and copied to `gout`.
+template <int BS>
+__device__ __forceinline__ int entropy_block_warp(const int16_t* lev, const uint8_t* zz, uint32_t* bits, int lane,
+                                                  uint32_t* gout) {
+    constexpr int N = BS * BS;
+    constexpr int PL = N >= 32 ? N / 32 : 1;   // positions per lane
+    constexpr int AL = N / PL;                 // active lanes
+    const bool act = lane < AL;
+    const int p0 = lane * PL;
+    int c[PL];
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < PL; i++) {
+        c[i] = act ? (int)lev[zz[p0 + i]] : 0;
+        nz |= (c[i] != 0 ? 1u : 0u) << i;
+    }
+    // run starts: position 0, or state differs from the previous position
+    uint32_t lastbit = (nz >> (PL - 1)) & 1u;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, lastbit, 1);
+    uint32_t start = (nz ^ ((nz << 1) | prev)) & ((1u << PL) - 1u);
+    if (lane == 0) start |= 1u;
+    if (!act) start = 0;
+    // first run start strictly after this lane's chunk (N if none)
+    int first = start ? p0 + (__ffs(start) - 1) : N;
+    int sfx = first;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_down_sync(0xffffffffu, sfx, d);
+        if (lane + d < 32) sfx = min(sfx, o);
+    }
+    int next = __shfl_down_sync(0xffffffffu, sfx, 1);
+    if (lane == 31) next = N;
+    // per position code (header and/or value), computed back to front so run lengths are known
+    unsigned long long code[PL];
+    int len[PL];
+    int total = 0;
+#pragma unroll
+    for (int i = PL - 1; i >= 0; i--) {
+        const int p = p0 + i;
+        unsigned long long cd = 0;
+        int ln = 0;
+        const bool st = (start >> i) & 1u;
+        const bool isnz = (nz >> i) & 1u;
+        int runlen = 0;
+        bool to_end = false;
+        if (st) { runlen = next - p; to_end = (next == N); next = p; }
+        if (isnz) {
+            if (st) {  // rle_encode: -count then the values (entropy_encoder.py:78-86)
+                const uint32_t e = eg_code(-runlen);
+                ln = eg_len_of_code(e);
+                cd = e;
+            }
+            const uint32_t e = eg_code(c[i]);
+            const int l2 = eg_len_of_code(e);
+            cd = (cd << l2) | e;
+            ln += l2;
+        } else if (st) {  // zero run: count, or 0 when it reaches the end (entropy_encoder.py:68-76)
+            const uint32_t e = eg_code(to_end ? 0 : runlen);
+            ln = eg_len_of_code(e);
+            cd = e;
+        }
+        code[i] = cd;
+        len[i] = ln;
+        total += ln;
+    }
+    // exclusive scan of lane totals
+    int incl = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    int off = incl - total;
+    const int body_bits = __shfl_sync(0xffffffffu, incl, 31);
+    const int nbits = body_bits + 27;  // + EG(8190) end-of-block marker (Frame.py:75)
+    const int nwords = (nbits + 31) >> 5;
+    for (int w = lane; w < nwords + 2; w += 32) bits[w] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < PL; i++) {
+        if (len[i]) put_bits_smem(bits, off, code[i], len[i]);
+        off += len[i];
+    }
+    if (lane == 0) put_bits_smem(bits, body_bits, (unsigned long long)eg_code(BVC_EOB_MARKER), 27);
+    __syncwarp();
+    for (int w = lane; w < nwords; w += 32) gout[w] = bits[w];
+    __syncwarp();
+    return nbits;
+}
+
+}  // namespace bvc

@@ -1,0 +1,123 @@
+/*
+ * bvc.h -- C ABI of libbvc_b200.so: the B200-native encoder hot path of dheri/basic_video_codec.
+ *
+ * The reference is pure Python and has no FFI; its seam is the object protocol between
+ * encoder/encoder.py (the frame loop) and the Frame classes.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference repository).  A maintainer binds
+ * these with ctypes (INTEGRATION.md shows the stub); basic_video_codec_b200/ ships that binding plus
+ * PFrame / IFrame / encode_video mirrors with the reference's names and attributes.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the boundary, int status
+ * (0 = BVC_OK, negative = error) and bvc_last_error() for the message.  All planes are row-major
+ * uint8 luma (H x W, W bytes per row).  A context is bound to one GPU and one geometry and is not
+ * thread safe; contexts are independent (one per GPU / host thread for GOP sharding).
+ * There is no CPU fallback: every function fails with BVC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef BVC_H
+#define BVC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVC_OK 0
+#define BVC_ERR_INVALID (-1)     /* ValueError in the reference (params.py:28-36, block_predictor.py:70-71) */
+#define BVC_ERR_CUDA (-2)
+#define BVC_ERR_OVERFLOW (-3)    /* OverflowError: payload does not fit the container length field (encoder.py:108-117) */
+#define BVC_ERR_NOMEM (-4)
+#define BVC_ERR_UNSUPPORTED (-5)
+
+typedef struct bvc_ctx bvc_ctx;
+
+/* EncoderConfig (encoder/params.py:6-23) + InputParameters.width/height (input_parameters.py:4-11).
+ * RCflag is 0 in this ABI revision: per-row QPs are passed explicitly to the frame-level calls. */
+typedef struct bvc_params {
+    int width, height;   /* luma size; must be multiples of block_size (pad_frame, common.py:22-32, is applied by the Python layer) */
+    int block_size;      /* i  : 4, 8 or 16 */
+    int search_range;    /* r  : integer-pel range; ignored when fast_me */
+    int qp;              /* quantization_factor (base QP) */
+    int nref_frames;     /* nRefFrames: length of the reference window, 1..8 */
+    int fast_me;         /* fastME */
+    int frac_me;         /* fracMeEnabled: half-pel motion vectors */
+    int i_period;        /* I_Period */
+} bvc_params;
+
+/* Outputs of one encoded frame: the attributes encoder/encoder.py reads off a Frame after
+ * encode_mc_q_dct() (encoder.py:89-155).  All pointers are caller-allocated host buffers; any of
+ * them may be NULL to skip that output (and its device-to-host copy). */
+typedef struct bvc_frame_out {
+    uint8_t *recon;          /* reconstructed_frame, H*W */
+    int16_t *levels;         /* quantized_dct_residual_frame, H*W, block-tiled in frame layout */
+    int32_t *mv;             /* P: mv_field in raster order, nblk*3 (mvx, mvy, ref_idx) */
+    int32_t *sad;            /* per-block min SAD (= MAE * i*i); I: mode-decision SAD */
+    int32_t *modes;          /* I: intra_modes, nblk */
+    int8_t  *resid_mc;       /* residual_frame (debug plane: PFrame.py:39,63 / IFrame.py:30,57) */
+    int8_t  *resid_nomc;     /* residual_wo_mc_frame (P only, PFrame.py:40,64) */
+    uint8_t *pred_bytes;     /* entropy_encoded_prediction_data.tobytes() */
+    size_t   pred_cap;
+    uint8_t *coef_bytes;     /* entropy_encoded_DCT_coffs.tobytes() */
+    size_t   coef_cap;
+    int64_t *bits_per_row;   /* bits_per_row, H/i entries */
+    /* scalars written by the call */
+    int64_t  pred_nbits, coef_nbits;
+    double   avg_mae;
+    int64_t  mae_comparisons; /* total_mae_comparisons */
+} bvc_frame_out;
+
+/* lifetime ---------------------------------------------------------------------------------- */
+/* max_lanes: how many independent GOPs the context may encode in lock-step (clip API); 1 is enough
+ * for the frame-level calls. */
+int bvc_create(bvc_ctx **ctx, int device, const bvc_params *params, int max_lanes);
+void bvc_destroy(bvc_ctx *ctx);
+const char *bvc_last_error(const bvc_ctx *ctx); /* ctx may be NULL: error of the last failed bvc_create */
+int bvc_set_qp(bvc_ctx *ctx, int qp);
+
+/* frame level -------------------------------------------------------------------------------- */
+/* IFrame.encode_mc_q_dct (encoder/IFrame.py:22-83).  qp_rows: H/i per-row QPs or NULL (= base QP). */
+int bvc_encode_iframe(bvc_ctx *ctx, const uint8_t *cur, const int32_t *qp_rows, bvc_frame_out *out);
+/* PFrame.encode_mc_q_dct (encoder/PFrame.py:29-97).  refs: the reference window in deque order,
+ * index 0 = oldest (encoder.py:33,154); nref_avail = len(reference_frames). */
+int bvc_encode_pframe(bvc_ctx *ctx, const uint8_t *cur, const uint8_t *const *refs, int nref_avail,
+                      const int32_t *qp_rows, bvc_frame_out *out);
+
+/* block-level hooks ---------------------------------------------------------------------------- */
+/* PFrame.get_motion_vector over a whole frame: find_lowest_mae_block or find_fast_me_block per the
+ * context's parameters (encoder/block_predictor.py:11-91).  mv: nblk*3, sad: nblk. */
+int bvc_me_search(bvc_ctx *ctx, const uint8_t *cur, const uint8_t *const *refs, int nref_avail,
+                  int32_t *mv, int32_t *sad, int64_t *comparisons);
+/* build_pre_interpolated_buffer (encoder/block_predictor.py:145-177): out is (2H x 2W). */
+int bvc_interp_halfpel(bvc_ctx *ctx, const uint8_t *ref, uint8_t *out2x);
+/* apply_dct_and_quantization + reconstruct_block (encoder/Frame.py:190-202) on nblocks dense
+ * bs x bs blocks.  idct / coef (fp64) may be NULL. */
+int bvc_dct_quant_recon(int device, const int16_t *residual, const int16_t *pred, int nblocks, int bs,
+                        int qp, int16_t *level, uint8_t *recon, double *idct, double *coef);
+
+/* clip level ------------------------------------------------------------------------------------ */
+/* The encode_video frame loop for RCflag = 0 (encoder/encoder.py:75-121,154-155,174-186): frame idx
+ * (1-based) with (idx-1) % I_Period == 0 is an I frame and clears the reference window, so GOPs are
+ * independent and are encoded max_lanes at a time.  `frames` = nframes planes (host memory, ideally
+ * pinned).  The container bytes (encoded.bin layout, encoder.py:104-121) are written to out[0..*out_len).
+ * recon (optional) receives the nframes reconstructed planes. */
+int bvc_encode_clip(bvc_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *out, size_t out_cap,
+                    size_t *out_len, uint8_t *recon);
+/* Same, for a clip whose planes are already resident in HBM (bvc_clip_upload), so the timed region
+ * of a throughput measurement holds no input transfer. */
+int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
+int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
+                             uint8_t *recon);
+
+/* instrumentation --------------------------------------------------------------------------- */
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t bvc_launch_count(const bvc_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) spent in the motion-estimation kernel and
+ * its launch count during the last clip call */
+int bvc_last_me_time(const bvc_ctx *ctx, double *ms, int64_t *launches);
+/* algorithmic pixel-absdiffs (valid candidates * i*i * refs) of one P frame with `nref_avail` references */
+int64_t bvc_me_work_per_frame(const bvc_ctx *ctx, int nref_avail);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

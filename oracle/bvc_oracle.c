@@ -219,45 +219,63 @@ int bvo_q_shift(int bs, int qp, int u, int v)
     return qp + 2;
 }
 
-/* Forward: apply_dct_2d dct.py:9-12 transforms columns first, then rows.
- * T[u][x] = sum_y Ct[u][y] X[y][x] ; Yu[u][v] = sum_x T[u][x] Ct[v][x] ; coef = Yu * W.
- * All sums are fma chains from 0.0 in ascending index order.                                    */
+/* Forward: apply_dct_2d dct.py:9-12 transforms columns first, then rows.  Both passes use the
+ * even/odd symmetry Ct[u][N-1-x] = (-1)^u Ct[u][x]:  with s[x] = a[x] + a[N-1-x], d[x] = a[x] - a[N-1-x],
+ *     out[u] = sum_{x < N/2} Ct[u][x] * (u even ? s[x] : d[x])        (fma chain from 0.0, x ascending)
+ * pass 1 (columns):  T[u][x]  from the integer residual (s, d exact);
+ * pass 2 (rows):     Yu[u][v] from T (s, d rounded once);   coef = Yu * W   (one rounding).         */
+static void fold_fwd(const double *a, int n, const double *ct, double *out)
+{
+    const int h = n / 2;
+    double s[BVO_MAX_BS / 2], d[BVO_MAX_BS / 2];
+    for (int x = 0; x < h; x++) { s[x] = a[x] + a[n - 1 - x]; d[x] = a[x] - a[n - 1 - x]; }
+    for (int u = 0; u < n; u++) {
+        const double *in = (u & 1) ? d : s;
+        double acc = 0.0;
+        for (int x = 0; x < h; x++) acc = fma(ct[u * n + x], in[x], acc);
+        out[u] = acc;
+    }
+}
+/* Inverse 1-D: E[y] = sum_{u even} Ct[u][y] V[u], O[y] = sum_{u odd} Ct[u][y] V[u] (fma chains, u
+ * ascending), out[y] = E + O, out[N-1-y] = E - O for y < N/2.                                      */
+static void fold_inv(const double *v, int n, const double *ct, double *out)
+{
+    const int h = n / 2;
+    for (int y = 0; y < h; y++) {
+        double e = 0.0, o = 0.0;
+        for (int u = 0; u < n; u += 2) e = fma(ct[u * n + y], v[u], e);
+        for (int u = 1; u < n; u += 2) o = fma(ct[u * n + y], v[u], o);
+        out[y] = e + o;
+        out[n - 1 - y] = e - o;
+    }
+}
+
 void bvo_fdct(const int16_t *res, int bs, double *coef)
 {
     const dct_tab *t = get_tab(bs);
-    double T[BVO_MAX_BS * BVO_MAX_BS];
-    for (int u = 0; u < bs; u++)
-        for (int x = 0; x < bs; x++) {
-            double acc = 0.0;
-            for (int y = 0; y < bs; y++) acc = fma(t->ct[u * bs + y], (double)res[y * bs + x], acc);
-            T[u * bs + x] = acc;
-        }
-    for (int u = 0; u < bs; u++)
-        for (int v = 0; v < bs; v++) {
-            double acc = 0.0;
-            for (int x = 0; x < bs; x++) acc = fma(T[u * bs + x], t->ct[v * bs + x], acc);
-            coef[u * bs + v] = acc * t->w[u * bs + v];
-        }
+    double T[BVO_MAX_BS * BVO_MAX_BS], a[BVO_MAX_BS], o[BVO_MAX_BS];
+    for (int x = 0; x < bs; x++) {
+        for (int y = 0; y < bs; y++) a[y] = (double)res[y * bs + x];
+        fold_fwd(a, bs, t->ct, o);
+        for (int u = 0; u < bs; u++) T[u * bs + x] = o[u];
+    }
+    for (int u = 0; u < bs; u++) {
+        fold_fwd(T + u * bs, bs, t->ct, o);
+        for (int v = 0; v < bs; v++) coef[u * bs + v] = o[v] * t->w[u * bs + v];
+    }
 }
 
-/* Inverse: V = coef * W ; R[y][v] = sum_u Ct[u][y] V[u][v] ; X[y][x] = sum_v R[y][v] Ct[v][x]. */
+/* Inverse: V = coef * W (one rounding); pass 1 over u for every column v; pass 2 over v for every row. */
 void bvo_idct(const double *coef, int bs, double *out)
 {
     const dct_tab *t = get_tab(bs);
-    double V[BVO_MAX_BS * BVO_MAX_BS], Rm[BVO_MAX_BS * BVO_MAX_BS];
-    for (int i = 0; i < bs * bs; i++) V[i] = coef[i] * t->w[i];
-    for (int y = 0; y < bs; y++)
-        for (int v = 0; v < bs; v++) {
-            double acc = 0.0;
-            for (int u = 0; u < bs; u++) acc = fma(t->ct[u * bs + y], V[u * bs + v], acc);
-            Rm[y * bs + v] = acc;
-        }
-    for (int y = 0; y < bs; y++)
-        for (int x = 0; x < bs; x++) {
-            double acc = 0.0;
-            for (int v = 0; v < bs; v++) acc = fma(Rm[y * bs + v], t->ct[v * bs + x], acc);
-            out[y * bs + x] = acc;
-        }
+    double Rm[BVO_MAX_BS * BVO_MAX_BS], a[BVO_MAX_BS], o[BVO_MAX_BS];
+    for (int v = 0; v < bs; v++) {
+        for (int u = 0; u < bs; u++) a[u] = coef[u * bs + v] * t->w[u * bs + v];
+        fold_inv(a, bs, t->ct, o);
+        for (int y = 0; y < bs; y++) Rm[y * bs + v] = o[y];
+    }
+    for (int y = 0; y < bs; y++) fold_inv(Rm + y * bs, bs, t->ct, out + y * bs);
 }
 
 /* Frame.py:190-202 */

@@ -1,0 +1,72 @@
+"""CPU-only checks of the host layer: the C-ABI library loads and exports every declared symbol, the
+parameter objects validate like the reference's, and the product never reaches into oracle/."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import basic_video_codec_b200._lib as l
+    L = l.load_library()
+    hdr = open(os.path.join(ROOT, "include", "bvc.h")).read()
+    declared = set(re.findall(r"\b(bvc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(l.EXPORTS)
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import basic_video_codec_b200 as bvc
+    with pytest.raises(bvc.BvcError):
+        bvc.Context(64, 64, 16, 4, 3)
+
+
+def test_encoder_config_validation():
+    from basic_video_codec_b200 import EncoderConfig
+    with pytest.raises(ValueError):
+        EncoderConfig(8, 4, 8, 11)            # qp > log2(8) + 7
+    with pytest.raises(ValueError):
+        EncoderConfig(8, 4, 8, 3, RCflag=1)   # rate control without a target bitrate
+    assert EncoderConfig(16, 16, 8, 3, fastME=True).search_range == -1
+    ec = EncoderConfig(8, 4, 8, 3)
+    assert (ec.nRefFrames, ec.fastME, ec.fracMeEnabled, ec.RCflag, ec.frame_rate, ec.resolution) == (1, False, False, 0, 30, (352, 288))
+
+
+def test_product_does_not_touch_oracle():
+    """oracle/ is test infrastructure: nothing in the product may import, include, link or load it."""
+    pkg = os.path.join(ROOT, "basic_video_codec_b200")
+    bad = re.compile(r'(#include\s+["<][^">]*oracle)|(^\s*import\s+oracle)|(^\s*from\s+oracle)|(libbvc_oracle)|(-lbvc_oracle)', re.M)
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                src = open(os.path.join(dp, f)).read()
+                assert not bad.search(src), f
+
+
+def test_bitstring_protocol():
+    from basic_video_codec_b200.encoder.Frame import BitString
+    b = BitString(bytes([0b10100000]), 3)
+    assert len(b) == 3 and b.tobytes() == bytes([0b10100000]) and b.to01() == "101" and bool(b)
+    assert not BitString()
+
+
+def test_dct_tables_agree_with_oracle():
+    """The product's generated constant tables (exact decimal arithmetic) and the oracle's independently
+    derived ones (long-double libm) must be bit-identical."""
+    from oracle import bindings as ob
+    hdr = open(os.path.join(ROOT, "basic_video_codec_b200", "csrc", "bvc_dct_tables.h")).read()
+    for bs in (2, 4, 8, 16, 32):
+        m = re.search(rf"#define BVC_CT{bs}_INIT \{{(.*?)\n\}}", hdr, re.S)
+        vals = [float.fromhex(t) for t in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+", m.group(1))]
+        ct, w = ob.dct_tables(bs)
+        assert len(vals) == bs * bs
+        assert [v.hex() for v in vals] == [float(x).hex() for x in ct.ravel()]
+        mw = re.search(rf"#define BVC_W{bs}_INIT \{{(.*?)\}}", hdr)
+        wv = [float.fromhex(t) for t in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+", mw.group(1))]
+        assert set(float(x).hex() for x in w.ravel()) <= set(v.hex() for v in wv)
