@@ -14,7 +14,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
-    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_me_time", "bvc_me_work_per_frame",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame",
 ]
 
 
@@ -69,7 +69,7 @@ def load_library():
     L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.bvc_launch_count.argtypes = [C.c_void_p]
     L.bvc_launch_count.restype = C.c_int64
-    L.bvc_last_me_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.bvc_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.bvc_me_work_per_frame.argtypes = [C.c_void_p, C.c_int]
     L.bvc_me_work_per_frame.restype = C.c_int64
     _LIB = L
@@ -222,10 +222,15 @@ class Context:
     def launch_count(self):
         return int(self._L.bvc_launch_count(self._h))
 
-    def last_me_time(self):
-        ms, n = C.c_double(0), C.c_int64(0)
-        self._L.bvc_last_me_time(self._h, C.byref(ms), C.byref(n))
-        return float(ms.value), int(n.value)
+    KERNEL_CLASSES = ("me", "tq_p", "tq_i", "pack", "halfpel")
+
+    def last_kernel_times(self):
+        """{class: (ms, launches)} of the last clip call plus the whole-call device time in ms."""
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        clip = C.c_double(0)
+        self._L.bvc_last_kernel_times(self._h, ms, n, C.byref(clip))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}, float(clip.value)
 
     def me_work_per_frame(self, nref_avail=1):
         return int(self._L.bvc_me_work_per_frame(self._h, int(nref_avail)))

@@ -76,11 +76,33 @@ struct bvc_ctx {
     void* h_desc = nullptr;       // pinned descriptor staging
     size_t h_desc_cap = 0;
 
-    // instrumentation of the last clip call
-    double last_me_ms = 0;
-    int64_t last_me_launches = 0;
+    // instrumentation of the last clip call: CUDA events on the compute stream around every kernel class
+    bool timing = true;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cls, e0, e1; };
+    std::vector<Span> spans;
+    double last_ms[BVC_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
+    int64_t last_launches[BVC_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
+    double last_clip_ms = 0;
     int resident_frames = 0;
 };
+
+// record an event on the compute stream and return its index (-1 when timing is off)
+static int tick(bvc_ctx* c) {
+    if (!c->timing) return -1;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        c->ev_pool.push_back(e);
+    }
+    const int i = (int)c->ev_used++;
+    cudaEventRecord(c->ev_pool[i], c->st);
+    return i;
+}
+static void span(bvc_ctx* c, int cls, int e0, int e1) {
+    if (e0 >= 0 && e1 >= 0) c->spans.push_back({cls, e0, e1});
+}
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -224,6 +246,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_bits) cudaFreeHost(c->h_bits);
     if (c->h_desc) cudaFreeHost(c->h_desc);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
     delete c;
@@ -231,10 +254,13 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
 
 extern "C" const char* bvc_last_error(const bvc_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" int64_t bvc_launch_count(const bvc_ctx* c) { return c ? c->launches : 0; }
-extern "C" int bvc_last_me_time(const bvc_ctx* c, double* ms, int64_t* launches) {
+extern "C" int bvc_last_kernel_times(const bvc_ctx* c, double* ms, int64_t* launches, double* clip_ms) {
     if (!c) return BVC_ERR_INVALID;
-    if (ms) *ms = c->last_me_ms;
-    if (launches) *launches = c->last_me_launches;
+    for (int i = 0; i < BVC_NUM_KERNEL_CLASSES; i++) {
+        if (ms) ms[i] = c->last_ms[i];
+        if (launches) launches[i] = c->last_launches[i];
+    }
+    if (clip_ms) *clip_ms = c->last_clip_ms;
     return BVC_OK;
 }
 
@@ -317,7 +343,7 @@ struct StepPlan {
 };
 
 // Enqueue the kernels of one step on c->st.  `parity` selects the stream double buffer.
-static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_api, cudaEvent_t me_start, cudaEvent_t me_stop) {
+static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_api) {
     const Geom& g = c->g;
     const int nl = sp.nl;
     TqArgs t{};
@@ -333,7 +359,9 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_a
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
     if (sp.intra) {
         CK(cudaMemsetAsync(c->d_progress, 0, (size_t)nl * g.bh * sizeof(int), c->st));
+        const int e0 = tick(c);
         CK(launch_tq_iframe(t, nl, c->st));
+        span(c, BVC_K_TQ_I, e0, tick(c));
         c->launches += 1;
     } else {
         MeArgs m{};
@@ -345,14 +373,16 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_a
         m.nphase = c->p.frac_me ? 4 : 1;
         m.R = c->p.search_range;
         m.Rh = c->p.search_range * m.sc;
-        if (me_start) CK(cudaEventRecord(me_start, c->st));
+        const int e0 = tick(c);
         if (c->p.fast_me) {
             CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
         } else {
             CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->st));
         }
-        if (me_stop) CK(cudaEventRecord(me_stop, c->st));
+        const int e1 = tick(c);
+        span(c, BVC_K_ME, e0, e1);
         CK(launch_tq_pframe(t, nl, c->st));
+        span(c, BVC_K_TQ_P, e1, tick(c));
         c->launches += 2;
     }
     PackArgs pk{};
@@ -364,7 +394,9 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_a
     pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
+    const int ep = tick(c);
     CK(launch_pack(pk, nl, c->st));
+    span(c, BVC_K_PACK, ep, tick(c));
     c->launches += 2;
     return BVC_OK;
 }
@@ -384,7 +416,9 @@ static int upload_halfpel_desc(bvc_ctx* c, const std::vector<int>& planes, size_
 static int enqueue_halfpel(bvc_ctx* c, size_t desc_off, int n) {
     if (!c->p.frac_me || n <= 0) return BVC_OK;
     const Geom& g = c->g;
+    const int e0 = tick(c);
     CK(launch_halfpel(c->d_hp_src + desc_off, c->d_hp_dst + desc_off, n, g.W, g.H, g.pitch, g.plane_bytes, c->st));
+    span(c, BVC_K_HALFPEL, e0, tick(c));
     c->launches += 1;
     return BVC_OK;
 }
@@ -437,7 +471,8 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
         else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
         c->launches += 1;
     } else {
-        if ((rc = enqueue_step(c, sp, 0, true, nullptr, nullptr)) != BVC_OK) return rc;
+        c->ev_used = 0; c->spans.clear();
+        if ((rc = enqueue_step(c, sp, 0, true)) != BVC_OK) return rc;
     }
     // ---- downloads ----
     std::vector<int4> hmv;
@@ -660,7 +695,11 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             if ((rc = upload_halfpel_desc(c, step_outplane[s], steps[s].desc_off)) != BVC_OK) return rc;
     }
 
-    // ---- input: whole-clip upload in GOP-wave order so step 0 can start after the first wave's I frames ----
+    cudaEvent_t ev_clip0, ev_clip1;
+    CK(cudaEventCreate(&ev_clip0));
+    CK(cudaEventCreate(&ev_clip1));
+    CK(cudaEventRecord(ev_clip0, c->st));
+    // ---- input: whole-clip upload ----
     if (host_frames) {
         if (g.pitch == g.W && g.plane_bytes == (size_t)g.W * g.H) {
             // chunked so that compute on early frames overlaps later copies (copy stream + events)
@@ -672,17 +711,18 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         }
     }
 
-    std::vector<cudaEvent_t> ev_bits(nsteps), ev_copy(nsteps), ev_me0(nsteps), ev_me1(nsteps);
+    std::vector<cudaEvent_t> ev_bits(nsteps), ev_copy(nsteps);
     for (size_t s = 0; s < nsteps; s++) {
         CK(cudaEventCreateWithFlags(&ev_bits[s], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_copy[s], cudaEventDisableTiming));
-        CK(cudaEventCreate(&ev_me0[s]));
-        CK(cudaEventCreate(&ev_me1[s]));
     }
+    c->ev_used = 0;
+    c->spans.clear();
+
     std::vector<FrameRec> recs(nframes);
     size_t stage_used = 0;
     // staging arena: grow geometrically; streams are small next to the planes
-    if ((rc = ensure_pinned(c, (void**)&c->h_stage, &c->h_stage_cap, std::max((size_t)nframes * g.W * g.H, (size_t)8 << 20))) != BVC_OK)
+    if ((rc = ensure_pinned(c, (void**)&c->h_stage, &c->h_stage_cap, std::max((size_t)nframes * g.W * g.H / 4, (size_t)16 << 20))) != BVC_OK)
         return rc;
 
     auto drain = [&](size_t s) -> int {  // host side of step s: learn sizes, enqueue the payload copies
@@ -711,7 +751,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         const int par = (int)(s & 1);
         // the stream buffers of this parity were last used by step s-2: its D2H must be done
         if (s >= 2) CK(cudaStreamWaitEvent(c->st, ev_copy[s - 2], 0));
-        if ((rc = enqueue_step(c, steps[s], par, false, ev_me0[s], ev_me1[s])) != BVC_OK) return rc;
+        if ((rc = enqueue_step(c, steps[s], par, false)) != BVC_OK) return rc;
         // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
         if ((rc = enqueue_halfpel(c, steps[s].desc_off, steps[s].nl)) != BVC_OK) return rc;
         CK(cudaMemcpyAsync(c->h_bits + s * (size_t)G * 2, c->d_frame_bits[par], (size_t)steps[s].nl * 2 * sizeof(long long),
@@ -726,19 +766,24 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         if (s >= 1 && (rc = drain(s - 1)) != BVC_OK) return rc;
     }
     if ((rc = drain(nsteps - 1)) != BVC_OK) return rc;
+    CK(cudaStreamWaitEvent(c->st, ev_copy[nsteps - 1], 0));
+    CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st_copy));
     CK(cudaStreamSynchronize(c->st));
 
     // ---- instrumentation ----
-    c->last_me_ms = 0;
-    c->last_me_launches = 0;
-    for (size_t s = 0; s < nsteps; s++) {
-        if (!steps[s].intra) {
-            float ms = 0;
-            if (cudaEventElapsedTime(&ms, ev_me0[s], ev_me1[s]) == cudaSuccess) { c->last_me_ms += ms; c->last_me_launches++; }
-        }
-        cudaEventDestroy(ev_bits[s]); cudaEventDestroy(ev_copy[s]); cudaEventDestroy(ev_me0[s]); cudaEventDestroy(ev_me1[s]);
+    for (int i = 0; i < BVC_NUM_KERNEL_CLASSES; i++) { c->last_ms[i] = 0; c->last_launches[i] = 0; }
+    for (const auto& sp : c->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[sp.e0], c->ev_pool[sp.e1]) == cudaSuccess) { c->last_ms[sp.cls] += ms; c->last_launches[sp.cls]++; }
     }
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_clip0, ev_clip1);
+        c->last_clip_ms = ms;
+        cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1);
+    }
+    for (size_t s = 0; s < nsteps; s++) { cudaEventDestroy(ev_bits[s]); cudaEventDestroy(ev_copy[s]); }
 
     // ---- container (encoder.py:104-121): host-side concatenation in frame order ----
     size_t o = 0;

@@ -111,9 +111,16 @@ int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out
 /* instrumentation --------------------------------------------------------------------------- */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t bvc_launch_count(const bvc_ctx *ctx);
-/* device time (ms, CUDA events on the context's stream) spent in the motion-estimation kernel and
- * its launch count during the last clip call */
-int bvc_last_me_time(const bvc_ctx *ctx, double *ms, int64_t *launches);
+/* Device time of the last clip call, from CUDA events recorded on the context's compute stream around
+ * every kernel launch: ms[k] / launches[k] per kernel class (BVC_K_*), and the whole call (first
+ * enqueue to last download) in *clip_ms.  Any pointer may be NULL. */
+#define BVC_K_ME 0       /* motion estimation (full search or FastME) */
+#define BVC_K_TQ_P 1     /* P-frame residual/transform/quantise/reconstruct + per-block entropy */
+#define BVC_K_TQ_I 2     /* I-frame intra wavefront (same body) */
+#define BVC_K_PACK 3     /* stream assembly (scan + emit) */
+#define BVC_K_HALFPEL 4  /* half-pel phase planes */
+#define BVC_NUM_KERNEL_CLASSES 5
+int bvc_last_kernel_times(const bvc_ctx *ctx, double *ms, int64_t *launches, double *clip_ms);
 /* algorithmic pixel-absdiffs (valid candidates * i*i * refs) of one P frame with `nref_avail` references */
 int64_t bvc_me_work_per_frame(const bvc_ctx *ctx, int nref_avail);
 

@@ -33,12 +33,14 @@ def moving_clip(seed: int, height: int, width: int, nframes: int, *, step: int =
     rng = np.random.default_rng(seed + 7919)
     dx = dy = 0
     out = np.empty((nframes, height, width), dtype=np.uint8)
+    crop_buf = np.empty((height, width), dtype=np.int16)
     for t in range(nframes):
         dx = int(np.clip(dx + rng.integers(-step, step + 1), -clamp, clamp))
         dy = int(np.clip(dy + rng.integers(-step, step + 1), -clamp, clamp))
         crop = T[margin + dy: margin + dy + height, margin + dx: margin + dx + width]
-        nz = np.random.default_rng(seed + 1 + t).integers(-noise, noise + 1, size=(height, width))
-        out[t] = np.clip(crop + nz, 0, 255).astype(np.uint8)
+        nz = np.random.default_rng(seed + 1 + t).integers(-noise, noise + 1, size=(height, width), dtype=np.int8)
+        np.clip(crop + nz, 0, 255, out=crop_buf)
+        out[t] = crop_buf
     return out
 
 
