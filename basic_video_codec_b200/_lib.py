@@ -197,23 +197,30 @@ class Context:
 
     # ---- clip level ------------------------------------------------------------------------------
     def encode_clip(self, frames, want_recon=False, out_capacity=None):
+        """Host-buffer clip encode (the public end-to-end call).  Returns (container bytes, recon | None)."""
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         n = frames.shape[0]
-        cap = int(out_capacity or (n * self.W * self.H + (1 << 20)))
+        cap = int(out_capacity or (n * self.W * self.H // 2 + (1 << 20)))
         out = np.empty(cap, np.uint8)
-        ln = C.c_size_t(0)
         recon = np.empty_like(frames) if want_recon else None
-        self._check(self._L.bvc_encode_clip(self._h, _p(frames), n, _p(out), cap, C.byref(ln), _p(recon)))
-        return out[: ln.value].tobytes(), recon
+        ln = self.encode_clip_into(frames, out, recon)
+        return out[:ln].tobytes(), recon
+
+    def encode_clip_into(self, frames, out, recon=None):
+        """Same call without Python-side copies: `out` is a caller-owned uint8 buffer (pinned for best
+        transfer speed); returns the number of container bytes written."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        self._check(self._L.bvc_encode_clip(self._h, _p(frames), frames.shape[0], _p(out), out.size, C.byref(ln), _p(recon)))
+        return int(ln.value)
 
     def clip_upload(self, frames):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         self._check(self._L.bvc_clip_upload(self._h, _p(frames), frames.shape[0]))
 
     def encode_clip_resident(self, nframes, out=None):
-        cap = nframes * self.W * self.H + (1 << 20)
         if out is None:
-            out = np.empty(cap, np.uint8)
+            out = np.empty(nframes * self.W * self.H // 2 + (1 << 20), np.uint8)
         ln = C.c_size_t(0)
         self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
         return out, int(ln.value)

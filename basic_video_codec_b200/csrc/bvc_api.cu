@@ -39,7 +39,7 @@ struct bvc_ctx {
     int max_lanes = 1;
     int pps = 1;          // planes per ring slot
     int slots = 2;        // ring slots per lane (nref + 1)
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_h2d = nullptr;
     std::string err;
     int64_t launches = 0;
 
@@ -56,10 +56,15 @@ struct bvc_ctx {
     int8_t *d_resid_mc = nullptr, *d_resid_nomc = nullptr;
     uint32_t* d_blk_bits = nullptr;
     int blk_words = 0;
-    long long *d_coef_off = nullptr, *d_frame_bits[2] = {nullptr, nullptr}, *d_row_bits = nullptr, *d_pred_row_off = nullptr,
-              *d_cmp = nullptr;
-    uint32_t *d_coef_stream[2] = {nullptr, nullptr}, *d_pred_stream[2] = {nullptr, nullptr};
+    long long *d_coef_off = nullptr, *d_row_bits = nullptr, *d_pred_row_off = nullptr, *d_cmp = nullptr;
+    // stream arena: one slot per frame of a clip call (slot 0 for the frame-level calls)
+    uint32_t *d_coef_stream = nullptr, *d_pred_stream = nullptr;
+    long long *d_frame_bits = nullptr, *d_frame_off = nullptr;
+    int* d_overflow = nullptr;
+    size_t stream_slots = 0;
     size_t coef_cap_words = 0, pred_cap_words = 0;
+    uint8_t* d_container = nullptr;
+    size_t container_cap = 0;
     int* d_progress = nullptr;
     MeLane* d_me_lanes = nullptr;
     FrameLane* d_fr_lanes = nullptr;
@@ -69,10 +74,6 @@ struct bvc_ctx {
     size_t hp_desc_cap = 0;
 
     // host staging
-    uint8_t* h_stage = nullptr;  // pinned arena for stream downloads
-    size_t h_stage_cap = 0;
-    long long* h_bits = nullptr;  // pinned [steps][lanes][2]
-    size_t h_bits_cap = 0;
     void* h_desc = nullptr;       // pinned descriptor staging
     size_t h_desc_cap = 0;
 
@@ -191,6 +192,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;
         CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
@@ -211,11 +213,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_progress, L * g.bh));
         c->coef_cap_words = nb * c->blk_words + 8;
         c->pred_cap_words = nb * 3 + g.bh + 8;
-        for (int i = 0; i < 2; i++) {
-            CK(dalloc(&c->d_coef_stream[i], L * c->coef_cap_words));
-            CK(dalloc(&c->d_pred_stream[i], L * c->pred_cap_words));
-            CK(dalloc(&c->d_frame_bits[i], L * 2));
-        }
+        CK(dalloc(&c->d_overflow, 1));
         std::vector<int32_t> q(L * g.bh, p->qp);
         CK(cudaMemcpy(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
         int rc = make_ref_map(c);
@@ -237,18 +235,19 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
+    if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
     cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_progress); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
-    for (int i = 0; i < 2; i++) { cudaFree(c->d_coef_stream[i]); cudaFree(c->d_pred_stream[i]); cudaFree(c->d_frame_bits[i]); }
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (c->h_bits) cudaFreeHost(c->h_bits);
+    cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
+    cudaFree(c->d_overflow); cudaFree(c->d_container);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     delete c;
 }
 
@@ -314,6 +313,26 @@ static int ensure_lane_desc(bvc_ctx* c, size_t n) {
     c->lane_desc_cap = n;
     return BVC_OK;
 }
+static int ensure_streams(bvc_ctx* c, size_t slots) {
+    if (slots <= c->stream_slots) return BVC_OK;
+    cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
+    c->d_coef_stream = c->d_pred_stream = nullptr; c->d_frame_bits = c->d_frame_off = nullptr;
+    c->stream_slots = 0;
+    CK(dalloc(&c->d_coef_stream, slots * c->coef_cap_words));
+    CK(dalloc(&c->d_pred_stream, slots * c->pred_cap_words));
+    CK(dalloc(&c->d_frame_bits, slots * 2));
+    CK(dalloc(&c->d_frame_off, slots + 1));
+    c->stream_slots = slots;
+    return BVC_OK;
+}
+static int ensure_container(bvc_ctx* c, size_t bytes) {
+    if (bytes <= c->container_cap) return BVC_OK;
+    cudaFree(c->d_container);
+    c->d_container = nullptr; c->container_cap = 0;
+    CK(cudaMalloc((void**)&c->d_container, bytes + 64));
+    c->container_cap = bytes;
+    return BVC_OK;
+}
 static int ensure_pinned(bvc_ctx* c, void** p, size_t* cap, size_t need) {
     if (need <= *cap) return BVC_OK;
     if (*p) CK(cudaFreeHost(*p));
@@ -342,8 +361,8 @@ struct StepPlan {
     size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
 };
 
-// Enqueue the kernels of one step on c->st.  `parity` selects the stream double buffer.
-static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_api) {
+// Enqueue the kernels of one step on c->st.
+static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api) {
     const Geom& g = c->g;
     const int nl = sp.nl;
     TqArgs t{};
@@ -389,8 +408,9 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, int parity, bool frame_a
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
     pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
     pk.coef_off = c->d_coef_off;
-    pk.coef_stream = c->d_coef_stream[parity]; pk.pred_stream = c->d_pred_stream[parity];
-    pk.frame_bits = c->d_frame_bits[parity]; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
+    pk.lanes = c->d_fr_lanes + sp.desc_off;
+    pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
     pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
@@ -435,10 +455,11 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
     int rc;
     if ((rc = ensure_in_pool(c, 1)) != BVC_OK) return rc;
     if ((rc = ensure_lane_desc(c, 1)) != BVC_OK) return rc;
+    if ((rc = ensure_streams(c, 1)) != BVC_OK) return rc;
     if ((rc = upload_plane(c, c->in_pool, cur)) != BVC_OK) return rc;
     MeLane ml{};
     FrameLane fl{};
-    ml.cur_plane = 0; fl.cur_plane = 0;
+    ml.cur_plane = 0; fl.cur_plane = 0; fl.slot = 0;
     ml.nref = fl.nref = intra ? 0 : nref_avail;
     std::vector<int> hp;
     for (int k = 0; k < ml.nref; k++) {
@@ -472,7 +493,7 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
         c->launches += 1;
     } else {
         c->ev_used = 0; c->spans.clear();
-        if ((rc = enqueue_step(c, sp, 0, true)) != BVC_OK) return rc;
+        if ((rc = enqueue_step(c, sp, true)) != BVC_OK) return rc;
     }
     // ---- downloads ----
     std::vector<int4> hmv;
@@ -487,7 +508,7 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
     }
     long long fb[2] = {0, 0};
     if (!me_only) {
-        CK(cudaMemcpyAsync(fb, c->d_frame_bits[0], sizeof fb, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(fb, c->d_frame_bits, sizeof fb, cudaMemcpyDeviceToHost, c->st));
     }
     CK(cudaStreamSynchronize(c->st));
     if (!intra) {
@@ -519,8 +540,8 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
     const size_t pb = (size_t)((fb[0] + 7) / 8), cb = (size_t)((fb[1] + 7) / 8);
     if ((out->pred_bytes && pb > out->pred_cap) || (out->coef_bytes && cb > out->coef_cap))
         return fail(c, BVC_ERR_NOMEM, "output bit buffer too small");
-    if (out->pred_bytes && pb) CK(cudaMemcpyAsync(out->pred_bytes, c->d_pred_stream[0], pb, cudaMemcpyDeviceToHost, c->st));
-    if (out->coef_bytes && cb) CK(cudaMemcpyAsync(out->coef_bytes, c->d_coef_stream[0], cb, cudaMemcpyDeviceToHost, c->st));
+    if (out->pred_bytes && pb) CK(cudaMemcpyAsync(out->pred_bytes, c->d_pred_stream, pb, cudaMemcpyDeviceToHost, c->st));
+    if (out->coef_bytes && cb) CK(cudaMemcpyAsync(out->coef_bytes, c->d_coef_stream, cb, cudaMemcpyDeviceToHost, c->st));
     if (out->recon && (rc = download_plane(c, out->recon, plane_ptr(c, fl.out_plane))) != BVC_OK) return rc;
     if (out->levels) CK(cudaMemcpyAsync(out->levels, c->d_levels, (size_t)g.W * g.H * 2, cudaMemcpyDeviceToHost, c->st));
     if (out->resid_mc) CK(cudaMemcpyAsync(out->resid_mc, c->d_resid_mc, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, c->st));
@@ -626,11 +647,6 @@ extern "C" int bvc_clip_upload(bvc_ctx* c, const uint8_t* frames, int nframes) {
     return BVC_OK;
 }
 
-struct FrameRec {
-    size_t pred_off = 0, coef_off = 0;  // offsets into the pinned staging arena
-    long long pred_bits = 0, coef_bits = 0;
-};
-
 static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
                             uint8_t* recon) {
     const Geom& g = c->g;
@@ -641,8 +657,10 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     const int nwaves = (ngop + G - 1) / G;
     int rc;
     if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+    if ((rc = ensure_streams(c, (size_t)nframes)) != BVC_OK) return rc;
+    if ((rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
 
-    // ---- plan: one step per (wave, k) ----
+    // ---- plan: one step per (wave, k); lane l of a step = GOP (wave*G + l) ----
     std::vector<StepPlan> steps;
     std::vector<MeLane> mel;
     std::vector<FrameLane> frl;
@@ -662,6 +680,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
                 MeLane ml{};
                 FrameLane fl{};
                 ml.cur_plane = fl.cur_plane = f;
+                fl.slot = f;
                 const int nav = std::min(k, c->p.nref_frames);  // deque(maxlen=nRef), cleared at the I frame
                 ml.nref = fl.nref = nav;
                 for (int j = 0; j < nav; j++) {
@@ -683,93 +702,79 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     }
     const size_t nsteps = steps.size();
     if ((rc = ensure_lane_desc(c, mel.size())) != BVC_OK) return rc;
-    if ((rc = ensure_pinned(c, &c->h_desc, &c->h_desc_cap, mel.size() * (sizeof(MeLane) + sizeof(FrameLane)))) != BVC_OK) return rc;
+    if ((rc = ensure_pinned(c, &c->h_desc, &c->h_desc_cap, mel.size() * (sizeof(MeLane) + sizeof(FrameLane)) + 64)) != BVC_OK) return rc;
     memcpy(c->h_desc, mel.data(), mel.size() * sizeof(MeLane));
     memcpy((uint8_t*)c->h_desc + mel.size() * sizeof(MeLane), frl.data(), frl.size() * sizeof(FrameLane));
     CK(cudaMemcpyAsync(c->d_me_lanes, c->h_desc, mel.size() * sizeof(MeLane), cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->d_fr_lanes, (uint8_t*)c->h_desc + mel.size() * sizeof(MeLane), frl.size() * sizeof(FrameLane),
                        cudaMemcpyHostToDevice, c->st));
-    if ((rc = ensure_pinned(c, (void**)&c->h_bits, &c->h_bits_cap, nsteps * (size_t)G * 2 * sizeof(long long))) != BVC_OK) return rc;
     if (c->p.frac_me) {
         for (size_t s = 0; s < nsteps; s++)
             if ((rc = upload_halfpel_desc(c, step_outplane[s], steps[s].desc_off)) != BVC_OK) return rc;
     }
+    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st));
 
+    c->ev_used = 0;
+    c->spans.clear();
     cudaEvent_t ev_clip0, ev_clip1;
     CK(cudaEventCreate(&ev_clip0));
     CK(cudaEventCreate(&ev_clip1));
     CK(cudaEventRecord(ev_clip0, c->st));
-    // ---- input: whole-clip upload ----
-    if (host_frames) {
-        if (g.pitch == g.W && g.plane_bytes == (size_t)g.W * g.H) {
-            // chunked so that compute on early frames overlaps later copies (copy stream + events)
-            CK(cudaMemcpyAsync(c->in_pool, host_frames, (size_t)nframes * g.plane_bytes, cudaMemcpyHostToDevice, c->st));
-        } else {
-            for (int f = 0; f < nframes; f++)
-                CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W,
-                                     g.H, cudaMemcpyHostToDevice, c->st));
-        }
-    }
-
-    std::vector<cudaEvent_t> ev_bits(nsteps), ev_copy(nsteps);
-    for (size_t s = 0; s < nsteps; s++) {
-        CK(cudaEventCreateWithFlags(&ev_bits[s], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_copy[s], cudaEventDisableTiming));
-    }
-    c->ev_used = 0;
-    c->spans.clear();
-
-    std::vector<FrameRec> recs(nframes);
-    size_t stage_used = 0;
-    // staging arena: grow geometrically; streams are small next to the planes
-    if ((rc = ensure_pinned(c, (void**)&c->h_stage, &c->h_stage_cap, std::max((size_t)nframes * g.W * g.H / 4, (size_t)16 << 20))) != BVC_OK)
-        return rc;
-
-    auto drain = [&](size_t s) -> int {  // host side of step s: learn sizes, enqueue the payload copies
-        CK(cudaEventSynchronize(ev_bits[s]));
-        const int par = (int)(s & 1);
-        const long long* hb = c->h_bits + s * (size_t)G * 2;
-        for (int l = 0; l < steps[s].nl; l++) {
-            FrameRec& r = recs[step_frames[s][l]];
-            r.pred_bits = hb[2 * l];
-            r.coef_bits = hb[2 * l + 1];
-            const size_t pb = (size_t)((r.pred_bits + 7) / 8), cb = (size_t)((r.coef_bits + 7) / 8);
-            if (stage_used + pb + cb + 16 > c->h_stage_cap) return fail(c, BVC_ERR_NOMEM, "stream staging arena exhausted");
-            r.pred_off = stage_used;
-            r.coef_off = stage_used + ((pb + 7) & ~(size_t)7);
-            stage_used = r.coef_off + ((cb + 7) & ~(size_t)7);
-            if (pb) CK(cudaMemcpyAsync(c->h_stage + r.pred_off, (uint8_t*)(c->d_pred_stream[par] + (size_t)l * c->pred_cap_words), pb,
-                                       cudaMemcpyDeviceToHost, c->st_copy));
-            if (cb) CK(cudaMemcpyAsync(c->h_stage + r.coef_off, (uint8_t*)(c->d_coef_stream[par] + (size_t)l * c->coef_cap_words), cb,
-                                       cudaMemcpyDeviceToHost, c->st_copy));
-        }
-        CK(cudaEventRecord(ev_copy[s], c->st_copy));
+    // ---- input: uploaded step by step on its own stream so the copies overlap compute ----
+    std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps : 0);
+    auto enqueue_upload = [&](size_t s) -> int {
+        if (!host_frames || s >= nsteps) return BVC_OK;
+        for (int f : step_frames[s])
+            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
+                                 cudaMemcpyHostToDevice, c->st_h2d));
+        CK(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_h2d[s], c->st_h2d));
         return BVC_OK;
     };
+    if (host_frames) {
+        CK(cudaStreamWaitEvent(c->st_h2d, ev_clip0, 0));
+        for (size_t s = 0; s < 3; s++)
+            if ((rc = enqueue_upload(s)) != BVC_OK) return rc;
+    }
 
+    // ---- the whole clip is enqueued without a single host wait ----
     for (size_t s = 0; s < nsteps; s++) {
-        const int par = (int)(s & 1);
-        // the stream buffers of this parity were last used by step s-2: its D2H must be done
-        if (s >= 2) CK(cudaStreamWaitEvent(c->st, ev_copy[s - 2], 0));
-        if ((rc = enqueue_step(c, steps[s], par, false)) != BVC_OK) return rc;
+        if (host_frames) {
+            CK(cudaStreamWaitEvent(c->st, ev_h2d[s], 0));
+            if ((rc = enqueue_upload(s + 3)) != BVC_OK) return rc;
+        }
+        if ((rc = enqueue_step(c, steps[s], false)) != BVC_OK) return rc;
         // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
         if ((rc = enqueue_halfpel(c, steps[s].desc_off, steps[s].nl)) != BVC_OK) return rc;
-        CK(cudaMemcpyAsync(c->h_bits + s * (size_t)G * 2, c->d_frame_bits[par], (size_t)steps[s].nl * 2 * sizeof(long long),
-                           cudaMemcpyDeviceToHost, c->st));
-        CK(cudaEventRecord(ev_bits[s], c->st));
         if (recon) {
             for (int l = 0; l < steps[s].nl; l++)
                 if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]))) != BVC_OK)
                     return rc;
         }
-        CK(cudaStreamWaitEvent(c->st_copy, ev_bits[s], 0));
-        if (s >= 1 && (rc = drain(s - 1)) != BVC_OK) return rc;
     }
-    if ((rc = drain(nsteps - 1)) != BVC_OK) return rc;
-    CK(cudaStreamWaitEvent(c->st, ev_copy[nsteps - 1], 0));
-    CK(cudaEventRecord(ev_clip1, c->st));
-    CK(cudaStreamSynchronize(c->st_copy));
+    // ---- container (encoder.py:104-121) assembled on the device, one download ----
+    ContainerArgs ca{};
+    ca.frame_bits = c->d_frame_bits; ca.coef_stream = c->d_coef_stream; ca.pred_stream = c->d_pred_stream;
+    ca.coef_cap_words = c->coef_cap_words; ca.pred_cap_words = c->pred_cap_words;
+    ca.frame_off = c->d_frame_off; ca.overflow = c->d_overflow;
+    ca.out = c->d_container; ca.out_cap = (long long)out_cap;
+    ca.nframes = nframes; ca.i_period = IP;
+    const int ec0 = tick(c);
+    CK(launch_container(ca, c->st));
+    span(c, BVC_K_PACK, ec0, tick(c));
+    c->launches += 2;
+    long long total = 0;
+    int overflow = 0;
+    CK(cudaMemcpyAsync(&total, c->d_frame_off + nframes, sizeof total, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&overflow, c->d_overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    for (auto e : ev_h2d) cudaEventDestroy(e);
+    if (overflow) { cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1); return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field"); }
+    if ((size_t)total > out_cap) { cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1); return fail(c, BVC_ERR_NOMEM, "output buffer too small"); }
+    CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaEventRecord(ev_clip1, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    *out_len = (size_t)total;
 
     // ---- instrumentation ----
     for (int i = 0; i < BVC_NUM_KERNEL_CLASSES; i++) { c->last_ms[i] = 0; c->last_launches[i] = 0; }
@@ -783,22 +788,6 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         c->last_clip_ms = ms;
         cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1);
     }
-    for (size_t s = 0; s < nsteps; s++) { cudaEventDestroy(ev_bits[s]); cudaEventDestroy(ev_copy[s]); }
-
-    // ---- container (encoder.py:104-121): host-side concatenation in frame order ----
-    size_t o = 0;
-    for (int f = 0; f < nframes; f++) {
-        const FrameRec& r = recs[f];
-        const size_t pb = (size_t)((r.pred_bits + 7) / 8), cb = (size_t)((r.coef_bits + 7) / 8);
-        if (pb > 0xFFFF || cb > 0xFFFFFF) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
-        if (o + 6 + pb + cb > out_cap) return fail(c, BVC_ERR_NOMEM, "output buffer too small");
-        out[o++] = (f % IP == 0) ? 1 : 0;  // PredictionMode: INTRA_FRAME = 1, INTER_FRAME = 0
-        out[o++] = (uint8_t)(pb >> 8); out[o++] = (uint8_t)pb;
-        memcpy(out + o, c->h_stage + r.pred_off, pb); o += pb;
-        out[o++] = (uint8_t)(cb >> 16); out[o++] = (uint8_t)(cb >> 8); out[o++] = (uint8_t)cb;
-        memcpy(out + o, c->h_stage + r.coef_off, cb); o += cb;
-    }
-    *out_len = o;
     return BVC_OK;
 }
 

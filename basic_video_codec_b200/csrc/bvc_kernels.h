@@ -26,6 +26,7 @@ struct MeArgs {
     int nphase;                    // 1 or 4
     int Rh;                        // range in MV units (= R*sc)
     int win_pitch, win_copy_bytes, win_lm; // filled by the launcher
+    int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
 };
 struct MeTileCfg {
     bool tiled;
@@ -54,6 +55,7 @@ cudaError_t launch_halfpel_interleave(const uint8_t* phases, int W, int H, int p
 // ---- K5 / K6 / K7: transform, reconstruction, intra wavefront, entropy ---------------------------
 struct FrameLane {
     int cur_plane;                 // input pool index
+    int slot;                      // per-frame slot of the stream arena (= frame index inside a clip call)
     int out_plane;                 // reference-pool plane receiving the reconstruction
     int nref;
     int ref_plane[BVC_MAX_REFS];
@@ -98,9 +100,10 @@ struct PackArgs {
     const int32_t* blk_nbits;
     int blk_words;
     long long* coef_off;             // device [lanes][nblk+1]  exclusive bit offsets (out)
-    uint32_t* coef_stream;         // device [lanes][coef_cap_words]
-    uint32_t* pred_stream;         // device [lanes][pred_cap_words]
-    long long* frame_bits;           // device [lanes][2] = (pred_bits, coef_bits) (out)
+    const FrameLane* lanes;        // device [lanes] (slot = where this frame's streams go)
+    uint32_t* coef_stream;         // device [slots][coef_cap_words]
+    uint32_t* pred_stream;         // device [slots][pred_cap_words]
+    long long* frame_bits;           // device [slots][2] = (pred_bits, coef_bits) (out)
     long long* row_bits;             // device [lanes][bh] (out) bits_per_row
     long long* pred_row_off;         // device [lanes][bh+1] scratch: prediction-stream offset of every row start
     size_t coef_cap_words, pred_cap_words;
@@ -110,5 +113,19 @@ struct PackArgs {
     int with_ref;                  // nRefFrames > 1: code the reference index difference
 };
 cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
+
+// ---- container assembly ---------------------------------------------------------------------------
+struct ContainerArgs {
+    const long long* frame_bits;   // device [nframes][2]
+    const uint32_t* coef_stream;   // device [nframes][coef_cap_words]
+    const uint32_t* pred_stream;
+    size_t coef_cap_words, pred_cap_words;
+    long long* frame_off;          // device [nframes+1] byte offset of every frame record (out), total at the end
+    int* overflow;                 // device flag: a payload does not fit its length field
+    uint8_t* out;                  // device container image
+    long long out_cap;
+    int nframes, i_period;
+};
+cudaError_t launch_container(const ContainerArgs& a, cudaStream_t st);
 
 }  // namespace bvc

@@ -29,8 +29,11 @@
 //     rotate through compile-time slots; the row loop is unrolled BS deep in three variants (ramp-up,
 //     steady, ramp-down) so no candidate outside [-R,R] is ever evaluated: executed VABSDIFF4 count
 //     equals the algorithmic count exactly.
-//   * argmin: per thread a strict-less scan on (SAD<<9 | L1); per pass merged with the full 64-bit
-//     key (SAD, L1, ref, mvy, mvx); per block a shared-memory 64-bit atomicMin.
+//   * argmin: per thread one IMAD (FMA pipe) + one VIMNMX per candidate on a packed key
+//     (SAD | L1 | m); per pass merged with the full 64-bit key (SAD, L1, ref, mvy, mvx); per block a
+//     shared-memory 64-bit atomicMin.
+//   * the last candidate column (dx = +R) of every block would leave a warp 1/32 full; it is given to
+//     one extra warp that splits it into vertical segments, so lane utilisation stays ~98 %.
 #include "bvc_common.cuh"
 #include "bvc_kernels.h"
 
@@ -68,15 +71,30 @@ __device__ __forceinline__ void load_cur(CurBlock<BS>& c, const uint8_t* p, int 
     }
 }
 
-enum { BODY_FIRST = 0, BODY_MID = 1, BODY_LAST = 2, BODY_ONLY = 3 };
+enum { BODY_FIRST = 0, BODY_MID = 1, BODY_LAST = 2 };
 
-// One unrolled body of BS window rows.  `rowp` points at this thread's first word of window row
-// body*BS; `wpitch` is the window pitch in words.  mb = m of the candidate completing at t = 0 minus..:
-// candidate completing after row t has m = mbase + t.
-template <int BS, int MODE>
-__device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp,
-                                        int wpitch, int mbase, int mlo, int mhi, int mvy0, int sc, uint32_t absmx,
-                                        uint32_t& best, uint32_t& bestm) {
+// Per-pass constants of the per-thread argmin.
+//   PACKED : key = SAD << (l1bits+mbits) | L1 << mbits | m   -- one IMAD + one VIMNMX per candidate;
+//            usable when the three fields fit 32 bits (always for the headline configurations).
+//   general: key = SAD << 9 | L1, m tracked separately (strict-less keeps the first m).
+struct KeyCfg {
+    uint32_t scale;   // PACKED: 1 << (l1bits + mbits)
+    int mbits;        // PACKED: bits of the m field
+};
+
+__device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));  // IMAD: FMA pipe, not the ALU pipe
+    return d;
+}
+
+// One unrolled body of BS window rows.  `rowp` points at this thread's first word of the body's first
+// window row; `wpitch` is the window pitch in words.  The candidate completing after row t has
+// m = mbase + t (m = vertical offset + R).
+template <int BS, int MODE, bool PACKED>
+__device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp, int wpitch,
+                                        int mbase, int mlo, int mhi, int mvy0, int sc, uint32_t tthr, uint32_t one,
+                                        const KeyCfg kc, uint32_t& best, uint32_t& bestm) {
     constexpr int WPR = BS / 4;
 #pragma unroll
     for (int t = 0; t < BS; t++) {
@@ -92,7 +110,6 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
                 if (MODE == BODY_FIRST) on = (j <= t);
                 if (MODE == BODY_LAST) on = (j >= t);
                 if (on) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int slot = (t - j) & (BS - 1);
                     // first word of a fresh candidate (j == 0, wi == 0) starts from zero: no reset needed
                     acc[slot] = sad4(w[wi], cur.w[j][wi], (j == 0 && wi == 0) ? 0u : acc[slot]);
@@ -103,16 +120,25 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
         const bool completes = (MODE != BODY_FIRST) || (t == BS - 1);
         if (completes) {
             const int slot = (t + 1) & (BS - 1);
-            const int m = mbase + t;
-            const int mvy = mvy0 + sc * m;
-            const uint32_t key = (acc[slot] << 9) + absmx + (uint32_t)abs(mvy);
-            if (m >= mlo && m <= mhi && key < best) { best = key; bestm = (uint32_t)m; }
+            const int m = mbase + t;                       // warp-uniform
+            const uint32_t amvy = (uint32_t)abs(mvy0 + sc * m);  // warp-uniform
+            if (PACKED) {
+                const uint32_t u = (amvy << kc.mbits) | (uint32_t)m;       // uniform datapath
+                const uint32_t key = imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr));
+                if (m >= mlo && m <= mhi) best = min(best, key);           // uniform predicate on one VIMNMX
+            } else {
+                const uint32_t key = imad_u32(acc[slot], 512u, imad_u32(one, amvy, tthr));
+                if (m >= mlo && m <= mhi && key < best) { best = key; bestm = (uint32_t)m; }
+            }
         }
     }
 }
 
-// Tiled full-search kernel.  grid = (ceil(bw/NB), bh, lanes).  Dynamic smem: 4 shifted window copies.
-template <int BS, int NB>
+// Tiled full-search kernel.  grid = (ceil(bw/NB), bh, lanes).  Dynamic smem: the TMA window + 3 shifted copies.
+// Threads: NB*2R "main" threads (one per candidate column dx in [-R, R-1], all 2R+1 vertical offsets)
+// plus one extra warp that covers the last column dx = +R of every block, split into vertical segments
+// of BS+1 candidates (ramp-up + ramp-down body only), so no warp idles on a 1/32-full column.
+template <int BS, int NB, bool PACKED>
 __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -120,20 +146,34 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
 
     const int tid = threadIdx.x;
     const int R = a.R;
-    const int ncx = 2 * R + 1;
     const int rows = BS + 2 * R;
     const int WW = a.win_pitch;               // bytes, multiple of 16
-    const int copy_bytes = a.win_copy_bytes;  // WW*rows rounded up to 128
+    const int copy_stride = a.win_copy_bytes + 32;  // +32 B: copy k starts 8 banks after copy k-1 (conflict-free LDS)
     const int bx0 = blockIdx.x * NB;
     const int by = blockIdx.y;
     const int lane = blockIdx.z;
     const MeLane& L = a.lanes[lane];
 
-    const int b = tid / ncx;
-    const int cxi = tid - b * ncx;
-    const bool active = (b < NB) && (bx0 + b < a.bw);
+    const int nmain = NB * 2 * R;
+    const int xbase = (nmain + 31) & ~31;     // first thread of the extra warp
+    const int nseg = (2 * R + 1 + BS) / (BS + 1);
+    const bool is_extra = tid >= xbase;
+    int b, dx, m0 = 0;
+    bool active;
+    if (!is_extra) {
+        b = tid / (2 * R);
+        dx = tid - b * 2 * R - R;
+        active = tid < nmain;
+    } else {
+        const int e = tid - xbase;
+        b = e / nseg;
+        const int seg = e - b * nseg;
+        dx = R;
+        m0 = min(seg * (BS + 1), 2 * R - BS);  // overlapping the previous segment is harmless for an argmin
+        active = b < NB;
+    }
+    active = active && (bx0 + b < a.bw);
     const int ox = (bx0 + b) * BS, oy = by * BS;
-    const int dx = cxi - R;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -146,9 +186,15 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     __syncthreads();
 
     // this thread's window column (left edge of the candidate) and the aligned copy it reads
-    const int X = a.win_lm + b * BS + cxi;
-    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_bytes) + (X >> 2);
+    const int X = a.win_lm + b * BS + dx + R;
     const int wpitch = WW >> 2;
+    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2) + m0 * wpitch;
+
+    uint32_t one;
+    asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque 1 so `one*u + t` stays an IMAD
+    KeyCfg kc;
+    kc.mbits = a.key_mbits;
+    kc.scale = 1u << (a.key_mbits + a.key_l1bits);
 
     uint32_t best_hi = 0xFFFFFFFFu, best_lo = 0xFFFFFFFFu;
     uint32_t parity = 0;
@@ -166,9 +212,9 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             parity ^= 1u;
             {   // byte-shifted copies 1..3 of the window
                 const uint32_t* c0 = reinterpret_cast<const uint32_t*>(smem);
-                uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_bytes);
-                uint32_t* c2 = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)copy_bytes);
-                uint32_t* c3 = reinterpret_cast<uint32_t*>(smem + 3 * (size_t)copy_bytes);
+                uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_stride);
+                uint32_t* c2 = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)copy_stride);
+                uint32_t* c3 = reinterpret_cast<uint32_t*>(smem + 3 * (size_t)copy_stride);
                 const int nw = (WW * rows) >> 2;
                 for (int w = tid; w < nw; w += blockDim.x) {
                     const uint32_t lo = c0[w], hi = c0[w + 1];
@@ -187,27 +233,38 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                 const bool xvalid = (ox + dx >= 0) && (ox + dx + BS <= a.W - px) && (dx <= R - px);
                 if (xvalid) {
                     const uint32_t absmx = (uint32_t)abs(mvx);
+                    const uint32_t tthr = PACKED ? (absmx << kc.mbits) : absmx;
                     const int mvy0 = py - a.sc * R;  // mvy = mvy0 + sc*m
                     uint32_t acc[BS];
 #pragma unroll
                     for (int i = 0; i < BS; i++) acc[i] = 0;
                     uint32_t best = 0xFFFFFFFFu, bestm = 0;
+                    // main threads: ramp-up, nmid steady bodies, ramp-down over all 2R+1 offsets;
+                    // extra-warp threads: ramp-up + ramp-down over the BS+1 offsets starting at m0
                     const uint32_t* rowp = colp;
-                    if (nmid >= 0) {
-                        me_body<BS, BODY_FIRST>(cur, acc, rowp, wpitch, -(BS - 1), mlo, mhi, mvy0, a.sc, absmx, best, bestm);
+                    int mbase = m0 - (BS - 1);
+                    const int nm = is_extra ? 0 : nmid;
+                    me_body<BS, BODY_FIRST, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                    rowp += BS * wpitch;
+                    mbase += BS;
+                    for (int i = 0; i < nm; i++) {
+                        me_body<BS, BODY_MID, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
                         rowp += BS * wpitch;
-                        int mbase = 1;
-                        for (int i = 0; i < nmid; i++) {
-                            me_body<BS, BODY_MID>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, absmx, best, bestm);
-                            rowp += BS * wpitch;
-                            mbase += BS;
-                        }
-                        me_body<BS, BODY_LAST>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, absmx, best, bestm);
+                        mbase += BS;
                     }
+                    me_body<BS, BODY_LAST, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
                     if (best != 0xFFFFFFFFu) {
+                        uint32_t hi;
+                        if (PACKED) {
+                            bestm = best & ((1u << kc.mbits) - 1u);
+                            const uint32_t l1 = (best >> kc.mbits) & ((1u << a.key_l1bits) - 1u);
+                            hi = ((best >> (kc.mbits + a.key_l1bits)) << 9) | l1;
+                        } else {
+                            hi = best;
+                        }
                         const int mvy = mvy0 + a.sc * (int)bestm;
                         const uint32_t lo = ((uint32_t)r << 20) | ((uint32_t)(mvy + a.Rh) << 10) | (uint32_t)(mvx + a.Rh);
-                        if (best < best_hi || (best == best_hi && lo < best_lo)) { best_hi = best; best_lo = lo; }
+                        if (hi < best_hi || (hi == best_hi && lo < best_lo)) { best_hi = hi; best_lo = lo; }
                     }
                 }
             }
@@ -274,29 +331,40 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     }
 }
 
-template <int BS, int NB>
-cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+template <int BS, int NB, bool PACKED>
+cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     const int R = a.R;
-    const int ncx = 2 * R + 1;
-    const int threads = ((NB * ncx + 31) / 32) * 32;
+    const int nmain = NB * 2 * R;
+    const int threads = ((nmain + 31) & ~31) + 32;
     const MeTileCfg cfg = me_tile_config(BS, R);
     a.win_pitch = cfg.win_pitch;
     a.win_lm = cfg.win_lm;
     a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
-    const size_t smem = 4 * (size_t)a.win_copy_bytes + 16;
+    const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + 16;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid((a.bw + NB - 1) / NB, a.bh, lanes);
-    me_tiled_kernel<BS, NB><<<grid, threads, smem, st>>>(map, a);
+    me_tiled_kernel<BS, NB, PACKED><<<grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
 }
 
+static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
+
+template <int BS, int NB>
+cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+    // packed 32-bit key: SAD | L1 | m
+    const int sadbits = bitlen(255u * BS * BS);
+    a.key_l1bits = bitlen(2u * a.Rh);
+    a.key_mbits = bitlen(2u * a.R);
+    if (sadbits + a.key_l1bits + a.key_mbits <= 32) return launch_tiled_p<BS, NB, true>(map, a, lanes, st);
+    return launch_tiled_p<BS, NB, false>(map, a, lanes, st);
+}
+
 int pick_nb(int bs, int R) {
-    const int ncx = 2 * R + 1;
     // as many blocks per CTA as fit 544 threads / 256-byte TMA boxes / ~100 KB of windows, so that
     // two CTAs are resident per SM and one CTA's TMA wait hides behind the other's arithmetic.
     // NB*BS is kept a multiple of 16 so the left margin of the aligned TMA box is the same for every CTA
@@ -307,7 +375,9 @@ int pick_nb(int bs, int R) {
     for (int i = 0; i < n; i++) {
         const int nb = c[i];
         const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
-        if (nb * ncx <= 544 && pitch <= 256 && 4 * pitch * (bs + 2 * R) <= 110 * 1024) return nb;
+        if (((nb * 2 * R + 31) & ~31) + 32 <= 544 && nb * ((2 * R + 1 + bs) / (bs + 1)) <= 32 && pitch <= 256 &&
+            4 * pitch * (bs + 2 * R) <= 110 * 1024)
+            return nb;
     }
     return 0;
 }

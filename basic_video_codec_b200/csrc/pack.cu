@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
     const int b0 = tid * chunk, b1 = min(a.nblk, b0 + chunk);
     const int32_t* nb = a.blk_nbits + (size_t)fl * a.nblk;
     long long* coff = a.coef_off + (size_t)fl * (a.nblk + 1);
-    uint32_t* cstream = a.coef_stream + (size_t)fl * a.coef_cap_words;
-    uint32_t* pstream = a.pred_stream + (size_t)fl * a.pred_cap_words;
+    const int slot = a.lanes[fl].slot;   // per-frame slot in the stream arena
+    uint32_t* cstream = a.coef_stream + (size_t)slot * a.coef_cap_words;
+    uint32_t* pstream = a.pred_stream + (size_t)slot * a.pred_cap_words;
 
     // ---- coefficient stream offsets ----
     long long csum = 0;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
     for (int b = b0; b < b1; b++) { PredCode pc = pred_code(a, fl, b); psum += pc.len + pc.qlen; }
     long long ptot;
     long long ppre = block_exscan(psum, warp_sums, &ptot);
-    if (tid == 0) { a.frame_bits[2 * fl] = ptot; a.frame_bits[2 * fl + 1] = ctot; }
+    if (tid == 0) { a.frame_bits[2 * slot] = ptot; a.frame_bits[2 * slot + 1] = ctot; }
 
     // ---- zero the used part of both streams (+2 words of slack for the 3-word OR window) ----
     const long long cw = min((long long)a.coef_cap_words, ((ctot + 31) >> 5) + 2);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) 
     const int nbits = a.blk_nbits[(size_t)fl * a.nblk + b];
     const long long D = a.coef_off[(size_t)fl * (a.nblk + 1) + b];
     const uint32_t* src = a.blk_bits + ((size_t)fl * a.nblk + b) * a.blk_words;
-    uint32_t* dst = a.coef_stream + (size_t)fl * a.coef_cap_words;
+    uint32_t* dst = a.coef_stream + (size_t)a.lanes[fl].slot * a.coef_cap_words;
     const int n = (nbits + 31) >> 5;
     const int sh = (int)(D & 31);
     const long long w0 = D >> 5;
@@ -173,6 +174,72 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) 
         const uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
         if (v) atomicOr(&dst[w0 + j], __byte_perm(v, 0, 0x0123));
     }
+}
+
+
+// ---- container assembly (encoder.py:104-121) on the device ---------------------------------------
+// Per frame: mode byte | 2-byte BE prediction length | prediction bytes | 3-byte BE coefficient length |
+// coefficient bytes.  container_scan_kernel turns the per-frame bit counts into byte offsets (one CTA);
+// container_copy_kernel writes headers and copies payloads, so the host receives the finished
+// encoded.bin image with a single download.
+__global__ void __launch_bounds__(1024) container_scan_kernel(ContainerArgs a) {
+    __shared__ long long warp_sums[33];
+    const int tid = threadIdx.x;
+    const int chunk = (a.nframes + 1023) / 1024;
+    const int f0 = tid * chunk, f1 = min(a.nframes, f0 + chunk);
+    long long sum = 0;
+    int bad = 0;
+    for (int f = f0; f < f1; f++) {
+        const long long pb = (a.frame_bits[2 * f] + 7) >> 3, cb = (a.frame_bits[2 * f + 1] + 7) >> 3;
+        if (pb > 0xFFFF || cb > 0xFFFFFF) bad = 1;   // OverflowError in the reference (int.to_bytes)
+        sum += 6 + pb + cb;
+    }
+    long long tot;
+    long long pre = block_exscan(sum, warp_sums, &tot);
+    for (int f = f0; f < f1; f++) {
+        a.frame_off[f] = pre;
+        pre += 6 + ((a.frame_bits[2 * f] + 7) >> 3) + ((a.frame_bits[2 * f + 1] + 7) >> 3);
+    }
+    if (tid == 0) a.frame_off[a.nframes] = tot;
+    if (bad) atomicExch(a.overflow, 1);
+}
+
+__global__ void __launch_bounds__(256) container_copy_kernel(ContainerArgs a) {
+    const int f = blockIdx.y;
+    const long long pb = (a.frame_bits[2 * f] + 7) >> 3, cb = (a.frame_bits[2 * f + 1] + 7) >> 3;
+    const long long off = a.frame_off[f];
+    if (off + 6 + pb + cb > a.out_cap) return;       // host reports BVC_ERR_NOMEM from frame_off[nframes]
+    uint8_t* o = a.out + off;
+    const uint8_t* ps = reinterpret_cast<const uint8_t*>(a.pred_stream + (size_t)f * a.pred_cap_words);
+    const uint8_t* cs = reinterpret_cast<const uint8_t*>(a.coef_stream + (size_t)f * a.coef_cap_words);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        o[0] = (uint8_t)((f % a.i_period == 0) ? 1 : 0);   // PredictionMode: INTRA_FRAME = 1, INTER_FRAME = 0
+        o[1] = (uint8_t)(pb >> 8); o[2] = (uint8_t)pb;
+        o[3 + pb] = (uint8_t)(cb >> 16); o[4 + pb] = (uint8_t)(cb >> 8); o[5 + pb] = (uint8_t)cb;
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t; i < pb; i += stride) o[3 + i] = ps[i];
+    uint8_t* oc = o + 6 + pb;
+    // coefficient payload: 16-byte vector copies once the destination is aligned
+    const long long head = min(cb, (long long)((16 - ((uintptr_t)oc & 15)) & 15));
+    for (long long i = t; i < head; i += stride) oc[i] = cs[i];
+    const long long nvec = (cb - head) >> 4;
+    for (long long v = t; v < nvec; v += stride) {
+        const uint8_t* src = cs + head + (v << 4);
+        uint4 val;
+        if ((((uintptr_t)src) & 3) == 0) {
+            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+            val = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = src[4 * k] | (src[4 * k + 1] << 8) | (src[4 * k + 2] << 16) | ((uint32_t)src[4 * k + 3] << 24);
+            val = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>(oc + head + (v << 4)) = val;
+    }
+    for (long long i = head + (nvec << 4) + t; i < cb; i += stride) oc[i] = cs[i];
 }
 
 }  // namespace
@@ -186,4 +253,15 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+}  // namespace bvc
+
+namespace bvc {
+cudaError_t launch_container(const ContainerArgs& a, cudaStream_t st) {
+    container_scan_kernel<<<1, 1024, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 grid(32, a.nframes);
+    container_copy_kernel<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
 }  // namespace bvc
