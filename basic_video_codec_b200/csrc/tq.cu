@@ -23,7 +23,7 @@ struct TqCtaSmem {
 // ---------------------------------------------------------------------------------------------
 // P frames: every block independent.  grid = (ceil(nblk / (TQ_WARPS*NBW)), lanes)
 template <int BS>
-__global__ void __launch_bounds__(TQ_WARPS * 32) tq_pframe_kernel(TqArgs a) {
+__global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a) {
     constexpr int NBW = 32 / BS;
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
@@ -52,10 +52,11 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) tq_pframe_kernel(TqArgs a) {
         dy = mv.y >> 1;
     }
     const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(oy + dy + x) * a.ref_pitch + (ox + dx);
-#pragma unroll
-    for (int i = 0; i < BS; i++) {
-        t.cur[q][x][i] = cur[i];
-        t.pred[q][x][i] = pr[i];
+    {
+        uint32_t cw[BS / 4], pw[BS / 4];
+        load_row_aligned<BS>(cur, cw);
+        load_row_unaligned<BS>(pr, pw);
+        stage_row<BS>(t, q, x, cw, pw);
     }
     if (a.resid_nomc && valid) {
         // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     struct ISmem {
         WarpTile<BS> t;
         uint8_t zz[BS * BS];
-        uint8_t left[NBW][BS];
-        uint8_t top[NBW][BS];
+        __align__(16) uint8_t left[NBW][BS];
+        __align__(16) uint8_t top[NBW][BS];
     };
     ISmem& sm = *reinterpret_cast<ISmem*>(smraw);
     const int lane = threadIdx.x;
@@ -137,8 +138,9 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         sm.left[q][x] = (uint8_t)lv;
         sm.top[q][x] = (uint8_t)tv;
         const uint8_t* cur = cur_plane + (size_t)(oy + x) * a.cur_pitch + ox;
-#pragma unroll
-        for (int i = 0; i < BS; i++) t.cur[q][x][i] = cur[i];
+        uint32_t cw[BS / 4];
+        load_row_aligned<BS>(cur, cw);
+        store_row_words<BS>(&t.cur[q][x][0], cw);
         __syncwarp();
         // mode decision, IFrame.py:184-195.  In-frame predictors are uint8, so cur - pred wraps mod 256
         // (:189-190); border predictors are int64 128, a true absolute difference.
@@ -156,8 +158,13 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
             sv += __shfl_xor_sync(0xffffffffu, sv, d);
         }
         const int mode = (sh < sv) ? 0 : 1;  // tie -> vertical, IFrame.py:192-195
+        {
+            // mode 0: row x of pred = left[0..BS-1]; mode 1: row x = top[x] replicated
+            uint32_t pw[BS / 4];
 #pragma unroll
-        for (int i = 0; i < BS; i++) t.pred[q][x][i] = mode == 0 ? sm.left[q][i] : (uint8_t)tv;
+            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i] : (uint32_t)tv * 0x01010101u;
+            stage_row<BS>(t, q, x, cw, pw);
+        }
         if (valid && x == 0) {
             a.modes[(size_t)fl * a.nblk + by * a.bw + bx] = mode;
             a.isad[(size_t)fl * a.nblk + by * a.bw + bx] = mode == 0 ? sh : sv;

@@ -15,12 +15,14 @@
 
 namespace bvc {
 
-__constant__ double c_ct4[16] = BVC_CT4_INIT;
-__constant__ double c_ct8[64] = BVC_CT8_INIT;
-__constant__ double c_ct16[256] = BVC_CT16_INIT;
-__constant__ double c_w4[3] = BVC_W4_INIT;
-__constant__ double c_w8[3] = BVC_W8_INIT;
-__constant__ double c_w16[3] = BVC_W16_INIT;
+// const-qualified device tables: every index is a compile-time constant after unrolling, so the
+// compiler folds the loads and the cosines become immediate / constant-bank operands of the DFMAs.
+__device__ static const double c_ct4[16] = BVC_CT4_INIT;
+__device__ static const double c_ct8[64] = BVC_CT8_INIT;
+__device__ static const double c_ct16[256] = BVC_CT16_INIT;
+__device__ static const double c_w4[3] = BVC_W4_INIT;
+__device__ static const double c_w8[3] = BVC_W8_INIT;
+__device__ static const double c_w16[3] = BVC_W16_INIT;
 
 template <int BS> struct DctC;
 template <> struct DctC<4>  { static __device__ __forceinline__ double ct(int i) { return c_ct4[i]; }  static __device__ __forceinline__ double w(int i) { return c_w4[i]; } };
@@ -38,9 +40,10 @@ template <int BS>
 struct WarpTile {
     static constexpr int NBW = 32 / BS;
     double buf[NBW][BS][BS + 1];
-    int16_t lev[NBW][BS][BS];
-    uint8_t cur[NBW][BS][BS];
-    uint8_t pred[NBW][BS][BS];
+    __align__(16) int16_t lev[NBW][BS][BS];
+    __align__(16) int16_t res[NBW][BS][BS];   // residual cur - pred (PFrame.py:248 / IFrame.py:222)
+    __align__(16) uint8_t cur[NBW][BS][BS];
+    __align__(16) uint8_t pred[NBW][BS][BS];
     uint32_t bits[blk_words_for<BS>() + 4];
 };
 
@@ -89,10 +92,68 @@ struct TqOut {
     double* coef_out;  // block hook only
 };
 
-// Transform + quantise + reconstruct the NBW blocks held in `t` (cur/pred filled, or residual given by
-// res_override for the block hook).  lane -> (q, x).  `valid` masks warps' trailing blocks.
-// qp: quantisation parameter of this block row.  Writes lev tile (smem) and the outputs in `o[q]`.
-// intra_u8_resid: I frames store the raw int16 residual as uint8 in the debug plane (IFrame.py:30,57-58).
+// vector helpers for one block row of BS bytes / BS int16
+template <int BS> struct RowVec;
+template <> struct RowVec<16> { using B = uint4; static constexpr int NW = 4; };
+template <> struct RowVec<8>  { using B = uint2; static constexpr int NW = 2; };
+template <> struct RowVec<4>  { using B = uint32_t; static constexpr int NW = 1; };
+
+template <int BS>
+__device__ __forceinline__ void load_row_aligned(const uint8_t* p, uint32_t (&w)[BS / 4]) {
+    typename RowVec<BS>::B v = *reinterpret_cast<const typename RowVec<BS>::B*>(p);
+    if constexpr (BS == 16) { w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+    else if constexpr (BS == 8) { w[0] = v.x; w[1] = v.y; }
+    else { w[0] = v; }
+}
+// BS bytes from an arbitrary byte address: aligned 32-bit loads + funnel shifts
+template <int BS>
+__device__ __forceinline__ void load_row_unaligned(const uint8_t* p, uint32_t (&w)[BS / 4]) {
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(ad & 3) * 8;
+    uint32_t raw[BS / 4 + 1];
+#pragma unroll
+    for (int i = 0; i <= BS / 4; i++) raw[i] = base[i];
+#pragma unroll
+    for (int i = 0; i < BS / 4; i++) w[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+}
+template <int BS>
+__device__ __forceinline__ void store_row_words(void* dst, const uint32_t (&w)[BS / 4]) {
+    if constexpr (BS == 16) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else if constexpr (BS == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint32_t*>(dst) = w[0];
+}
+
+// Stage row r of block q: cur and pred bytes (as words) -> t.cur / t.pred / t.res (int16 residual).
+template <int BS>
+__device__ __forceinline__ void stage_row(WarpTile<BS>& t, int q, int r, const uint32_t (&cw)[BS / 4], const uint32_t (&pw)[BS / 4]) {
+    store_row_words<BS>(&t.cur[q][r][0], cw);
+    store_row_words<BS>(&t.pred[q][r][0], pw);
+    uint32_t rw[BS / 2];
+#pragma unroll
+    for (int i = 0; i < BS / 4; i++) {
+        // bytes -> two packed int16 differences per word pair
+        const uint32_t c_lo = __byte_perm(cw[i], 0, 0x4140), c_hi = __byte_perm(cw[i], 0, 0x4342);
+        const uint32_t p_lo = __byte_perm(pw[i], 0, 0x4140), p_hi = __byte_perm(pw[i], 0, 0x4342);
+        rw[2 * i] = __vsub2(c_lo, p_lo);
+        rw[2 * i + 1] = __vsub2(c_hi, p_hi);
+    }
+    uint32_t* d = reinterpret_cast<uint32_t*>(&t.res[q][r][0]);
+    if constexpr (BS == 16) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+        *reinterpret_cast<uint4*>(d + 4) = make_uint4(rw[4], rw[5], rw[6], rw[7]);
+    } else if constexpr (BS == 8) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+    } else {
+        *reinterpret_cast<uint2*>(d) = make_uint2(rw[0], rw[1]);
+    }
+}
+
+// Transform + quantise + reconstruct the NBW blocks held in `t` (t.res and t.pred staged, or dense
+// int16 residual / pred given by the overrides for the block hook).  lane -> (q, x).  `valid` masks a
+// warp's trailing blocks.  qp: quantisation parameter of this block row.  Writes the lev tile (smem)
+// and the outputs in `o`.  intra_u8_resid: I frames store the raw int16 residual as uint8 in the debug
+// plane (IFrame.py:30,57-58).
 template <int BS>
 __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, int qp, const TqOut& o,
                                         const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid) {
@@ -100,10 +161,7 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
     double a[BS], r[BS];
     // ---- forward pass 1: columns (apply_dct_2d transforms columns first, dct.py:12) ----
 #pragma unroll
-    for (int y = 0; y < BS; y++) {
-        if (res_override) a[y] = (double)res_override[y * BS + x];
-        else a[y] = (double)((int)t.cur[q][y][x] - (int)t.pred[q][y][x]);  // PFrame.py:248 / IFrame.py:222
-    }
+    for (int y = 0; y < BS; y++) a[y] = (double)(res_override ? (int)res_override[y * BS + x] : (int)t.res[q][y][x]);
     if (intra_u8_resid && o.resid_mc && valid) {
 #pragma unroll
         for (int y = 0; y < BS; y++) o.resid_mc[(size_t)y * o.resid_pitch + x] = (int8_t)(uint8_t)(int)a[y];
@@ -120,8 +178,6 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
     const bool su = (u == 0) || (2 * u == BS);
     const double w_sp = su ? DctC<BS>::w(0) : DctC<BS>::w(1);  // for v in {0, BS/2}
     const double w_nm = su ? DctC<BS>::w(1) : DctC<BS>::w(2);
-    const double inv0 = pow2_neg(qp), inv1 = pow2_neg(qp + 1), inv2 = pow2_neg(qp + 2);
-    const double q0 = pow2_pos(qp), q1 = pow2_pos(qp + 1), q2 = pow2_pos(qp + 2);
     short lv[BS];
 #pragma unroll
     for (int v = 0; v < BS; v++) {
@@ -129,28 +185,40 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         const double w = sv ? w_sp : w_nm;
         const double coef = __dmul_rn(r[v], w);
         if (o.coef_out && valid) o.coef_out[u * BS + v] = coef;
-        // generate_quantization_matrix dct.py:21-32 ; quantize_block :35-37 (round half to even)
-        const int d = u + v - (BS - 1);
-        const double inv = d < 0 ? inv0 : (d == 0 ? inv1 : inv2);
-        const double qs = d < 0 ? q0 : (d == 0 ? q1 : q2);
-        const double lq = rint(__dmul_rn(coef, inv));
+        // generate_quantization_matrix dct.py:21-32: shift s = qp + {0,1,2} for u+v <,=,> BS-1;
+        // quantize_block :35-37 = round half to even of coef * 2^-s (exact scaling)
+        const int s = qp + min(max(u + v - (BS - 2), 0), 2);
+        const double lq = rint(__dmul_rn(coef, pow2_neg(s)));
         lv[v] = (short)(int)lq;
-        // rescale_block dct.py:40-42 (exact) then the inverse transform's input scaling
-        a[v] = __dmul_rn(__dmul_rn(lq, qs), w);
+        // rescale_block dct.py:40-42 is exact, so (lq * 2^s) * w == lq * (w * 2^s) with one rounding
+        const double wq = __hiloint2double(__double2hiint(w) + (s << 20), __double2loint(w));
+        a[v] = __dmul_rn(lq, wq);
+    }
+    {
+        uint32_t pk[BS / 2];
+#pragma unroll
+        for (int v = 0; v < BS / 2; v++) pk[v] = (uint32_t)(uint16_t)lv[2 * v] | ((uint32_t)(uint16_t)lv[2 * v + 1] << 16);
+        uint32_t* ls = reinterpret_cast<uint32_t*>(&t.lev[q][u][0]);
+        uint32_t* lg = (o.levels && valid) ? reinterpret_cast<uint32_t*>(o.levels + (size_t)u * o.lev_pitch) : nullptr;
+        if constexpr (BS == 16) {
+            *reinterpret_cast<uint4*>(ls) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(ls + 4) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (lg) { *reinterpret_cast<uint4*>(lg) = make_uint4(pk[0], pk[1], pk[2], pk[3]); *reinterpret_cast<uint4*>(lg + 4) = make_uint4(pk[4], pk[5], pk[6], pk[7]); }
+        } else if constexpr (BS == 8) {
+            *reinterpret_cast<uint4*>(ls) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (lg) *reinterpret_cast<uint4*>(lg) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+            *reinterpret_cast<uint2*>(ls) = make_uint2(pk[0], pk[1]);
+            if (lg) *reinterpret_cast<uint2*>(lg) = make_uint2(pk[0], pk[1]);
+        }
     }
 #pragma unroll
-    for (int v = 0; v < BS; v++) { t.lev[q][u][v] = lv[v]; t.buf[q][u][v] = a[v]; }
-    if (o.levels && valid) {
-        int16_t* lp = o.levels + (size_t)u * o.lev_pitch;
-#pragma unroll
-        for (int v = 0; v < BS; v++) lp[v] = lv[v];
-    }
+    for (int v = 0; v < BS; v++) t.buf[q][u][v] = a[v];
     __syncwarp();
     // ---- inverse pass 1: over u for column v = x ----
 #pragma unroll
     for (int i = 0; i < BS; i++) a[i] = t.buf[q][i][x];
     fold_inv<BS>(a, r);
-    __syncwarp();
 #pragma unroll
     for (int y = 0; y < BS; y++) t.buf[q][y][x] = r[y];
     __syncwarp();
@@ -160,16 +228,21 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
     for (int i = 0; i < BS; i++) a[i] = t.buf[q][y][i];
     fold_inv<BS>(a, r);
     if (valid) {
+        uint32_t pw[BS / 4];
+        if (!pred_override) load_row_aligned<BS>(&t.pred[q][y][0], pw);
+        uint32_t ow[BS / 4];
 #pragma unroll
         for (int i = 0; i < BS; i++) {
-            const double p = pred_override ? (double)pred_override[y * BS + i] : (double)t.pred[q][y][i];
+            const int pb = pred_override ? (int)pred_override[y * BS + i] : (int)((pw[i >> 2] >> (8 * (i & 3))) & 255u);
             // reconstruct_block Frame.py:197-202: round(idct + pred) -> int16 -> clip -> uint8
-            const int v = (int)(short)(int)rint(__dadd_rn(r[i], p));
-            o.recon[(size_t)y * o.rec_pitch + i] = (uint8_t)min(max(v, 0), 255);
+            const int v = (int)(short)(int)rint(__dadd_rn(r[i], (double)pb));
+            const uint32_t c8 = (uint32_t)min(max(v, 0), 255);
+            if ((i & 3) == 0) ow[i >> 2] = c8; else ow[i >> 2] |= c8 << (8 * (i & 3));
             if (o.idct_out) o.idct_out[y * BS + i] = r[i];
             // PFrame.py:39,63: float64 idct residual stored into an int8 plane (C cast: truncate, wrap)
             if (!intra_u8_resid && o.resid_mc) o.resid_mc[(size_t)y * o.resid_pitch + i] = (int8_t)(int)r[i];
         }
+        store_row_words<BS>(o.recon + (size_t)y * o.rec_pitch, ow);
     }
     __syncwarp();
 }
