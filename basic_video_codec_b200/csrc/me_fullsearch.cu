@@ -91,10 +91,14 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 // One unrolled body of BS window rows.  `rowp` points at this thread's first word of the body's first
 // window row; `wpitch` is the window pitch in words.  The candidate completing after row t has
 // m = mbase + t (m = vertical offset + R).
+//   PACKED : `utab[m]` (shared memory, rebuilt per pass) holds (|mvy(m)| << mbits) | m, with bit 31 set
+//            when the vertical offset leaves the plane, so a finished candidate costs one LDS, two IMAD
+//            (FMA pipe) and ONE ALU-pipe instruction (VIMNMX); no compare, select or branch.
+//   general: per-thread arithmetic (used only when SAD | L1 | m does not fit 31 bits).
 template <int BS, int MODE, bool PACKED>
 __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp, int wpitch,
-                                        int mbase, int mlo, int mhi, int mvy0, int sc, uint32_t tthr, uint32_t one,
-                                        const KeyCfg kc, uint32_t& best, uint32_t& bestm) {
+                                        int mbase, const uint32_t* utab_m, int mlo, int mhi, int mvy0, int sc, uint32_t tthr,
+                                        uint32_t one, const KeyCfg kc, uint32_t& best, uint32_t& bestm) {
     constexpr int WPR = BS / 4;
 #pragma unroll
     for (int t = 0; t < BS; t++) {
@@ -120,13 +124,12 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
         const bool completes = (MODE != BODY_FIRST) || (t == BS - 1);
         if (completes) {
             const int slot = (t + 1) & (BS - 1);
-            const int m = mbase + t;                       // warp-uniform
-            const uint32_t amvy = (uint32_t)abs(mvy0 + sc * m);  // warp-uniform
             if (PACKED) {
-                const uint32_t u = (amvy << kc.mbits) | (uint32_t)m;       // uniform datapath
-                const uint32_t key = imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr));
-                if (m >= mlo && m <= mhi) best = min(best, key);           // uniform predicate on one VIMNMX
+                const uint32_t u = utab_m[t];   // utab_m = utab + mbase (per thread)
+                best = min(best, imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr)));
             } else {
+                const int m = mbase + t;
+                const uint32_t amvy = (uint32_t)abs(mvy0 + sc * m);
                 const uint32_t key = imad_u32(acc[slot], 512u, imad_u32(one, amvy, tthr));
                 if (m >= mlo && m <= mhi && key < best) { best = key; bestm = (uint32_t)m; }
             }
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ unsigned long long sbest[NB];
+    __shared__ uint32_t utab[2 * 128 + 1 + 2 * BS];   // per-pass candidate table, indexed by m + BS (m in [-(BS-1), 2R+BS])
 
     const int tid = threadIdx.x;
     const int R = a.R;
@@ -210,6 +214,16 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             }
             mbar_wait(&bar, parity);
             parity ^= 1u;
+            if (PACKED) {
+                // utab[m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane
+                const int mlo = max(0, R - oy);
+                const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                for (int i = tid; i < 2 * R + 1 + 2 * BS; i += blockDim.x) {
+                    const int m = i - BS;
+                    const uint32_t amvy = (uint32_t)abs(py - a.sc * R + a.sc * m);
+                    utab[i] = (m >= mlo && m <= mhi) ? ((amvy << kc.mbits) | (uint32_t)m) : 0x80000000u;
+                }
+            }
             {   // byte-shifted copies 1..3 of the window
                 const uint32_t* c0 = reinterpret_cast<const uint32_t*>(smem);
                 uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_stride);
@@ -243,17 +257,20 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                     // extra-warp threads: ramp-up + ramp-down over the BS+1 offsets starting at m0
                     const uint32_t* rowp = colp;
                     int mbase = m0 - (BS - 1);
+                    const uint32_t* ut = utab + BS + mbase;
                     const int nm = is_extra ? 0 : nmid;
-                    me_body<BS, BODY_FIRST, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                    me_body<BS, BODY_FIRST, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
                     rowp += BS * wpitch;
                     mbase += BS;
+                    ut += BS;
                     for (int i = 0; i < nm; i++) {
-                        me_body<BS, BODY_MID, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                        me_body<BS, BODY_MID, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
                         rowp += BS * wpitch;
                         mbase += BS;
+                        ut += BS;
                     }
-                    me_body<BS, BODY_LAST, PACKED>(cur, acc, rowp, wpitch, mbase, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
-                    if (best != 0xFFFFFFFFu) {
+                    me_body<BS, BODY_LAST, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                    if (PACKED ? (best < 0x80000000u) : (best != 0xFFFFFFFFu)) {
                         uint32_t hi;
                         if (PACKED) {
                             bestm = best & ((1u << kc.mbits) - 1u);
@@ -360,7 +377,7 @@ cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream
     const int sadbits = bitlen(255u * BS * BS);
     a.key_l1bits = bitlen(2u * a.Rh);
     a.key_mbits = bitlen(2u * a.R);
-    if (sadbits + a.key_l1bits + a.key_mbits <= 32) return launch_tiled_p<BS, NB, true>(map, a, lanes, st);
+    if (sadbits + a.key_l1bits + a.key_mbits <= 31 && a.R <= 128) return launch_tiled_p<BS, NB, true>(map, a, lanes, st);
     return launch_tiled_p<BS, NB, false>(map, a, lanes, st);
 }
 
