@@ -30,7 +30,8 @@ struct MeArgs {
 };
 struct MeTileCfg {
     bool tiled;
-    int nb;         // blocks per CTA
+    int nb;         // blocks per CTA, side by side
+    int nby;        // block rows per CTA, stacked
     int win_pitch;  // TMA box width in bytes
     int rows;       // TMA box height
     int win_lm;     // left margin: window column of x0-R inside the 16-byte aligned box

@@ -137,32 +137,38 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
     }
 }
 
-// Tiled full-search kernel.  grid = (ceil(bw/NB), bh, lanes).  Dynamic smem: the TMA window + 3 shifted copies.
-// Threads: NB*2R "main" threads (one per candidate column dx in [-R, R-1], all 2R+1 vertical offsets)
-// plus one extra warp that covers the last column dx = +R of every block, split into vertical segments
-// of BS+1 candidates (ramp-up + ramp-down body only), so no warp idles on a 1/32-full column.
-template <int BS, int NB, bool PACKED>
+// Tiled full-search kernel.  One CTA = NB x NBY blocks (NB side by side, NBY stacked); grid =
+// (ceil(bw/NB), ceil(bh/NBY), lanes).  Dynamic smem: the TMA window (NBY*BS+2R rows) + 3 shifted copies +
+// the CTA's current blocks.
+// Threads: NB*2R "main" threads, one per candidate column dx in [-R, R-1] of one block column; each slides
+// over all 2R+1 vertical offsets once per stacked block row (current block reloaded into registers from
+// shared memory).  The last column dx = +R of every block would leave a warp 1/32 full: it is split into
+// vertical segments of BS+1 candidates (ramp-up + ramp-down body only) and all NB*NBY*nseg segments are
+// packed into extra warps that run once per window, so lane utilisation stays ~98 % and -- with NBY
+// stacked rows per CTA -- the extra warps weigh little against the main warps of their SM sub-partition.
+template <int BS, int NB, int NBY, bool PACKED>
 __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
-    __shared__ unsigned long long sbest[NB];
-    __shared__ uint32_t utab[2 * 128 + 1 + 2 * BS];   // per-pass candidate table, indexed by m + BS (m in [-(BS-1), 2R+BS])
+    __shared__ unsigned long long sbest[NBY][NB];
+    __shared__ uint32_t utab[NBY][2 * 128 + 1 + 2 * BS];   // per-pass candidate tables, indexed by m + BS
 
     const int tid = threadIdx.x;
     const int R = a.R;
-    const int rows = BS + 2 * R;
+    const int rows = NBY * BS + 2 * R;
     const int WW = a.win_pitch;               // bytes, multiple of 16
     const int copy_stride = a.win_copy_bytes + 32;  // +32 B: copy k starts 8 banks after copy k-1 (conflict-free LDS)
     const int bx0 = blockIdx.x * NB;
-    const int by = blockIdx.y;
+    const int by0 = blockIdx.y * NBY;
     const int lane = blockIdx.z;
     const MeLane& L = a.lanes[lane];
+    uint8_t* scur = smem + 4 * (size_t)copy_stride;   // [NBY*BS][NB*BS] current pixels of the CTA's blocks
 
     const int nmain = NB * 2 * R;
-    const int xbase = (nmain + 31) & ~31;     // first thread of the extra warp
+    const int xbase = (nmain + 31) & ~31;     // first thread of the extra warps
     const int nseg = (2 * R + 1 + BS) / (BS + 1);
     const bool is_extra = tid >= xbase;
-    int b, dx, m0 = 0;
+    int b, dx, m0 = 0, yye = 0;
     bool active;
     if (!is_extra) {
         b = tid / (2 * R);
@@ -170,29 +176,42 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
         active = tid < nmain;
     } else {
         const int e = tid - xbase;
-        b = e / nseg;
-        const int seg = e - b * nseg;
+        yye = e / (NB * nseg);
+        const int e2 = e - yye * NB * nseg;
+        b = e2 / nseg;
+        const int seg = e2 - b * nseg;
         dx = R;
         m0 = min(seg * (BS + 1), 2 * R - BS);  // overlapping the previous segment is harmless for an argmin
-        active = b < NB;
+        active = yye < NBY;
     }
     active = active && (bx0 + b < a.bw);
-    const int ox = (bx0 + b) * BS, oy = by * BS;
+    const int ox = (bx0 + b) * BS;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
-    if (tid < NB) sbest[tid] = ~0ull;
-
-    CurBlock<BS> cur;
-    if (active) load_cur<BS>(cur, a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)oy * a.cur_pitch + ox, a.cur_pitch);
+    for (int i = tid; i < NB * NBY; i += blockDim.x) sbest[i / NB][i % NB] = ~0ull;
+    {   // stage the current blocks (NB*BS x NBY*BS bytes) in shared memory, 16 B per thread-iteration
+        const uint8_t* cp = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
+        constexpr int VPR = NB * BS / 16 > 0 ? NB * BS / 16 : 1;   // 16-byte vectors per row
+        constexpr int RB = NB * BS;                               // bytes per staged row
+        if constexpr (RB % 16 == 0) {
+            for (int i = tid; i < NBY * BS * VPR; i += blockDim.x) {
+                const int y = i / VPR, v = i - y * VPR;
+                const int gy = by0 * BS + y, gx = bx0 * BS + v * 16;
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (gy < a.H && gx < a.W) val = *reinterpret_cast<const uint4*>(cp + (size_t)gy * a.cur_pitch + gx);
+                *reinterpret_cast<uint4*>(scur + y * RB + v * 16) = val;
+            }
+        }
+    }
     __syncthreads();
 
     // this thread's window column (left edge of the candidate) and the aligned copy it reads
     const int X = a.win_lm + b * BS + dx + R;
     const int wpitch = WW >> 2;
-    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2) + m0 * wpitch;
+    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2);
 
     uint32_t one;
     asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque 1 so `one*u + t` stays an IMAD
@@ -200,7 +219,6 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     kc.mbits = a.key_mbits;
     kc.scale = 1u << (a.key_mbits + a.key_l1bits);
 
-    uint32_t best_hi = 0xFFFFFFFFu, best_lo = 0xFFFFFFFFu;
     uint32_t parity = 0;
     const int nmid = (2 * R) / BS - 1;
 
@@ -210,20 +228,23 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             if (tid == 0) {
                 mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
                 // box origin: 16-byte aligned column (bx0*BS - R - win_lm), rows <= 256
-                tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, oy - R, L.ref_plane[r] + ph);
+                tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r] + ph);
+            }
+            if (PACKED) {
+                // utab[yy][m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane
+                const int per = 2 * R + 1 + 2 * BS;
+                for (int i = tid; i < NBY * per; i += blockDim.x) {
+                    const int yy = i / per, ii = i - yy * per;
+                    const int oy = (by0 + yy) * BS;
+                    const int mlo = max(0, R - oy);
+                    const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                    const int m = ii - BS;
+                    const uint32_t amvy = (uint32_t)abs(py - a.sc * R + a.sc * m);
+                    utab[yy][ii] = (m >= mlo && m <= mhi) ? ((amvy << kc.mbits) | (uint32_t)m) : 0x80000000u;
+                }
             }
             mbar_wait(&bar, parity);
             parity ^= 1u;
-            if (PACKED) {
-                // utab[m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane
-                const int mlo = max(0, R - oy);
-                const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
-                for (int i = tid; i < 2 * R + 1 + 2 * BS; i += blockDim.x) {
-                    const int m = i - BS;
-                    const uint32_t amvy = (uint32_t)abs(py - a.sc * R + a.sc * m);
-                    utab[i] = (m >= mlo && m <= mhi) ? ((amvy << kc.mbits) | (uint32_t)m) : 0x80000000u;
-                }
-            }
             {   // byte-shifted copies 1..3 of the window
                 const uint32_t* c0 = reinterpret_cast<const uint32_t*>(smem);
                 uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_stride);
@@ -239,25 +260,28 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             }
             __syncthreads();
 
-            if (active) {
-                // vertical validity interval in m = dy + R; horizontal validity is per thread
-                const int mlo = max(0, R - oy);
-                const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
-                const int mvx = a.sc * dx + px;
-                const bool xvalid = (ox + dx >= 0) && (ox + dx + BS <= a.W - px) && (dx <= R - px);
-                if (xvalid) {
-                    const uint32_t absmx = (uint32_t)abs(mvx);
-                    const uint32_t tthr = PACKED ? (absmx << kc.mbits) : absmx;
-                    const int mvy0 = py - a.sc * R;  // mvy = mvy0 + sc*m
+            const int mvx = a.sc * dx + px;
+            const bool xvalid = active && (ox + dx >= 0) && (ox + dx + BS <= a.W - px) && (dx <= R - px);
+            if (xvalid) {
+                const uint32_t absmx = (uint32_t)abs(mvx);
+                const uint32_t tthr = PACKED ? (absmx << kc.mbits) : absmx;
+                const int mvy0 = py - a.sc * R;  // mvy = mvy0 + sc*m
+                // main threads: every stacked block row; extra threads: their one (row, segment)
+                const int yy_lo = is_extra ? yye : 0, yy_hi = is_extra ? yye + 1 : NBY;
+                for (int yy = yy_lo; yy < yy_hi; yy++) {
+                    if (by0 + yy >= a.bh) break;
+                    const int oy = (by0 + yy) * BS;
+                    const int mlo = max(0, R - oy);
+                    const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                    CurBlock<BS> cur;
+                    load_cur<BS>(cur, scur + (size_t)yy * BS * (NB * BS) + b * BS, NB * BS);
                     uint32_t acc[BS];
 #pragma unroll
                     for (int i = 0; i < BS; i++) acc[i] = 0;
                     uint32_t best = 0xFFFFFFFFu, bestm = 0;
-                    // main threads: ramp-up, nmid steady bodies, ramp-down over all 2R+1 offsets;
-                    // extra-warp threads: ramp-up + ramp-down over the BS+1 offsets starting at m0
-                    const uint32_t* rowp = colp;
+                    const uint32_t* rowp = colp + (yy * BS + m0) * wpitch;
                     int mbase = m0 - (BS - 1);
-                    const uint32_t* ut = utab + BS + mbase;
+                    const uint32_t* ut = &utab[yy][0] + BS + mbase;
                     const int nm = is_extra ? 0 : nmid;
                     me_body<BS, BODY_FIRST, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
                     rowp += BS * wpitch;
@@ -281,25 +305,25 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                         }
                         const int mvy = mvy0 + a.sc * (int)bestm;
                         const uint32_t lo = ((uint32_t)r << 20) | ((uint32_t)(mvy + a.Rh) << 10) | (uint32_t)(mvx + a.Rh);
-                        if (hi < best_hi || (hi == best_hi && lo < best_lo)) { best_hi = hi; best_lo = lo; }
+                        atomicMin(&sbest[yy][b], ((unsigned long long)hi << 32) | lo);
                     }
                 }
             }
             __syncthreads();  // everyone is done with the window before the next TMA overwrites it
         }
     }
-    if (active && best_hi != 0xFFFFFFFFu)
-        atomicMin(&sbest[b], ((unsigned long long)best_hi << 32) | best_lo);
-    __syncthreads();
-    if (tid < NB && bx0 + tid < a.bw) {
-        const unsigned long long k = sbest[tid];
-        const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
-        int4 o;
-        o.x = (int)(lo & 1023u) - a.Rh;
-        o.y = (int)((lo >> 10) & 1023u) - a.Rh;
-        o.z = (int)(lo >> 20);
-        o.w = (int)(hi >> 9);
-        a.out[(size_t)lane * a.nblk + (size_t)by * a.bw + bx0 + tid] = o;
+    for (int i = tid; i < NB * NBY; i += blockDim.x) {
+        const int yy = i / NB, bb = i - yy * NB;
+        if (bx0 + bb < a.bw && by0 + yy < a.bh) {
+            const unsigned long long k = sbest[yy][bb];
+            const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
+            int4 o;
+            o.x = (int)(lo & 1023u) - a.Rh;
+            o.y = (int)((lo >> 10) & 1023u) - a.Rh;
+            o.z = (int)(lo >> 20);
+            o.w = (int)(hi >> 9);
+            a.out[(size_t)lane * a.nblk + (size_t)(by0 + yy) * a.bw + bx0 + bb] = o;
+        }
     }
 }
 
@@ -348,72 +372,85 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     }
 }
 
-template <int BS, int NB, bool PACKED>
+template <int BS, int NB, int NBY, bool PACKED>
 cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     const int R = a.R;
     const int nmain = NB * 2 * R;
-    const int threads = ((nmain + 31) & ~31) + 32;
+    const int nseg = (2 * R + 1 + BS) / (BS + 1);
+    const int threads = ((nmain + 31) & ~31) + ((NB * NBY * nseg + 31) & ~31);
     const MeTileCfg cfg = me_tile_config(BS, R);
     a.win_pitch = cfg.win_pitch;
     a.win_lm = cfg.win_lm;
     a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
-    const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + 16;
+    const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + (size_t)NBY * BS * NB * BS + 16;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    dim3 grid((a.bw + NB - 1) / NB, a.bh, lanes);
-    me_tiled_kernel<BS, NB, PACKED><<<grid, threads, smem, st>>>(map, a);
+    dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, lanes);
+    me_tiled_kernel<BS, NB, NBY, PACKED><<<grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
 }
 
 static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
 
-template <int BS, int NB>
+template <int BS, int NB, int NBY>
 cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
-    // packed 32-bit key: SAD | L1 | m
+    // packed key: SAD | L1 | m in 31 bits (bit 31 marks offsets outside the plane)
     const int sadbits = bitlen(255u * BS * BS);
     a.key_l1bits = bitlen(2u * a.Rh);
     a.key_mbits = bitlen(2u * a.R);
-    if (sadbits + a.key_l1bits + a.key_mbits <= 31 && a.R <= 128) return launch_tiled_p<BS, NB, true>(map, a, lanes, st);
-    return launch_tiled_p<BS, NB, false>(map, a, lanes, st);
+    if (sadbits + a.key_l1bits + a.key_mbits <= 31 && a.R <= 128) return launch_tiled_p<BS, NB, NBY, true>(map, a, lanes, st);
+    return launch_tiled_p<BS, NB, NBY, false>(map, a, lanes, st);
 }
 
-int pick_nb(int bs, int R) {
-    // as many blocks per CTA as fit 544 threads / 256-byte TMA boxes / ~100 KB of windows, so that
-    // two CTAs are resident per SM and one CTA's TMA wait hides behind the other's arithmetic.
-    // NB*BS is kept a multiple of 16 so the left margin of the aligned TMA box is the same for every CTA
+// Tile shape: NB blocks side by side (NB*BS a multiple of 16 so the left margin of the aligned TMA box is
+// the same for every CTA) and NBY stacked.  Constraints: <= 544 threads (two CTAs per SM at 96 registers),
+// TMA box <= 256 x 256, four window copies <= ~100 KB so that two CTAs fit an SM.
+struct TileShape { int nb, nby; };
+TileShape pick_shape(int bs, int R) {
     const int cand16[] = {4, 2, 1}, cand8[] = {8, 4, 2}, cand4[] = {8, 4, 4};
     const int* c = bs == 16 ? cand16 : bs == 8 ? cand8 : cand4;
-    const int n = 3;
     const int lm = (16 - R % 16) % 16;
-    for (int i = 0; i < n; i++) {
+    const int nseg = (2 * R + 1 + bs) / (bs + 1);
+    for (int i = 0; i < 3; i++) {
         const int nb = c[i];
         const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
-        if (((nb * 2 * R + 31) & ~31) + 32 <= 544 && nb * ((2 * R + 1 + bs) / (bs + 1)) <= 32 && pitch <= 256 &&
-            4 * pitch * (bs + 2 * R) <= 110 * 1024)
-            return nb;
+        const int nbys[] = {4, 2, 1};
+        for (int j = 0; j < 3; j++) {
+            const int nby = nbys[j];
+            const int rows = nby * bs + 2 * R;
+            const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
+            if (threads <= 544 && pitch <= 256 && rows <= 256 && 4 * pitch * rows + nb * nby * bs * bs <= 100 * 1024) return {nb, nby};
+        }
     }
-    return 0;
+    return {0, 0};
 }
 
 }  // namespace
 
 MeTileCfg me_tile_config(int bs, int R) {
-    MeTileCfg c{false, 0, 0, 0, 0};
+    MeTileCfg c{false, 0, 0, 0, 0, 0};
     if (!(bs == 4 || bs == 8 || bs == 16)) return c;
     if (R < 1 || (2 * R) % bs != 0 || 2 * R < bs) return c;
-    if (bs + 2 * R > 256) return c;  // TMA box rows
-    const int nb = pick_nb(bs, R);
-    if (nb == 0) return c;
+    const TileShape t = pick_shape(bs, R);
+    if (t.nb == 0) return c;
     c.tiled = true;
-    c.nb = nb;
+    c.nb = t.nb;
+    c.nby = t.nby;
     c.win_lm = (16 - R % 16) % 16;
-    c.win_pitch = ((c.win_lm + nb * bs + 2 * R + 15) / 16) * 16;
-    c.rows = bs + 2 * R;
+    c.win_pitch = ((c.win_lm + t.nb * bs + 2 * R + 15) / 16) * 16;
+    c.rows = t.nby * bs + 2 * R;
     return c;
+}
+
+template <int BS, int NB>
+static cudaError_t launch_by_nby(const MeTileCfg& cfg, const CUtensorMap& map, const MeArgs& a, int lanes, cudaStream_t st) {
+    if (cfg.nby == 4) return launch_tiled<BS, NB, 4>(map, a, lanes, st);
+    if (cfg.nby == 2) return launch_tiled<BS, NB, 2>(map, a, lanes, st);
+    return launch_tiled<BS, NB, 1>(map, a, lanes, st);
 }
 
 cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
@@ -422,16 +459,16 @@ cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args,
     const MeTileCfg cfg = me_tile_config(a.bs, a.R);
     if (cfg.tiled && ref_map) {
         if (a.bs == 16) {
-            if (cfg.nb == 4) return launch_tiled<16, 4>(*ref_map, a, lanes, st);
-            if (cfg.nb == 2) return launch_tiled<16, 2>(*ref_map, a, lanes, st);
-            return launch_tiled<16, 1>(*ref_map, a, lanes, st);
+            if (cfg.nb == 4) return launch_by_nby<16, 4>(cfg, *ref_map, a, lanes, st);
+            if (cfg.nb == 2) return launch_by_nby<16, 2>(cfg, *ref_map, a, lanes, st);
+            return launch_by_nby<16, 1>(cfg, *ref_map, a, lanes, st);
         } else if (a.bs == 8) {
-            if (cfg.nb == 8) return launch_tiled<8, 8>(*ref_map, a, lanes, st);
-            if (cfg.nb == 4) return launch_tiled<8, 4>(*ref_map, a, lanes, st);
-            return launch_tiled<8, 2>(*ref_map, a, lanes, st);
+            if (cfg.nb == 8) return launch_by_nby<8, 8>(cfg, *ref_map, a, lanes, st);
+            if (cfg.nb == 4) return launch_by_nby<8, 4>(cfg, *ref_map, a, lanes, st);
+            return launch_by_nby<8, 2>(cfg, *ref_map, a, lanes, st);
         } else {
-            if (cfg.nb == 8) return launch_tiled<4, 8>(*ref_map, a, lanes, st);
-            return launch_tiled<4, 4>(*ref_map, a, lanes, st);
+            if (cfg.nb == 8) return launch_by_nby<4, 8>(cfg, *ref_map, a, lanes, st);
+            return launch_by_nby<4, 4>(cfg, *ref_map, a, lanes, st);
         }
     }
     dim3 grid(a.bw, a.bh, lanes);
