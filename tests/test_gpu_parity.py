@@ -229,3 +229,127 @@ def test_full_size_1080p_properties():
         assert [p[0] for p in parts] == [1, 0, 0]
         assert recon.shape == frames.shape
         assert ctx.me_work_per_frame(1) == 8527896576
+
+
+# ---- Python drop-in layer --------------------------------------------------------------------------------
+def _run_encode_video(tmp_path, g):
+    from basic_video_codec_b200 import EncoderConfig, InputParameters
+    from basic_video_codec_b200.encoder.encoder import encode_video, output_dir
+    frames, e = g["frames"], g["meta"]["enc"]
+    n, H, W = frames.shape
+    yfile = tmp_path / "clip.y"
+    yfile.write_bytes(frames.tobytes())
+    ec = EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e.get("nref", 1),
+                       fastME=e.get("fastme", False), fracMeEnabled=e.get("frac", False), resolution=(W, H))
+    params = InputParameters(str(yfile), W, H, ec, frames_to_process=n)
+    encode_video(params)
+    return output_dir(params)
+
+
+@pytest.mark.parametrize("name", ["fs_i8_r4_qp3", "fastme_i16_nref4", "frac_fs_i8_r2_nref2", "fs_i16_r2_nref4"])
+def test_encode_video_dropin_writes_reference_files(name, tmp_path):
+    """encode_video(InputParameters) through PFrame/IFrame objects: every side file the reference writes
+    (encoder.py:104-152, file_io.py) is byte-identical to the reference's own output."""
+    import os
+    g = gu.load(name)
+    out = _run_encode_video(tmp_path, g)
+    e = g["meta"]["enc"]
+    sr = -1 if e.get("fastme") else e["search_range"]
+    ident = f'{e["block"]}_{sr}{".0" if e.get("frac") else ""}_{e["qp"]}_{e["i_period"]}_{e.get("nref", 1)}_0_0'
+    assert out.endswith(os.path.join("clip", ident))          # output naming scheme, file_io.py:20-26
+    rd = lambda f: open(os.path.join(out, f), "rb").read()
+    assert rd("encoded.bin") == g["encoded"]
+    assert rd("mc_reconstructed.yuv") == g["recon"].tobytes()
+    assert rd("mc_quant_dct_coff.bin") == g["levels"].tobytes()
+    assert rd("residuals_w_mc.yuv") == g["resid_mc"].tobytes()
+    assert rd("residuals_wo_mc.yuv") == g["resid_nomc"].tobytes()
+    assert open(os.path.join(out, "mv.txt")).read() == g["mv_txt"]
+    rows = open(os.path.join(out, "metrics.csv")).read().strip().splitlines()
+    assert rows[0] == "idx,I-Frame,avg_MAE,mae_comps,PSNR,frame_bytes,file_bits,enc_time,elapsed_time"
+    assert len(rows) == 1 + g["frames"].shape[0]
+    for r, det in zip(rows[1:], g["meta"]["frames"]):
+        f = r.split(",")
+        assert int(f[1]) == det["intra"] and float(f[2]) == det["avg_mae"] and int(f[3]) == det["mae_comparisons"]
+
+
+def test_frame_objects_keep_reference_attribute_protocol():
+    from collections import deque
+    from basic_video_codec_b200 import EncoderConfig
+    from basic_video_codec_b200.encoder.IFrame import IFrame
+    from basic_video_codec_b200.encoder.PFrame import PFrame
+    from basic_video_codec_b200.encoder.PredictionMode import PredictionMode
+    g = gu.load("fs_i16_r2_nref4")
+    frames, e = g["frames"], g["meta"]["enc"]
+    ec = EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e["nref"], resolution=frames.shape[:0:-1])
+    refs = deque(maxlen=e["nref"])
+    fi = IFrame(frames[0])
+    fi.encode_mc_q_dct(ec)
+    assert fi.prediction_mode == PredictionMode.INTRA_FRAME and fi.is_iframe()
+    assert fi.intra_modes == g["meta"]["frames"][0]["modes"]
+    assert len(fi.entropy_encoded_DCT_coffs) == g["meta"]["frames"][0]["coef_nbits"]
+    refs.append(fi.reconstructed_frame)
+    fp = PFrame(frames[1], refs, deque())
+    fp.encode_mc_q_dct(ec)
+    det = g["meta"]["frames"][1]
+    assert fp.is_pframe() and list(fp.mv_field.values()) == det["mv"]
+    assert list(fp.mv_field.keys())[:2] == [(0, 0), (16, 0)]
+    assert fp.bits_per_row == det["bits_per_row"] and fp.total_mae_comparisons == det["mae_comparisons"]
+    assert fp.get_mv_extremes()[0] == np.array(det["mv"]).min(axis=0).tolist()
+    assert fp.get_quat_dct_coffs_extremes() == [g["levels"][1].min(), g["levels"][1].max()]
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------
+EDGE = [
+    # (H, W, bs, r, qp, nref, ip, n, frac, fastme)
+    (16, 16, 16, 8, 3, 1, 2, 3, False, False),     # a single block: every non-zero candidate leaves the frame
+    (16, 48, 16, 32, 3, 2, 3, 4, False, False),    # search range larger than the frame
+    (24, 40, 8, 4, 0, 3, 1, 3, False, False),      # I_Period 1 (all intra), qp 0, width not a multiple of 16
+    (32, 32, 4, 2, 9, 2, 4, 5, False, False),      # qp at the validation limit log2(4)+7
+    (32, 48, 8, 4, 10, 1, 5, 5, True, False),      # half-pel at max qp
+    (32, 48, 16, 4, 5, 4, 8, 7, True, True),       # FastME half-pel, window longer than the clip start
+    (40, 56, 8, 8, 2, 8, 9, 9, False, False),      # 8 reference frames
+]
+
+
+@pytest.mark.parametrize("H,W,bs,r,qp,nref,ip,n,frac,fastme", EDGE)
+def test_edge_cases_match_oracle(H, W, bs, r, qp, nref, ip, n, frac, fastme):
+    ob = _ob()
+    frames = synth.moving_clip(500 + H + W + bs, H, W, n, step=3, clamp=8, blur=3)
+    cfg = ob.make_config(W, H, bs, r, qp, nref=nref, fastme=fastme, frac=frac, i_period=ip)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    with _ctx(W, H, bs, r, qp, nref, fastme, frac, ip, lanes=2) as ctx:
+        got, recon = ctx.encode_clip(frames, want_recon=True)
+    assert np.array_equal(recon, want_recon)
+    assert got == want
+
+
+def test_extreme_content():
+    """Saturated / flat / checkerboard planes: clipping in reconstruction, all-zero blocks, maximal levels."""
+    ob = _ob()
+    H, W, bs = 32, 48, 8
+    rng = np.random.default_rng(5)
+    planes = [np.zeros((H, W), np.uint8), np.full((H, W), 255, np.uint8),
+              ((np.indices((H, W)).sum(0) % 2) * 255).astype(np.uint8), rng.integers(0, 256, (H, W)).astype(np.uint8),
+              np.full((H, W), 255, np.uint8), np.zeros((H, W), np.uint8)]
+    frames = np.stack(planes)
+    for qp in (0, 5):
+        cfg = ob.make_config(W, H, bs, 4, qp, nref=2, i_period=6)
+        want, want_recon = ob.encode_clip(cfg, frames)
+        with _ctx(W, H, bs, 4, qp, 2, False, False, 6) as ctx:
+            got, recon = ctx.encode_clip(frames, want_recon=True)
+        assert got == want and np.array_equal(recon, want_recon)
+
+
+def test_error_mapping():
+    import basic_video_codec_b200 as bvc
+    with pytest.raises(ValueError):
+        bvc.Context(64, 64, 8, 4, 11)          # qp > log2(8)+7  (params.py:29-30)
+    with pytest.raises(ValueError):
+        bvc.Context(8, 8, 16, 4, 3)            # frame smaller than a block (block_predictor.py:70-71)
+    with pytest.raises(NotImplementedError):
+        bvc.Context(60, 64, 8, 4, 3)           # not a multiple of the block size: pad first
+    with _ctx(32, 32, 8, 4, 3) as ctx:
+        with pytest.raises(ValueError):
+            ctx.encode_pframe(np.zeros((32, 32), np.uint8), [])       # empty reference window
+        with pytest.raises(MemoryError):
+            ctx.encode_clip(np.zeros((2, 32, 32), np.uint8), out_capacity=4)
