@@ -57,8 +57,10 @@ def load_reference():
         for p in (REFERENCE_ROOT, _SHIMS):
             if p in sys.path:
                 sys.path.remove(p)
-        sys.path.insert(0, REFERENCE_ROOT)
-        sys.path.insert(0, _SHIMS)
+        # appended, not prepended: the reference has a top-level `tests` package that must not shadow ours
+        # (its hot-path modules -- encoder, common, decoder, file_io, ... -- have no namesakes here)
+        sys.path.append(_SHIMS)
+        sys.path.append(REFERENCE_ROOT)
         # the reference's `tests` package name collides with ours only if imported; we never do.
         importlib.import_module("encoder.encoder")
         importlib.import_module("decoder")
