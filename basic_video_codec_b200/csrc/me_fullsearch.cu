@@ -423,7 +423,7 @@ TileShape pick_shape(int bs, int R) {
             const int nby = nbys[j];
             const int rows = nby * bs + 2 * R;
             const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
-            if (threads <= 544 && pitch <= 256 && rows <= 256 && 4 * pitch * rows + nb * nby * bs * bs <= 100 * 1024) return {nb, nby};
+            if (threads <= 544 && pitch <= 256 && rows <= 256 && 4 * pitch * rows + nb * nby * bs * bs <= 110 * 1024) return {nb, nby};
         }
     }
     return {0, 0};

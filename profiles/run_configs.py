@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Secondary workloads of BASELINE.json (configs 0, 1, 2, 4) on one B200: throughput through the public
+clip API (host buffers), per-kernel device time, and a parity spot check of the first GOP against the CPU
+oracle (GOPs are independent, so the first GOP of the stream must equal the oracle's encoding of it).
+Foreman is not available (git-LFS pointer), so the CIF configs use the synthetic stand-in.
+Usage: python profiles/run_configs.py [name ...]   -> one JSON line per workload."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import basic_video_codec_b200 as bvc  # noqa: E402
+from basic_video_codec_b200.sharding import split_container_by_gop  # noqa: E402
+from oracle import bindings as ob  # noqa: E402
+from tests import synth  # noqa: E402
+
+WORKLOADS = {
+    # name: (W, H, frames, block, r, qp, I_Period, nref, fastme, frac, lanes, synth kwargs)
+    "c0_cif_i8_r4": (352, 288, 10, 8, 4, 3, 8, 1, False, False, 2, dict(step=3, clamp=16)),
+    "c1_cif_fastme_nref4": (352, 288, 300, 16, 16, 3, 8, 4, True, False, 38, dict(step=2, clamp=24)),
+    "c2_cif_halfpel_r4": (352, 288, 296, 16, 4, 3, 8, 1, False, True, 37, dict(step=2, clamp=16)),
+    "c4_4k_r64_nref4": (3840, 2160, 512, 16, 64, 4, 8, 4, False, False, 32, dict(step=3, clamp=48)),
+    "c3_1080p_r32": (1920, 1088, 600, 16, 32, 4, 30, 1, False, False, 20, dict(step=6, clamp=96)),
+}
+
+
+def run(name):
+    W, H, n, bs, r, qp, ip, nref, fastme, frac, lanes, sk = WORKLOADS[name]
+    t0 = time.time()
+    frames = synth.moving_clip(abs(hash(name)) % 1000 + 7, H, W, n, **sk)
+    tgen = time.time() - t0
+    out = np.empty(n * W * H // 2 + (1 << 20), np.uint8)
+    with bvc.Context(W, H, bs, r, qp, nref, fastme, frac, ip, device=0, max_lanes=lanes) as ctx:
+        ctx.encode_clip_into(frames, out)                      # warm-up
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ln = ctx.encode_clip_into(frames, out)
+        dt = (time.perf_counter() - t0) / reps
+        kt, clip_ms = ctx.last_kernel_times()
+        work = ctx.me_work_per_frame(1)
+    data = out[:ln].tobytes()
+    # parity spot check: first GOP (and the last, possibly short, one) against the oracle
+    gops = [(f0, min(ip, n - f0)) for f0 in range(0, n, ip)]
+    parts = split_container_by_gop(data, [g[1] for g in gops])
+    cfg = ob.make_config(W, H, bs, r, qp, nref=nref, fastme=fastme, frac=frac, i_period=ip)
+    checked = []
+    t0 = time.perf_counter()
+    for gi in sorted({0, len(gops) - 1}) if W <= 1920 else [0]:
+        f0, nf = gops[gi]
+        nchk = nf if W <= 352 else min(nf, 3)                  # oracle time at 1080p/4K: a few seconds per P frame
+        want, _ = ob.encode_clip(cfg, frames[f0:f0 + nchk], want_recon=False)
+        got = parts[gi]
+        if nchk < nf:   # compare the first nchk frame records only
+            got = b"".join(split_container_by_gop(got, [1] * nf)[:nchk])
+        checked.append(bool(got == want))
+    t_oracle = time.perf_counter() - t0
+    line = {"workload": name, "geometry": f"{W}x{H} i={bs} r={r} qp={qp} I_Period={ip} nRef={nref} fastME={fastme} frac={frac}",
+            "frames": n, "lanes": lanes, "e2e_frames_per_s": n / dt, "ms_per_clip": dt * 1e3, "device_ms": clip_ms,
+            "kernel_ms": {k: v[0] for k, v in kt.items()}, "kernel_launches": {k: v[1] for k, v in kt.items()},
+            "bitstream_bytes": ln, "oracle_gops_checked": checked, "oracle_check_s": t_oracle, "synth_s": tgen}
+    if not fastme and kt["me"][0] > 0:
+        line["me_px_absdiff_per_frame_1ref"] = work
+    print(json.dumps(line), flush=True)
+    assert all(checked), f"{name}: GPU stream differs from the oracle"
+
+
+if __name__ == "__main__":
+    for nm in (sys.argv[1:] or ["c0_cif_i8_r4", "c1_cif_fastme_nref4", "c2_cif_halfpel_r4"]):
+        run(nm)
