@@ -13,7 +13,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
-    "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
+    "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
     "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame",
 ]
 
@@ -59,6 +59,9 @@ def load_library():
     L.bvc_set_qp.argtypes = [C.c_void_p, C.c_int]
     L.bvc_encode_iframe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(FrameOut)]
     L.bvc_encode_pframe.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(FrameOut)]
+    L.bvc_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    L.bvc_frame_encode_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    L.bvc_frame_end.argtypes = [C.c_void_p, C.POINTER(FrameOut)]
     L.bvc_me_search.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_int64)]
     L.bvc_interp_halfpel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -136,11 +139,8 @@ class Context:
             _raise(rc, self._L.bvc_last_error(self._h).decode())
 
     # ---- frame level -------------------------------------------------------------------------
-    def _frame(self, cur, refs, qp_rows, intra, debug_planes=True):
+    def _alloc_out(self, debug_planes=True):
         H, W = self.H, self.W
-        cur = np.ascontiguousarray(cur, dtype=np.uint8)
-        if cur.shape != (H, W):
-            raise ValueError(f"frame shape {cur.shape} != {(H, W)}")
         r = FrameResult()
         r.recon = np.empty((H, W), np.uint8)
         r.levels = np.empty((H, W), np.int16)
@@ -159,6 +159,25 @@ class Context:
         fo.resid_mc, fo.resid_nomc = _p(r.resid_mc), _p(r.resid_nomc)
         fo.pred_bytes, fo.pred_cap, fo.coef_bytes, fo.coef_cap = _p(pred), pred_cap, _p(coef), coef_cap
         fo.bits_per_row = _p(r.bits_per_row)
+        return r, fo, pred, coef
+
+    @staticmethod
+    def _finish_out(r, fo, pred, coef):
+        r.pred_nbits, r.coef_nbits = int(fo.pred_nbits), int(fo.coef_nbits)
+        r.pred_bytes = pred[: (r.pred_nbits + 7) // 8].tobytes()
+        r.coef_bytes = coef[: (r.coef_nbits + 7) // 8].tobytes()
+        r.avg_mae, r.mae_comparisons = float(fo.avg_mae), int(fo.mae_comparisons)
+        return r
+
+    def _check_frame(self, cur):
+        cur = np.ascontiguousarray(cur, dtype=np.uint8)
+        if cur.shape != (self.H, self.W):
+            raise ValueError(f"frame shape {cur.shape} != {(self.H, self.W)}")
+        return cur
+
+    def _frame(self, cur, refs, qp_rows, intra, debug_planes=True):
+        cur = self._check_frame(cur)
+        r, fo, pred, coef = self._alloc_out(debug_planes)
         qp = np.ascontiguousarray(qp_rows, dtype=np.int32) if qp_rows is not None else None
         if intra:
             self._check(self._L.bvc_encode_iframe(self._h, _p(cur), _p(qp), C.byref(fo)))
@@ -166,11 +185,29 @@ class Context:
             keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
             arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
             self._check(self._L.bvc_encode_pframe(self._h, _p(cur), arr, len(keep), _p(qp), C.byref(fo)))
-        r.pred_nbits, r.coef_nbits = int(fo.pred_nbits), int(fo.coef_nbits)
-        r.pred_bytes = pred[: (r.pred_nbits + 7) // 8].tobytes()
-        r.coef_bytes = coef[: (r.coef_nbits + 7) // 8].tobytes()
-        r.avg_mae, r.mae_comparisons = float(fo.avg_mae), int(fo.mae_comparisons)
-        return r
+        return self._finish_out(r, fo, pred, coef)
+
+    # ---- row level (rate-control feedback loop) ---------------------------------------------------------
+    def frame_begin(self, cur, refs=None):
+        """Upload a frame (and, for a P frame, its reference window) and run motion estimation."""
+        cur = self._check_frame(cur)
+        if refs is None:
+            self._check(self._L.bvc_frame_begin(self._h, _p(cur), None, 0, 1))
+        else:
+            keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+            arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+            self._check(self._L.bvc_frame_begin(self._h, _p(cur), arr, len(keep), 0))
+
+    def frame_encode_row(self, row, qp):
+        """Encode block row `row` with `qp`; returns the bits it added to both streams."""
+        bits = C.c_int64(0)
+        self._check(self._L.bvc_frame_encode_row(self._h, int(row), int(qp), C.byref(bits)))
+        return int(bits.value)
+
+    def frame_end(self, debug_planes=True):
+        r, fo, pred, coef = self._alloc_out(debug_planes)
+        self._check(self._L.bvc_frame_end(self._h, C.byref(fo)))
+        return self._finish_out(r, fo, pred, coef)
 
     def encode_iframe(self, cur, qp_rows=None, debug_planes=True):
         return self._frame(cur, None, qp_rows, True, debug_planes)

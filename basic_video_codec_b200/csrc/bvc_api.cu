@@ -87,6 +87,11 @@ struct bvc_ctx {
     int64_t last_launches[BVC_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
     double last_clip_ms = 0;
     int resident_frames = 0;
+    // row-by-row (rate control) state
+    bool row_open = false, row_intra = false;
+    int row_nref = 0, row_next = 0;
+    FrameLane row_fl{};
+    long long* d_rowbits = nullptr;
 };
 
 // record an event on the compute stream and return its index (-1 when timing is off)
@@ -210,6 +215,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_row_bits, L * g.bh));
         CK(dalloc(&c->d_pred_row_off, L * (g.bh + 1)));
         CK(dalloc(&c->d_cmp, L));
+        CK(dalloc(&c->d_rowbits, 1));
         CK(dalloc(&c->d_progress, L * g.bh));
         c->coef_cap_words = nb * c->blk_words + 8;
         c->pred_cap_words = nb * 3 + g.bh + 8;
@@ -239,7 +245,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
-    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_progress); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container);
@@ -376,6 +382,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api) {
     t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
+    t.row_begin = 0; t.row_count = g.bh;
     if (sp.intra) {
         CK(cudaMemsetAsync(c->d_progress, 0, (size_t)nl * g.bh * sizeof(int), c->st));
         const int e0 = tick(c);
@@ -445,8 +452,10 @@ static int enqueue_halfpel(bvc_ctx* c, size_t desc_off, int n) {
 
 // ---------------------------------------------------------------------------------------------
 // frame-level API
-static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, const int32_t* qp_rows,
-                        bvc_frame_out* out, bool intra, bool me_only, int32_t* mv_out, int32_t* sad_out, int64_t* cmp_out) {
+// Upload the current frame and its reference window into lane 0, build the half-pel planes, write the lane
+// descriptors and per-row QPs.  Leaves everything enqueued on c->st.
+static int frame_prepare(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, const int32_t* qp_rows,
+                         bool intra, FrameLane* fl_out) {
     const Geom& g = c->g;
     CK(cudaSetDevice(c->device));
     if (!cur) return fail(c, BVC_ERR_INVALID, "cur is null");
@@ -478,24 +487,28 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
         if ((rc = upload_halfpel_desc(c, hp, 0)) != BVC_OK) return rc;
         if ((rc = enqueue_halfpel(c, 0, (int)hp.size())) != BVC_OK) return rc;
     }
+    *fl_out = fl;
+    return BVC_OK;
+}
 
-    StepPlan sp;
-    sp.nl = 1; sp.intra = intra; sp.desc_off = 0;
-    if (me_only) {
-        // run only the ME kernel
-        MeArgs m{};
-        m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
-        m.lanes = c->d_me_lanes; m.out = c->d_mv;
-        m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
-        m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
-        if (c->p.fast_me) CK(launch_fastme(m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
-        else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
-        c->launches += 1;
-    } else {
-        c->ev_used = 0; c->spans.clear();
-        if ((rc = enqueue_step(c, sp, true)) != BVC_OK) return rc;
-    }
-    // ---- downloads ----
+static int launch_me_lane0(bvc_ctx* c) {
+    const Geom& g = c->g;
+    MeArgs m{};
+    m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
+    m.lanes = c->d_me_lanes; m.out = c->d_mv;
+    m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
+    m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
+    if (c->p.fast_me) CK(launch_fastme(m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
+    else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
+    c->launches += 1;
+    return BVC_OK;
+}
+
+// Download the outputs of the frame in lane 0 (after ME, or after ME + transform + pack).
+static int frame_collect(bvc_ctx* c, bvc_frame_out* out, bool intra, int nref_avail, const FrameLane& fl, bool me_only,
+                         int32_t* mv_out, int32_t* sad_out, int64_t* cmp_out) {
+    const Geom& g = c->g;
+    int rc;
     std::vector<int4> hmv;
     std::vector<int32_t> hsad(g.nblk);
     long long hcmp = 0;
@@ -507,9 +520,7 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
         CK(cudaMemcpyAsync(hsad.data(), c->d_isad, (size_t)g.nblk * 4, cudaMemcpyDeviceToHost, c->st));
     }
     long long fb[2] = {0, 0};
-    if (!me_only) {
-        CK(cudaMemcpyAsync(fb, c->d_frame_bits, sizeof fb, cudaMemcpyDeviceToHost, c->st));
-    }
+    if (!me_only) CK(cudaMemcpyAsync(fb, c->d_frame_bits, sizeof fb, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (!intra) {
         for (int b = 0; b < g.nblk; b++) hsad[b] = hmv[b].w;
@@ -552,11 +563,26 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
     CK(cudaStreamSynchronize(c->st));
     if (out->bits_per_row) for (int r = 0; r < g.bh; r++) out->bits_per_row[r] = rb[r];
     // restore the base-QP rows for later clip calls
-    if (qp_rows) {
-        std::vector<int32_t> qb((size_t)c->max_lanes * g.bh, c->p.qp);
-        CK(cudaMemcpy(c->d_qp_rows, qb.data(), qb.size() * 4, cudaMemcpyHostToDevice));
-    }
+    std::vector<int32_t> qb((size_t)c->max_lanes * g.bh, c->p.qp);
+    CK(cudaMemcpy(c->d_qp_rows, qb.data(), qb.size() * 4, cudaMemcpyHostToDevice));
     return BVC_OK;
+}
+
+static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, const int32_t* qp_rows,
+                        bvc_frame_out* out, bool intra, bool me_only, int32_t* mv_out, int32_t* sad_out, int64_t* cmp_out) {
+    FrameLane fl{};
+    int rc;
+    c->row_open = false;
+    if ((rc = frame_prepare(c, cur, refs, nref_avail, qp_rows, intra, &fl)) != BVC_OK) return rc;
+    StepPlan sp;
+    sp.nl = 1; sp.intra = intra; sp.desc_off = 0;
+    if (me_only) {
+        if ((rc = launch_me_lane0(c)) != BVC_OK) return rc;
+    } else {
+        c->ev_used = 0; c->spans.clear();
+        if ((rc = enqueue_step(c, sp, true)) != BVC_OK) return rc;
+    }
+    return frame_collect(c, out, intra, nref_avail, fl, me_only, mv_out, sad_out, cmp_out);
 }
 
 extern "C" int bvc_encode_iframe(bvc_ctx* c, const uint8_t* cur, const int32_t* qp_rows, bvc_frame_out* out) {
@@ -572,6 +598,83 @@ extern "C" int bvc_me_search(bvc_ctx* c, const uint8_t* cur, const uint8_t* cons
                              int32_t* sad, int64_t* comparisons) {
     if (!c) return BVC_ERR_INVALID;
     return frame_common(c, cur, refs, nref_avail, nullptr, nullptr, false, true, mv, sad, comparisons);
+}
+
+// ---- row-by-row encoding: the rate-control feedback loop (RCflag = 1) -------------------------------
+// Frame.get_rc_qp (Frame.py:168-188) picks the QP of block row k from the bits rows < k actually
+// consumed (PFrame.py:53-83, IFrame.py:38-70), so rows are encoded one launch at a time and their bit
+// count is read back before the next row.  Motion estimation does not depend on the QP and runs once,
+// for the whole frame, in bvc_frame_begin.
+static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
+    const Geom& g = c->g;
+    t = TqArgs{};
+    t.cur_base = c->in_pool; t.cur_plane_bytes = g.plane_bytes; t.cur_pitch = g.pitch;
+    t.ref_base = c->ref_pool; t.ref_plane_bytes = g.plane_bytes; t.ref_pitch = g.pitch;
+    t.lanes = c->d_fr_lanes;
+    t.mv = c->d_mv; t.modes = c->d_modes; t.isad = c->d_isad; t.qp_rows = c->d_qp_rows;
+    t.levels = c->d_levels; t.resid_mc = c->d_resid_mc; t.resid_nomc = c->d_resid_nomc;
+    t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
+    t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
+    pk = PackArgs{};
+    pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
+    pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
+    pk.coef_off = c->d_coef_off; pk.lanes = c->d_fr_lanes;
+    pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
+    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
+    pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
+    pk.intra = intra; pk.with_ref = c->p.nref_frames > 1;
+}
+
+extern "C" int bvc_frame_begin(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* refs, int nref_avail, int intra) {
+    if (!c) return BVC_ERR_INVALID;
+    int rc;
+    c->row_open = false;
+    if ((rc = frame_prepare(c, cur, refs, nref_avail, nullptr, intra != 0, &c->row_fl)) != BVC_OK) return rc;
+    if (!intra && (rc = launch_me_lane0(c)) != BVC_OK) return rc;
+    CK(cudaMemsetAsync(c->d_progress, 0, (size_t)c->g.bh * sizeof(int), c->st));
+    c->row_open = true;
+    c->row_intra = intra != 0;
+    c->row_nref = nref_avail;
+    c->row_next = 0;
+    return BVC_OK;
+}
+
+extern "C" int bvc_frame_encode_row(bvc_ctx* c, int row, int qp, int64_t* row_bits) {
+    if (!c) return BVC_ERR_INVALID;
+    if (!c->row_open) return fail(c, BVC_ERR_INVALID, "bvc_frame_begin has not been called");
+    if (row != c->row_next || row >= c->g.bh) return fail(c, BVC_ERR_INVALID, "rows must be encoded in order");
+    int lg = 0; while ((1 << lg) < c->g.bs) lg++;
+    if (qp < 0 || qp > lg + 7) return fail(c, BVC_ERR_INVALID, "qp > log2(block_size) + 7");
+    CK(cudaSetDevice(c->device));
+    const int32_t q32 = qp;
+    CK(cudaMemcpyAsync(c->d_qp_rows + row, &q32, 4, cudaMemcpyHostToDevice, c->st));
+    TqArgs t; PackArgs pk;
+    fill_row_args(c, t, pk, c->row_intra);
+    t.row_begin = row; t.row_count = 1;
+    if (c->row_intra) CK(launch_tq_iframe(t, 1, c->st));
+    else CK(launch_tq_pframe(t, 1, c->st));
+    CK(launch_row_bits(pk, 1, row, c->d_rowbits, c->st));
+    c->launches += 2;
+    long long bits = 0;
+    CK(cudaMemcpyAsync(&bits, c->d_rowbits, sizeof bits, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (row_bits) *row_bits = bits;
+    c->row_next = row + 1;
+    return BVC_OK;
+}
+
+extern "C" int bvc_frame_end(bvc_ctx* c, bvc_frame_out* out) {
+    if (!c) return BVC_ERR_INVALID;
+    if (!c->row_open || c->row_next != c->g.bh) return fail(c, BVC_ERR_INVALID, "not every block row has been encoded");
+    CK(cudaSetDevice(c->device));
+    TqArgs t; PackArgs pk;
+    fill_row_args(c, t, pk, c->row_intra);
+    CK(launch_pack(pk, 1, c->st));
+    c->launches += 2;
+    c->row_open = false;
+    return frame_collect(c, out, c->row_intra, c->row_nref, c->row_fl, false, nullptr, nullptr, nullptr);
 }
 
 extern "C" int bvc_interp_halfpel(bvc_ctx* c, const uint8_t* ref, uint8_t* out2x) {

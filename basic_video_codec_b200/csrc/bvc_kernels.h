@@ -83,6 +83,8 @@ struct TqArgs {
     int frac;                      // MVs in half-pel units, pred from phase planes
     int multi_ref;                 // nRefFrames > 1: pred from refs[mv.ref] else refs[0]
     int* progress;                 // I frames: device [lanes][bh] wavefront progress counters (zeroed)
+    int row_begin, row_count;      // block rows to encode in this launch (0, bh = whole frame); the row-by-row
+                                   // rate-control loop (Frame.get_rc_qp, Frame.py:168-188) launches one row at a time
 };
 cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st);
 cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st);
@@ -114,6 +116,9 @@ struct PackArgs {
     int with_ref;                  // nRefFrames > 1: code the reference index difference
 };
 cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
+// bits the reference accounts to one block row (PFrame.py:76-83): coefficient bits of its blocks + its
+// prediction symbols (row QP symbol included).  out: device long long[lanes].
+cudaError_t launch_row_bits(const PackArgs& a, int lanes, int row, long long* out, cudaStream_t st);
 
 // ---- container assembly ---------------------------------------------------------------------------
 struct ContainerArgs {

@@ -155,6 +155,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
         a.row_bits[(size_t)fl * a.bh + r] = (prow[r + 1] - prow[r]) + (coff[(size_t)(r + 1) * a.bw] - coff[(size_t)r * a.bw]);
 }
 
+// bits of one block row: coefficient strings of its blocks + its prediction symbols
+__global__ void __launch_bounds__(256) pack_row_bits_kernel(PackArgs a, int row, long long* out) {
+    __shared__ long long warp_sums[33];
+    const int fl = blockIdx.x;
+    long long s = 0;
+    for (int bx = threadIdx.x; bx < a.bw; bx += blockDim.x) {
+        const int b = row * a.bw + bx;
+        const PredCode pc = pred_code(a, fl, b);
+        s += a.blk_nbits[(size_t)fl * a.nblk + b] + pc.len + pc.qlen;
+    }
+    long long tot;
+    block_exscan(s, warp_sums, &tot);
+    if (threadIdx.x == 0) out[fl] = tot;
+}
+
 constexpr int EMIT_WARPS = 8;
 __global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) {
     const int fl = blockIdx.y;
@@ -256,6 +271,10 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st) {
 }  // namespace bvc
 
 namespace bvc {
+cudaError_t launch_row_bits(const PackArgs& a, int lanes, int row, long long* out, cudaStream_t st) {
+    pack_row_bits_kernel<<<lanes, 256, 0, st>>>(a, row, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_container(const ContainerArgs& a, cudaStream_t st) {
     container_scan_kernel<<<1, 1024, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();

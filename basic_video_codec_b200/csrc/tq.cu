@@ -34,9 +34,10 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a) {
     const int fl = blockIdx.y;
     const FrameLane& L = a.lanes[fl];
     const int q = lane / BS, x = lane % BS;
-    const int b = (blockIdx.x * TQ_WARPS + warp) * NBW + q;
-    const bool valid = b < a.nblk;
-    const int bb = valid ? b : a.nblk - 1;
+    const int blk_begin = a.row_begin * a.bw, blk_end = (a.row_begin + a.row_count) * a.bw;
+    const int b = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + q;
+    const bool valid = b < blk_end;
+    const int bb = valid ? b : blk_end - 1;
     const int bx = bb % a.bw, by = bb / a.bw;
     const int ox = bx * BS, oy = by * BS;
 
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a) {
 
     // entropy-code the warp's blocks one after the other
     for (int qq = 0; qq < NBW; qq++) {
-        const int b2 = (blockIdx.x * TQ_WARPS + warp) * NBW + qq;
-        if (b2 >= a.nblk) break;
+        const int b2 = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + qq;
+        if (b2 >= blk_end) break;
         uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b2) * a.blk_words;
         const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], sm.zz, t.bits, lane, gout);
         if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b2] = nb;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     build_zigzag<BS>(sm.zz, lane, 32);
     __syncwarp();
     const int ngrp = (lanes + NBW - 1) / NBW;
-    const int by = blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
+    const int by = a.row_begin + blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
     const int q = lane / BS, x = lane % BS;
     const int fl_raw = grp * NBW + q;
     const bool valid = fl_raw < lanes;
@@ -233,7 +234,8 @@ cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         once = true;
     }
-    dim3 grid((a.nblk + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), lanes);
+    const int nb = a.row_count * a.bw;
+    dim3 grid((nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), lanes);
     tq_pframe_kernel<BS><<<grid, TQ_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -243,7 +245,7 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(WarpTile<BS>) + BS * BS + 2 * NBW * BS + 64;
     const int ngrp = (lanes + NBW - 1) / NBW;
-    tq_iframe_kernel<BS><<<a.bh * ngrp, 32, smem, st>>>(a, lanes);
+    tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
     return cudaGetLastError();
 }
 

@@ -3,11 +3,14 @@
 from __future__ import annotations
 
 import threading
+from statistics import mean
 
 import numpy as np
 
 from .._lib import Context
 from .PredictionMode import PredictionMode
+from .RateControl.RateControl import (calculate_constant_row_bit_budget, calculate_proportional_row_bit_budget,
+                                      find_rc_qp_for_row)
 
 
 class BitString:
@@ -82,12 +85,61 @@ class Frame:
     def encode_mc_q_dct(self, encoder_config):
         raise NotImplementedError(f"{type(self)} need to be overridden")
 
-    def _row_qps(self, ec):
-        """Per-row QPs.  Rate control (RCflag != 0, Frame.py:168-188) feeds row bit counts back into the
-        next row's QP; that loop is host logic outside this hot path."""
-        if getattr(ec, "RCflag", 0):
-            raise NotImplementedError("RCflag != 0: rate control is not part of the B200 hot path yet")
-        return None
+    # ---- rate control (reference Frame.py:155-188) ---------------------------------------------------
+    def get_rc_qp(self, encoder_config, prev_frame_avg_qp, rc_qp, row_idx):
+        ec = encoder_config
+        frame_type = "I"  # Frame.py:169: `'I' if self.prediction_mode.INTRA_FRAME else 'P'` is always 'I'
+        if ec.RCflag:
+            if ec.RCflag == 1:
+                budget = calculate_constant_row_bit_budget(self.bit_budget, row_idx, ec)
+                rc_qp = find_rc_qp_for_row(budget, ec.rc_lookup_table, frame_type)
+            if ec.RCflag > 1:
+                if self.is_first_pass:
+                    rc_qp = prev_frame_avg_qp
+                else:
+                    budget, _ = calculate_proportional_row_bit_budget(self, row_idx, ec)
+                    rc_qp = find_rc_qp_for_row(budget, ec.rc_lookup_table, frame_type, scaling_factor=self.scaling_factor)
+            self.rc_qp_per_row.append(rc_qp)
+        return rc_qp
+
+    def _prev_frame_avg_qp(self):
+        """int(mean(prev_frame.rc_qp_per_row) - 0.1) + 1: a ceil with an offset of 0.1 (PFrame.py:49, IFrame.py:35).
+        The reference crashes here on an empty list (second I frame with RCflag 0); the value is unused then."""
+        q = getattr(self.prev_frame, "rc_qp_per_row", None)
+        return int(mean(q) - 0.1) + 1 if q else 0
+
+    def get_overage_ratios(self, encoder_config):
+        """Frame size against the lookup's expected I / P frame size (Frame.py:155-163)."""
+        ec = encoder_config
+        if not self.is_first_pass:
+            raise ValueError("why is overage being called in first pass?")
+        bits = len(self.entropy_encoded_DCT_coffs) + len(self.entropy_encoded_prediction_data) + 8 * 6
+        rows = ec.resolution[1] // ec.block_size
+        row = ec.rc_lookup_table[ec.quantization_factor]
+        return bits / (row["I"] * rows), bits / (row["P"] * rows)
+
+    def _encode_on(self, ctx, ec, refs):
+        """Run the frame on the GPU context with the reference's per-row QP protocol."""
+        rows = self.curr_frame.shape[0] // ec.block_size
+        rc_qp = ec.quantization_factor
+        avg = self._prev_frame_avg_qp() if (ec.RCflag > 1 or refs is None) else 0
+        if not ec.RCflag:
+            return ctx.encode_iframe(self.curr_frame) if refs is None else ctx.encode_pframe(self.curr_frame, refs)
+        if ec.RCflag == 1:
+            # row k's QP depends on the bits rows < k consumed: encode row by row (bvc_frame_encode_row)
+            ctx.frame_begin(self.curr_frame, refs)
+            for row in range(rows):
+                rc_qp = self.get_rc_qp(ec, avg, rc_qp, row)
+                self.bit_budget -= ctx.frame_encode_row(row, rc_qp)
+            r = ctx.frame_end()
+            self.bit_budget += int(r.bits_per_row.sum())   # _store subtracts the row bits once more
+            return r
+        # RCflag 2 / 3: every row QP is known before the frame is coded
+        qps = []
+        for row in range(rows):
+            rc_qp = self.get_rc_qp(ec, avg, rc_qp, row)
+            qps.append(rc_qp)
+        return ctx.encode_iframe(self.curr_frame, qps) if refs is None else ctx.encode_pframe(self.curr_frame, refs, qps)
 
     def _store(self, r):
         self.reconstructed_frame = r.recon

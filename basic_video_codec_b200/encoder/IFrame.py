@@ -15,7 +15,7 @@ class IFrame(Frame):
         ec = encoder_config
         H, W = self.curr_frame.shape
         ctx = context_for(ec, W, H, self.device)
-        r = ctx.encode_iframe(self.curr_frame, self._row_qps(ec))
+        r = self._encode_on(ctx, ec, None)
         self._store(r)
         self.intra_modes = [int(m) for m in r.modes]
         # IFrame.py:30,57-58,81-83: one uint8 plane serves as both residual planes

@@ -16,7 +16,7 @@ class PFrame(Frame):
         ctx = context_for(ec, W, H, self.device)
         # the half-pel planes are rebuilt on the GPU from the references; the reference's
         # interpolated_reference_frames deque is accepted for signature compatibility only
-        r = ctx.encode_pframe(self.curr_frame, list(self.reference_frames), self._row_qps(ec))
+        r = self._encode_on(ctx, ec, list(self.reference_frames))
         self._store(r)
         self.residual_frame = r.resid_mc
         self.residual_wo_mc_frame = r.resid_nomc

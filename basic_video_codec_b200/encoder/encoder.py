@@ -4,7 +4,9 @@ Same signature, same output directory scheme and files (file_io.py:20-26): encod
 mc_reconstructed.yuv, mc_quant_dct_coff.bin, residuals_w_mc.yuv, residuals_wo_mc.yuv, mv.txt,
 metrics.csv.  Differences, all deliberate: no rate-control lookup CSV is required when RCflag = 0
 (reference quirk Q14), nothing is appended to a results.csv inside the package, and the half-pel
-planes live on the GPU.  RCflag != 0 is not handled by this path yet.
+planes live on the GPU.  Rate control (RCflag 1: per-row feedback; 2/3: two passes with scene-change
+detection, encoder.py:85-98,188-201) is driven from here exactly like the reference does; its lookup
+tables are only needed when RCflag != 0.
 """
 from __future__ import annotations
 
@@ -15,8 +17,11 @@ from collections import deque
 
 import numpy as np
 
+from .Frame import Frame
 from .IFrame import IFrame
 from .PFrame import PFrame
+from .RateControl.RateControl import bit_budget_per_frame
+from .RateControl.lookup import get_combined_lookup_table, rc_lookup_file_path
 
 
 def pad_frame(frame, block_size, pad_value=128):
@@ -45,7 +50,8 @@ def output_dir(params):
 def encode_video(params, device: int = 0):
     ec = params.encoder_config
     if ec.RCflag:
-        raise NotImplementedError("RCflag != 0: rate control is not part of the B200 hot path yet")
+        ec.rc_lookup_table = get_combined_lookup_table(rc_lookup_file_path(ec, "I"), rc_lookup_file_path(ec, "P"))
+    scene_change_threshold = 1.3
     out = output_dir(params)
     os.makedirs(out, exist_ok=True)
     W, H, bs = params.width, params.height, ec.block_size
@@ -63,7 +69,8 @@ def encode_video(params, device: int = 0):
             open(os.path.join(out, "metrics.csv"), "wt", newline="") as met_fh:
         met = csv.writer(met_fh)
         met.writerow(["idx", "I-Frame", "avg_MAE", "mae_comps", "PSNR", "frame_bytes", "file_bits", "enc_time", "elapsed_time"])
-        prev = None
+        prev = Frame()
+        prev.rc_qp_per_row = [ec.quantization_factor]  # arbitrary seed for the first frame (encoder.py:72-73)
         idx = 0
         while True:
             t0 = time.time()
@@ -73,14 +80,30 @@ def encode_video(params, device: int = 0):
             if not raw or idx > params.frames_to_process:
                 break
             cur = pad_frame(np.frombuffer(raw, dtype=np.uint8).reshape(H, W), bs)
-            if (idx - 1) % ec.I_Period == 0:  # encoder.py:174-178
-                frame = IFrame(cur)
-                reference_frames.clear()
-                interpolated_reference_frames.clear()
-            else:
-                frame = PFrame(cur, reference_frames, interpolated_reference_frames)
-            frame.prev_frame, frame.index, frame.device = prev, idx, device
+
+            def make(intra, first_pass, prev_pass=None):
+                if intra:  # encoder.py:174-178,189-192
+                    reference_frames.clear()
+                    interpolated_reference_frames.clear()
+                    fr = IFrame(cur)
+                else:
+                    fr = PFrame(cur, reference_frames, interpolated_reference_frames)
+                fr.is_first_pass, fr.prev_frame, fr.index, fr.device = first_pass, prev, idx, device
+                fr.bit_budget = bit_budget_per_frame(ec) if ec.RCflag else 0
+                fr.prev_pass_frame = prev_pass
+                return fr
+
+            frame = make((idx - 1) % ec.I_Period == 0, True)
             frame.encode_mc_q_dct(ec)
+            if ec.RCflag > 1:  # second pass, encoder.py:91-98
+                first = frame
+                overage = first.get_overage_ratios(ec)
+                scene_change = False
+                if first.is_pframe() and overage[1] > scene_change_threshold:
+                    first.scaling_factor = (1 - overage[1]) * 0.95  # set on the first-pass object, as the reference does
+                    scene_change = True
+                frame = make(scene_change or first.is_iframe(), False, first)
+                frame.encode_mc_q_dct(ec)
             enc_time = time.time() - t0
             # container, encoder.py:104-121
             pb = (len(frame.entropy_encoded_prediction_data) + 7) // 8

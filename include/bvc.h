@@ -82,6 +82,17 @@ int bvc_encode_iframe(bvc_ctx *ctx, const uint8_t *cur, const int32_t *qp_rows, 
 int bvc_encode_pframe(bvc_ctx *ctx, const uint8_t *cur, const uint8_t *const *refs, int nref_avail,
                       const int32_t *qp_rows, bvc_frame_out *out);
 
+/* row level: the rate-control feedback loop (RCflag = 1) ------------------------------------------- */
+/* Frame.get_rc_qp (encoder/Frame.py:168-188) derives the QP of block row k from the bits rows < k
+ * consumed (encoder/PFrame.py:53-83, encoder/IFrame.py:38-70).  bvc_frame_begin uploads the frame and
+ * its reference window and runs motion estimation once (it does not depend on the QP);
+ * bvc_frame_encode_row transforms / reconstructs / entropy-codes block row `row` with `qp` and returns
+ * the bits that row added to both streams (row_bits_consumed); rows must be given in order 0..H/i-1;
+ * bvc_frame_end assembles the streams and fills `out` exactly like bvc_encode_pframe / _iframe. */
+int bvc_frame_begin(bvc_ctx *ctx, const uint8_t *cur, const uint8_t *const *refs, int nref_avail, int intra);
+int bvc_frame_encode_row(bvc_ctx *ctx, int row, int qp, int64_t *row_bits);
+int bvc_frame_end(bvc_ctx *ctx, bvc_frame_out *out);
+
 /* block-level hooks ---------------------------------------------------------------------------- */
 /* PFrame.get_motion_vector over a whole frame: find_lowest_mae_block or find_fast_me_block per the
  * context's parameters (encoder/block_predictor.py:11-91).  mv: nblk*3, sad: nblk. */

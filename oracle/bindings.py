@@ -24,7 +24,11 @@ class FrameOut(C.Structure):
     _fields_ = [("recon", C.c_void_p), ("levels", C.c_void_p), ("mv", C.c_void_p), ("sad", C.c_void_p),
                 ("modes", C.c_void_p), ("resid_mc", C.c_void_p), ("resid_nomc", C.c_void_p),
                 ("pred_bits", Bits), ("coef_bits", Bits), ("bits_per_row", C.c_void_p),
-                ("avg_mae", C.c_double), ("mae_comparisons", C.c_int64)]
+                ("avg_mae", C.c_double), ("mae_comparisons", C.c_int64),
+                ("qp_cb", C.c_void_p), ("qp_user", C.c_void_p), ("qp_used", C.c_void_p)]
+
+
+QP_CALLBACK = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int64)
 
 
 def build(force: bool = False) -> str:
@@ -130,7 +134,7 @@ class FrameResult:
     pass
 
 
-def _encode_frame(cfg: Config, cur, refs, hp_refs, qp_rows, intra: bool):
+def _encode_frame(cfg: Config, cur, refs, hp_refs, qp_rows, intra: bool, qp_callback=None):
     L = lib()
     H, W, bs = cfg.height, cfg.width, cfg.block
     nblk = (W // bs) * (H // bs)
@@ -153,6 +157,12 @@ def _encode_frame(cfg: Config, cur, refs, hp_refs, qp_rows, intra: bool):
     qp = None
     if qp_rows is not None:
         qp = np.ascontiguousarray(qp_rows, dtype=np.int32)
+    r.qp_used = np.zeros(rows, dtype=np.int32)
+    fo.qp_used = _p(r.qp_used)
+    cb = None
+    if qp_callback is not None:   # qp_callback(row, prev_row_bits) -> qp
+        cb = QP_CALLBACK(lambda user, row, bits: int(qp_callback(int(row), int(bits))))
+        fo.qp_cb = C.cast(cb, C.c_void_p)
     if intra:
         L.bvo_encode_iframe(C.byref(cfg), _p(cur), _p(qp) if qp is not None else None, C.byref(fo))
     else:
@@ -168,12 +178,12 @@ def _encode_frame(cfg: Config, cur, refs, hp_refs, qp_rows, intra: bool):
     return r
 
 
-def encode_pframe(cfg, cur, refs, hp_refs=None, qp_rows=None):
-    return _encode_frame(cfg, cur, refs, hp_refs, qp_rows, False)
+def encode_pframe(cfg, cur, refs, hp_refs=None, qp_rows=None, qp_callback=None):
+    return _encode_frame(cfg, cur, refs, hp_refs, qp_rows, False, qp_callback)
 
 
-def encode_iframe(cfg, cur, qp_rows=None):
-    return _encode_frame(cfg, cur, None, None, qp_rows, True)
+def encode_iframe(cfg, cur, qp_rows=None, qp_callback=None):
+    return _encode_frame(cfg, cur, None, None, qp_rows, True, qp_callback)
 
 
 def encode_clip(cfg: Config, frames: np.ndarray, nthreads: int = 1, want_recon: bool = True):

@@ -416,8 +416,10 @@ void bvo_encode_pframe(const bvo_config *cfg, const uint8_t *cur, const uint8_t 
     int32_t prev_mv[3] = {0, 0, 0}; /* PFrame.py:140 ; chained across rows (:144) */
     size_t pred_len = 0, coef_len = 0;
 
+    int64_t prev_row_bits = 0;
     for (int by = 0; by < bh; by++) {
-        const int qp = qp_rows ? qp_rows[by] : cfg->qp;
+        const int qp = out->qp_cb ? out->qp_cb(out->qp_user, by, prev_row_bits) : (qp_rows ? qp_rows[by] : cfg->qp);
+        if (out->qp_used) out->qp_used[by] = qp;
         for (int bx = 0; bx < bw; bx++) {
             const int b = by * bw + bx, ox = bx * bs, oy = by * bs;
             const int32_t *mv = out->mv + 3 * b;
@@ -455,8 +457,8 @@ void bvo_encode_pframe(const bvo_config *cfg, const uint8_t *cur, const uint8_t 
             prev_mv[0] = mv[0]; prev_mv[1] = mv[1]; prev_mv[2] = mv[2];
         }
         code_coef_row(cfg, out->levels, by, &out->coef_bits);
-        if (out->bits_per_row)
-            out->bits_per_row[by] = (int64_t)(out->coef_bits.nbits - coef_len) + (int64_t)(out->pred_bits.nbits - pred_len);
+        prev_row_bits = (int64_t)(out->coef_bits.nbits - coef_len) + (int64_t)(out->pred_bits.nbits - pred_len);
+        if (out->bits_per_row) out->bits_per_row[by] = prev_row_bits;
         pred_len = out->pred_bits.nbits; coef_len = out->coef_bits.nbits;
     }
     out->avg_mae = mae_sum / (double)nblk; /* PFrame.py:88 */
@@ -476,8 +478,10 @@ void bvo_encode_iframe(const bvo_config *cfg, const uint8_t *cur, const int32_t 
     memset(recon, 0, (size_t)W * H);
     out->mae_comparisons = 0;
 
+    int64_t prev_row_bits = 0;
     for (int by = 0; by < bh; by++) {
-        const int qp = qp_rows ? qp_rows[by] : cfg->qp;
+        const int qp = out->qp_cb ? out->qp_cb(out->qp_user, by, prev_row_bits) : (qp_rows ? qp_rows[by] : cfg->qp);
+        if (out->qp_used) out->qp_used[by] = qp;
         for (int bx = 0; bx < bw; bx++) {
             const int b = by * bw + bx, ox = bx * bs, oy = by * bs;
             const uint8_t *c = cur + (size_t)oy * W + ox;
@@ -522,8 +526,8 @@ void bvo_encode_iframe(const bvo_config *cfg, const uint8_t *cur, const int32_t 
         bvo_put_eg(&out->pred_bits, qp - cfg->qp);
         for (int bx = 0; bx < bw; bx++) bvo_put_eg(&out->pred_bits, out->modes[by * bw + bx]);
         code_coef_row(cfg, out->levels, by, &out->coef_bits);
-        if (out->bits_per_row)
-            out->bits_per_row[by] = (int64_t)(out->coef_bits.nbits - coef_len) + (int64_t)(out->pred_bits.nbits - pred_len);
+        prev_row_bits = (int64_t)(out->coef_bits.nbits - coef_len) + (int64_t)(out->pred_bits.nbits - pred_len);
+        if (out->bits_per_row) out->bits_per_row[by] = prev_row_bits;
         pred_len = out->pred_bits.nbits; coef_len = out->coef_bits.nbits;
     }
     out->avg_mae = mae_sum / (double)nblk;

@@ -105,6 +105,12 @@ typedef struct bvo_frame_out {
     int64_t  *bits_per_row;   /* rows entries (may be NULL) */
     double    avg_mae;
     int64_t   mae_comparisons;
+    /* optional per-row QP feedback (rate control, Frame.get_rc_qp Frame.py:168-188): called before block row
+     * `row` is coded with the bits the previous row consumed (0 for row 0); returns the row's QP.
+     * qp_used (optional, rows entries) receives the QPs. */
+    int32_t (*qp_cb)(void *user, int32_t row, int64_t prev_row_bits);
+    void     *qp_user;
+    int32_t  *qp_used;
 } bvo_frame_out;
 
 /* PFrame.encode_mc_q_dct, PFrame.py:29-97.  refs: deque order (index 0 = oldest).

@@ -68,6 +68,60 @@ def frame_details(frames, enc):
     return det
 
 
+RC_CASES = {
+    # name: (gen kwargs, enc kwargs, RCflag, targetBR)
+    "rc1_i16": (dict(seed=51, height=64, width=96, nframes=7, step=3, clamp=16), dict(block=16, search_range=4, qp=4, i_period=4, nref=1), 1, 280000),
+    "rc1_i8_nref2": (dict(seed=52, height=48, width=64, nframes=6, step=2, clamp=16), dict(block=8, search_range=2, qp=3, i_period=3, nref=2), 1, 220000),
+    "rc2_i16": (dict(seed=53, height=64, width=96, nframes=7, step=3, clamp=16), dict(block=16, search_range=4, qp=5, i_period=7, nref=1), 2, 200000),
+    "rc3_i8_scene": (dict(seed=54, height=48, width=64, nframes=6, step=1, clamp=16, noise=0), dict(block=8, search_range=2, qp=5, i_period=6, nref=2), 3, 330000),
+    "rc1_frac_fastme": (dict(seed=55, height=48, width=64, nframes=5, step=2, clamp=16), dict(block=8, search_range=2, qp=3, i_period=5, nref=2, frac=True, fastme=True), 1, 150000),
+}
+
+
+def rc_main(only=None):
+    from oracle import rc_oracle
+    ns = rh.load_reference()
+    for name, (gk, enc, rcflag, br) in RC_CASES.items():
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        frames = synth.moving_clip(**gk)
+        if name == "rc3_i8_scene":   # a hard cut in the middle of the GOP so the scene-change path triggers
+            frames[3:] = synth.moving_clip(seed=99, height=gk["height"], width=gk["width"], nframes=gk["nframes"] - 3, step=1, clamp=16, noise=0, blur=3)
+        table = rc_oracle.measure_table(frames, enc["block"], nref=1)
+        out = ref_encode_video_rc(ns, frames, enc, rcflag, br, table)
+        meta = {"generator": "moving", "gen_kwargs": gk, "enc": enc, "rcflag": rcflag, "targetBR": br,
+                "table": {str(k): v for k, v in table.items()}, "dct_mode": "fp64_defined",
+                "encoded_sha256": hashlib.sha256(out["encoded"]).hexdigest()}
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), frames=frames,
+                            encoded=np.frombuffer(out["encoded"], dtype=np.uint8), recon=out["recon"],
+                            meta=np.array(json.dumps(meta)))
+        print(f"{name}: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
+
+
+def ref_encode_video_rc(ns, frames, enc, rcflag, br, table):
+    """The reference's own encode_video with RCflag set and `table` returned by its lookup loader."""
+    import tempfile
+    rh.set_dct_mode("fp64_defined")
+    n, H, W = frames.shape
+    ec = ns.params.EncoderConfig(enc["block"], enc["search_range"], enc["i_period"], enc["qp"], nRefFrames=enc.get("nref", 1),
+                                 fastME=enc.get("fastme", False), fracMeEnabled=enc.get("frac", False), RCflag=rcflag,
+                                 targetBR=br, resolution=(W, H))
+    orig = ns.encoder.get_combined_lookup_table
+    ns.encoder.get_combined_lookup_table = lambda a, b: {int(k): dict(v) for k, v in table.items()}
+    try:
+        with tempfile.TemporaryDirectory(prefix="bvc_ref_rc_") as td:
+            yfile = os.path.join(td, "clip.y")
+            open(yfile, "wb").write(np.ascontiguousarray(frames).tobytes())
+            params = ns.input_parameters.InputParameters(yfile, W, H, ec, frames_to_process=n)
+            ns.encoder.encode_video(params)
+            fio = ns.encoder.FileIOHelper(params)
+            return {"encoded": open(fio.get_encoded_file_name(), "rb").read(),
+                    "recon": np.fromfile(fio.get_mc_reconstructed_file_name(), dtype=np.uint8).reshape(n, H, W)}
+    finally:
+        ns.encoder.get_combined_lookup_table = orig
+
+
 def main(only=None):
     os.makedirs(GOLD, exist_ok=True)
     for name, (gen, gk, enc) in CASES.items():
@@ -85,6 +139,9 @@ def main(only=None):
                             resid_nomc=out["resid_nomc"], mv_txt=np.array(out["mv_txt"]),
                             meta=np.array(json.dumps(meta)))
         print(f"{name}: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
+
+    # ---- rate control (RCflag 1/2/3) with a lookup table measured by the oracle, patched into the reference ----
+    rc_main(only)
 
     # CIF stand-in for BASELINE config 1 (Foreman is an LFS pointer): the reference's own synthetic
     # generator tests/y_generator.py, 10 frames, i=8 r=4 qp=3 I_Period=8.

@@ -158,7 +158,7 @@ def test_frames_match_oracle(case):
 
 
 # ---- clip level: goldens from the Python reference -----------------------------------------------------
-@pytest.mark.parametrize("name", gu.names())
+@pytest.mark.parametrize("name", [n for n in gu.names() if not n.startswith("rc")])
 def test_clip_matches_reference_golden(name):
     g = gu.load(name)
     frames, e = g["frames"], g["meta"]["enc"]

@@ -1,0 +1,114 @@
+"""Rate control (RCflag 1/2/3): goldens from the reference's encode_video with a measured lookup table patched
+in, against (CPU) the oracle restatement of the control loop and (GPU) the Python drop-in layer driving
+libbvc_b200.so row by row."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_util as gu
+
+RC = [n for n in gu.names() if n.startswith("rc")]
+
+
+def _table(meta):
+    return {int(k): dict(v) for k, v in meta["table"].items()}
+
+
+@pytest.mark.parametrize("name", RC)
+def test_oracle_control_loop_matches_reference(name):
+    from oracle import bindings as ob, rc_oracle
+    g = gu.load(name)
+    e, frames = g["meta"]["enc"], g["frames"]
+    n, H, W = frames.shape
+    cfg = ob.make_config(W, H, e["block"], e["search_range"], e["qp"], nref=e.get("nref", 1), fastme=e.get("fastme", False),
+                         frac=e.get("frac", False), i_period=e["i_period"])
+    data, recon, qps, kinds = rc_oracle.encode_video_rc(frames, cfg, g["meta"]["rcflag"], g["meta"]["targetBR"], _table(g["meta"]))
+    assert data == g["encoded"]
+    assert np.array_equal(recon, g["recon"])
+    # the cases actually exercise rate control: QPs move, and the scene-change case re-codes a P frame as I
+    assert len({q for row in qps for q in row}) > 1
+    if name == "rc3_i8_scene":
+        assert kinds.count(True) >= 2
+
+
+def test_lookup_parsing_drops_qp0_like_the_reference(tmp_path):
+    """lookup.py:107,118: the first CSV column is skipped, so QP 0 is never in the table."""
+    from basic_video_codec_b200 import EncoderConfig
+    from basic_video_codec_b200.encoder.RateControl import lookup
+    os.environ["BVC_RC_LOOKUP_DIR"] = str(tmp_path)
+    try:
+        for kind, vals in (("I", [900, 800, 700, 600]), ("P", [500, 400, 300, 200])):
+            (tmp_path / f"96_64_16_{kind}.csv").write_text("0,1,2,3\n" + ",".join(map(str, vals)) + "\n")
+        ec = EncoderConfig(16, 4, 8, 3, resolution=(96, 64))
+        t = lookup.get_combined_lookup_table(lookup.rc_lookup_file_path(ec, "I"), lookup.rc_lookup_file_path(ec, "P"))
+        assert t == {1: {"I": 800, "P": 400, "C": 600}, 2: {"I": 700, "P": 300, "C": 500}, 3: {"I": 600, "P": 200, "C": 400}}
+        with pytest.raises(FileNotFoundError):
+            lookup.get_combined_lookup_table(str(tmp_path / "nope.csv"), str(tmp_path / "nope.csv"))
+    finally:
+        del os.environ["BVC_RC_LOOKUP_DIR"]
+
+
+def test_find_rc_qp_for_row():
+    from basic_video_codec_b200.encoder.RateControl.RateControl import find_rc_qp_for_row
+    t = {1: {"I": 800}, 2: {"I": 700}, 3: {"I": 600}}
+    assert find_rc_qp_for_row(750, t, "I") == 2
+    assert find_rc_qp_for_row(10, t, "I") == 3          # nothing fits: largest QP
+    assert find_rc_qp_for_row(5000, t, "I") == 1
+    assert find_rc_qp_for_row(750, t, "I", scaling_factor=0.9) == 1
+    with pytest.raises(ValueError):
+        find_rc_qp_for_row(1, t, "X")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", RC)
+def test_gpu_encode_video_with_rate_control(name, tmp_path):
+    """encode_video(InputParameters) with RCflag set: the GPU row-by-row path reproduces the reference stream."""
+    from basic_video_codec_b200 import EncoderConfig, InputParameters
+    from basic_video_codec_b200.encoder import encoder as enc_mod
+    g = gu.load(name)
+    e, frames, meta = g["meta"]["enc"], g["frames"], g["meta"]
+    n, H, W = frames.shape
+    yfile = tmp_path / "clip.y"
+    yfile.write_bytes(frames.tobytes())
+    ec = EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e.get("nref", 1),
+                       fastME=e.get("fastme", False), fracMeEnabled=e.get("frac", False), RCflag=meta["rcflag"],
+                       targetBR=meta["targetBR"], resolution=(W, H))
+    params = InputParameters(str(yfile), W, H, ec, frames_to_process=n)
+    orig = enc_mod.get_combined_lookup_table
+    enc_mod.get_combined_lookup_table = lambda a, b: _table(meta)
+    try:
+        enc_mod.encode_video(params)
+    finally:
+        enc_mod.get_combined_lookup_table = orig
+    out = enc_mod.output_dir(params)
+    data = open(os.path.join(out, "encoded.bin"), "rb").read()
+    assert hashlib.sha256(data).hexdigest() == meta["encoded_sha256"]
+    assert open(os.path.join(out, "mc_reconstructed.yuv"), "rb").read() == g["recon"].tobytes()
+
+
+@pytest.mark.gpu
+def test_row_api_matches_frame_api():
+    """bvc_frame_begin / _encode_row / _end with fixed row QPs == bvc_encode_pframe with the same qp_rows."""
+    import basic_video_codec_b200 as bvc
+    from tests import synth
+    H, W, bs = 64, 96, 16
+    clip = synth.moving_clip(77, H, W, 3, step=3, clamp=16)
+    qps = [2, 5, 3, 4]
+    with bvc.Context(W, H, bs, 8, 3, 2) as ctx:
+        i0 = ctx.encode_iframe(clip[0], qps)
+        ctx.frame_begin(clip[0])
+        bits = [ctx.frame_encode_row(r, qps[r]) for r in range(4)]
+        i1 = ctx.frame_end()
+        assert bits == i0.bits_per_row.tolist() == i1.bits_per_row.tolist()
+        assert i1.coef_bytes == i0.coef_bytes and i1.pred_bytes == i0.pred_bytes and np.array_equal(i1.recon, i0.recon)
+        p0 = ctx.encode_pframe(clip[1], [i0.recon], qps)
+        ctx.frame_begin(clip[1], [i0.recon])
+        bits = [ctx.frame_encode_row(r, qps[r]) for r in range(4)]
+        p1 = ctx.frame_end()
+        assert bits == p0.bits_per_row.tolist()
+        assert p1.coef_bytes == p0.coef_bytes and p1.pred_bytes == p0.pred_bytes and np.array_equal(p1.recon, p0.recon)
+        assert np.array_equal(p1.mv, p0.mv) and np.array_equal(p1.levels, p0.levels)
+        with pytest.raises(ValueError):
+            ctx.frame_encode_row(0, 3)           # frame already closed
