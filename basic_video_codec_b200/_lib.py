@@ -14,7 +14,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
-    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups",
 ]
 
 
@@ -70,6 +70,7 @@ def load_library():
     L.bvc_encode_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.bvc_clip_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+    L.bvc_set_lane_groups.argtypes = [C.c_void_p, C.c_int]
     L.bvc_launch_count.argtypes = [C.c_void_p]
     L.bvc_launch_count.restype = C.c_int64
     L.bvc_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -120,6 +121,7 @@ class Context:
         self.nblk = (self.W // self.bs) * (self.H // self.bs)
         self.rows = self.H // self.bs
         self.max_lanes = int(max_lanes)
+        self.lane_groups = int(os.environ.get("BVC_LANE_GROUPS", "2"))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -263,6 +265,11 @@ class Context:
         return out, int(ln.value)
 
     # ---- instrumentation -----------------------------------------------------------------------
+    def set_lane_groups(self, groups: int):
+        """Lane groups of the clip path (bvc_set_lane_groups): 1 = serial, default 2."""
+        self._check(self._L.bvc_set_lane_groups(self._h, int(groups)))
+        self.lane_groups = int(groups)
+
     def launch_count(self):
         return int(self._L.bvc_launch_count(self._h))
 

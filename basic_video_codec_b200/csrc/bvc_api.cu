@@ -16,12 +16,15 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/bvc.h"
 #include "bvc_kernels.h"
+
+#define BVC_MAX_GROUPS 4
 
 namespace bvc {
 cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
@@ -40,6 +43,14 @@ struct bvc_ctx {
     int pps = 1;          // planes per ring slot
     int slots = 2;        // ring slots per lane (nref + 1)
     cudaStream_t st = nullptr, st_copy = nullptr, st_h2d = nullptr;
+    // clip path: the GOP lanes of a step are split into `ngroups` lane groups with their own streams, so the tail
+    // of one group's motion search (a last, partly filled wave of 77 us CTAs) is filled by the other group's
+    // kernels.  st_grp: motion search (low priority), st_post: everything after it (high priority).  B200's block
+    // scheduler does not place a second kernel's CTAs next to a kernel that still has CTAs to dispatch
+    // (profiles/microbench/cosched.cu), so this buys the tails (~1.5 %), not a transform-under-search overlap.
+    int ngroups = 2;
+    cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
+    cudaEvent_t ev_me[BVC_MAX_GROUPS] = {}, ev_post[BVC_MAX_GROUPS] = {};
     std::string err;
     int64_t launches = 0;
 
@@ -94,8 +105,8 @@ struct bvc_ctx {
     long long* d_rowbits = nullptr;
 };
 
-// record an event on the compute stream and return its index (-1 when timing is off)
-static int tick(bvc_ctx* c) {
+// record an event on `st` (default: the compute stream) and return its index (-1 when timing is off)
+static int tick(bvc_ctx* c, cudaStream_t st = nullptr) {
     if (!c->timing) return -1;
     if (c->ev_used == c->ev_pool.size()) {
         cudaEvent_t e;
@@ -103,7 +114,7 @@ static int tick(bvc_ctx* c) {
         c->ev_pool.push_back(e);
     }
     const int i = (int)c->ev_used++;
-    cudaEventRecord(c->ev_pool[i], c->st);
+    cudaEventRecord(c->ev_pool[i], st ? st : c->st);
     return i;
 }
 static void span(bvc_ctx* c, int cls, int e0, int e1) {
@@ -198,6 +209,15 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
+        for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
+            CK(cudaStreamCreateWithPriority(&c->st_grp[gi], cudaStreamNonBlocking, prio_lo));
+            CK(cudaStreamCreateWithPriority(&c->st_post[gi], cudaStreamNonBlocking, prio_hi));
+            CK(cudaEventCreateWithFlags(&c->ev_me[gi], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_post[gi], cudaEventDisableTiming));
+        }
+        if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;
         CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
@@ -242,6 +262,12 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st_copy) cudaStreamSynchronize(c->st_copy);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
+    for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
+        if (c->st_grp[gi]) { cudaStreamSynchronize(c->st_grp[gi]); cudaStreamDestroy(c->st_grp[gi]); }
+        if (c->st_post[gi]) { cudaStreamSynchronize(c->st_post[gi]); cudaStreamDestroy(c->st_post[gi]); }
+        if (c->ev_me[gi]) cudaEventDestroy(c->ev_me[gi]);
+        if (c->ev_post[gi]) cudaEventDestroy(c->ev_post[gi]);
+    }
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
@@ -278,6 +304,12 @@ extern "C" int bvc_set_qp(bvc_ctx* c, int qp) {
     std::vector<int32_t> q((size_t)c->max_lanes * c->g.bh, qp);
     CK(cudaMemcpyAsync(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaStreamSynchronize(c->st));
+    return BVC_OK;
+}
+
+extern "C" int bvc_set_lane_groups(bvc_ctx* c, int groups) {
+    if (!c || groups < 1 || groups > BVC_MAX_GROUPS) return BVC_ERR_INVALID;
+    c->ngroups = groups;
     return BVC_OK;
 }
 
@@ -356,8 +388,8 @@ static int upload_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src) {
     CK(cudaMemcpy2DAsync(dst, c->g.pitch, src, c->g.W, c->g.W, c->g.H, cudaMemcpyHostToDevice, c->st));
     return BVC_OK;
 }
-static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src) {
-    CK(cudaMemcpy2DAsync(dst, c->g.W, src, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToHost, c->st));
+static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src, cudaStream_t st = nullptr) {
+    CK(cudaMemcpy2DAsync(dst, c->g.W, src, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToHost, st ? st : c->st));
     return BVC_OK;
 }
 
@@ -367,65 +399,77 @@ struct StepPlan {
     size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
 };
 
-// Enqueue the kernels of one step on c->st.
-static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api) {
+// Enqueue the kernels of lanes [l0, l0+nl) of one step: the motion search on `st_me`, everything after it on
+// `st_post` (the same stream for the frame-level calls).  Per-lane scratch arrays are indexed by the lane
+// inside a launch, so a lane group simply gets base pointers advanced by l0 lanes.
+static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStream_t st_me, cudaStream_t st_post, int l0, int nl,
+                        cudaEvent_t ev_me_done) {
     const Geom& g = c->g;
-    const int nl = sp.nl;
+    const size_t nb = (size_t)g.nblk, L0 = (size_t)l0;
     TqArgs t{};
     t.cur_base = c->in_pool; t.cur_plane_bytes = g.plane_bytes; t.cur_pitch = g.pitch;
     t.ref_base = c->ref_pool; t.ref_plane_bytes = g.plane_bytes; t.ref_pitch = g.pitch;
-    t.lanes = c->d_fr_lanes + sp.desc_off;
-    t.mv = c->d_mv; t.modes = c->d_modes; t.isad = c->d_isad; t.qp_rows = c->d_qp_rows;
+    t.lanes = c->d_fr_lanes + sp.desc_off + L0;
+    t.mv = c->d_mv + L0 * nb; t.modes = c->d_modes + L0 * nb; t.isad = c->d_isad + L0 * nb; t.qp_rows = c->d_qp_rows + L0 * g.bh;
     t.levels = frame_api ? c->d_levels : nullptr;
     t.resid_mc = frame_api ? c->d_resid_mc : nullptr;
     t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
-    t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
+    t.blk_bits = c->d_blk_bits + L0 * nb * c->blk_words; t.blk_nbits = c->d_blk_nbits + L0 * nb; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
-    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh;
     t.row_begin = 0; t.row_count = g.bh;
     if (sp.intra) {
-        CK(cudaMemsetAsync(c->d_progress, 0, (size_t)nl * g.bh * sizeof(int), c->st));
-        const int e0 = tick(c);
-        CK(launch_tq_iframe(t, nl, c->st));
-        span(c, BVC_K_TQ_I, e0, tick(c));
+        CK(cudaMemsetAsync(t.progress, 0, (size_t)nl * g.bh * sizeof(int), st_post));
+        const int e0 = tick(c, st_post);
+        CK(launch_tq_iframe(t, nl, st_post));
+        span(c, BVC_K_TQ_I, e0, tick(c, st_post));
         c->launches += 1;
     } else {
         MeArgs m{};
         m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
-        m.lanes = c->d_me_lanes + sp.desc_off;
-        m.out = c->d_mv;
+        m.lanes = c->d_me_lanes + sp.desc_off + L0;
+        m.out = c->d_mv + L0 * nb;
         m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
         m.sc = c->p.frac_me ? 2 : 1;
         m.nphase = c->p.frac_me ? 4 : 1;
         m.R = c->p.search_range;
         m.Rh = c->p.search_range * m.sc;
-        const int e0 = tick(c);
+        const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
-            CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
+            CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st_me));
         } else {
-            CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->st));
+            CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, st_me));
         }
-        const int e1 = tick(c);
+        const int e1 = tick(c, st_me);
         span(c, BVC_K_ME, e0, e1);
-        CK(launch_tq_pframe(t, nl, c->st));
-        span(c, BVC_K_TQ_P, e1, tick(c));
+        int e1p = e1;
+        if (st_post != st_me) {
+            CK(cudaEventRecord(ev_me_done, st_me));
+            CK(cudaStreamWaitEvent(st_post, ev_me_done, 0));
+            e1p = tick(c, st_post);
+        }
+        CK(launch_tq_pframe(t, nl, st_post));
+        span(c, BVC_K_TQ_P, e1p, tick(c, st_post));
         c->launches += 2;
     }
     PackArgs pk{};
-    pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
-    pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
-    pk.coef_off = c->d_coef_off;
-    pk.lanes = c->d_fr_lanes + sp.desc_off;
+    pk.mv = t.mv; pk.modes = t.modes; pk.qp_rows = t.qp_rows;
+    pk.blk_bits = t.blk_bits; pk.blk_nbits = t.blk_nbits; pk.blk_words = c->blk_words;
+    pk.coef_off = c->d_coef_off + L0 * (nb + 1);
+    pk.lanes = t.lanes;
     pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
-    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh; pk.pred_row_off = c->d_pred_row_off + L0 * (g.bh + 1);
     pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
-    const int ep = tick(c);
-    CK(launch_pack(pk, nl, c->st));
-    span(c, BVC_K_PACK, ep, tick(c));
+    const int ep = tick(c, st_post);
+    CK(launch_pack(pk, nl, st_post));
+    span(c, BVC_K_PACK, ep, tick(c, st_post));
     c->launches += 2;
     return BVC_OK;
+}
+static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api) {
+    return enqueue_step(c, sp, frame_api, c->st, c->st, 0, sp.nl, nullptr);
 }
 
 // half-pel phase planes (K2).  Descriptors (phase-0 plane pointers and the three destination planes
@@ -440,12 +484,13 @@ static int upload_halfpel_desc(bvc_ctx* c, const std::vector<int>& planes, size_
     CK(cudaMemcpy(c->d_hp_dst + desc_off, dst.data(), n * sizeof(void*), cudaMemcpyHostToDevice));
     return BVC_OK;
 }
-static int enqueue_halfpel(bvc_ctx* c, size_t desc_off, int n) {
+static int enqueue_halfpel(bvc_ctx* c, size_t desc_off, int n, cudaStream_t st = nullptr) {
     if (!c->p.frac_me || n <= 0) return BVC_OK;
+    if (!st) st = c->st;
     const Geom& g = c->g;
-    const int e0 = tick(c);
-    CK(launch_halfpel(c->d_hp_src + desc_off, c->d_hp_dst + desc_off, n, g.W, g.H, g.pitch, g.plane_bytes, c->st));
-    span(c, BVC_K_HALFPEL, e0, tick(c));
+    const int e0 = tick(c, st);
+    CK(launch_halfpel(c->d_hp_src + desc_off, c->d_hp_dst + desc_off, n, g.W, g.H, g.pitch, g.plane_bytes, st));
+    span(c, BVC_K_HALFPEL, e0, tick(c, st));
     c->launches += 1;
     return BVC_OK;
 }
@@ -841,18 +886,46 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     }
 
     // ---- the whole clip is enqueued without a single host wait ----
+    // Lane groups: group gi owns lanes [gi*per, (gi+1)*per) of every step and two streams.  Inside a group
+    // the order is ME(k) -> [TQ, pack, half-pel, recon download](k) -> ME(k+1); across groups there is no
+    // dependency, so the post-ME kernels of one group run while the other groups search.
+    const int NG = std::max(1, std::min(c->ngroups, G));
+    const int per = (G + NG - 1) / NG;
+    for (int gi = 0; gi < NG; gi++) {
+        CK(cudaStreamWaitEvent(c->st_grp[gi], ev_clip0, 0));
+        CK(cudaStreamWaitEvent(c->st_post[gi], ev_clip0, 0));
+    }
     for (size_t s = 0; s < nsteps; s++) {
-        if (host_frames) {
-            CK(cudaStreamWaitEvent(c->st, ev_h2d[s], 0));
+        if (host_frames)
             if ((rc = enqueue_upload(s + 3)) != BVC_OK) return rc;
+        for (int gi = 0; gi < NG; gi++) {
+            const int l0 = gi * per, nl = std::min(steps[s].nl, l0 + per) - l0;
+            if (nl <= 0) continue;
+            cudaStream_t sm = NG == 1 ? c->st : c->st_grp[gi], spst = NG == 1 ? c->st : c->st_post[gi];
+            if (host_frames) {
+                CK(cudaStreamWaitEvent(sm, ev_h2d[s], 0));
+                if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s], 0));
+            }
+            if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi])) != BVC_OK) return rc;
+            // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
+            if ((rc = enqueue_halfpel(c, steps[s].desc_off + l0, nl, spst)) != BVC_OK) return rc;
+            if (recon) {
+                for (int l = l0; l < l0 + nl; l++)
+                    if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]), spst)) != BVC_OK)
+                        return rc;
+            }
+            if (spst != sm) {   // the next motion search of this group needs this step's reconstructions
+                CK(cudaEventRecord(c->ev_post[gi], spst));
+                CK(cudaStreamWaitEvent(sm, c->ev_post[gi], 0));
+            }
         }
-        if ((rc = enqueue_step(c, steps[s], false)) != BVC_OK) return rc;
-        // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
-        if ((rc = enqueue_halfpel(c, steps[s].desc_off, steps[s].nl)) != BVC_OK) return rc;
-        if (recon) {
-            for (int l = 0; l < steps[s].nl; l++)
-                if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]))) != BVC_OK)
-                    return rc;
+    }
+    if (NG > 1) {
+        for (int gi = 0; gi < NG; gi++) {
+            CK(cudaEventRecord(c->ev_post[gi], c->st_post[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
+            CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
         }
     }
     // ---- container (encoder.py:104-121) assembled on the device, one download ----

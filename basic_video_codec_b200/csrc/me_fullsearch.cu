@@ -387,6 +387,9 @@ cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStre
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // largest shared-memory carve-out: CTAs of other kernels (another lane group's tail) never wait for a re-partition
+        e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, lanes);

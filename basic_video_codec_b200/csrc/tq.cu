@@ -232,6 +232,8 @@ cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         once = true;
     }
     const int nb = a.row_count * a.bw;
@@ -245,6 +247,12 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(WarpTile<BS>) + BS * BS + 2 * NBW * BS + 64;
     const int ngrp = (lanes + NBW - 1) / NBW;
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(tq_iframe_kernel<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
     tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
     return cudaGetLastError();
 }

@@ -28,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
+# DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r1_ncu_*.csv)
+ME_TRAFFIC_BYTES_PER_LANE = (83.670784e6 + 5.514240e6) / 20
+TQ_TRAFFIC_BYTES_PER_LANE = (89.095168e6 + 26.661120e6) / 20
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
 
@@ -61,7 +64,7 @@ class ClockSampler:
             os.close(fd)
             q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -213,27 +216,27 @@ def main():
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     t0 = time.perf_counter()
     dev_ms = 0.0
-    kt_acc = None
     for _ in range(args.steps):
         _, nbytes = ctx.encode_clip_resident(NFRAMES, out_buf)
-        kt, clip_ms = ctx.last_kernel_times()
-        dev_ms += clip_ms
-        if kt_acc is None:
-            kt_acc = {k: [0.0, 0] for k in kt}
-        for k, (ms, n) in kt.items():
-            kt_acc[k][0] += ms
-            kt_acc[k][1] += n
+        dev_ms += ctx.last_kernel_times()[1]
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
     dt = max_over_ranks(dt)
     dev_ms = max_over_ranks(dev_ms)
     value = world * NFRAMES * args.steps / dt
+    if world > 1:   # every rank samples its own GPU; report the slowest clock and the union of throttle reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        ok = [c for c in allc if c and c.get("sm_mhz")]
+        if ok:
+            clocks = {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] for c in ok),
+                      "reasons": sorted({r for c in ok for r in c["reasons"]}), "samples": sum(c.get("samples", 0) for c in ok),
+                      "per_rank_sm_mhz": [c["sm_mhz"] for c in ok]}
 
     # ---- e2e: host buffers through the public API ---------------------------------------------------
     ctx.encode_clip_into(frames, out_buf)  # warm-up of the host path
@@ -247,7 +250,31 @@ def main():
     e2e_val = world * NFRAMES * e2e_steps / dt_e2e
 
     # ---- roofline of the dominant kernel (motion estimation) ----------------------------------------
+    # The timed steps above run two lane groups on separate streams (kernels of different groups overlap, so
+    # event spans around a kernel are not exclusive).  Per-kernel launch durations are therefore taken from extra
+    # passes over the same resident clip with one lane group: every kernel back to back on one stream, CUDA events
+    # on that stream around each launch.
+    groups = ctx.lane_groups
+    ctx.set_lane_groups(1)
+    ctx.encode_clip_resident(NFRAMES, out_buf)
+    kt_acc = None
+    serial_ms = 0.0
+    KSTEPS = 2
+    for _ in range(KSTEPS):
+        ctx.encode_clip_resident(NFRAMES, out_buf)
+        kt, clip_ms = ctx.last_kernel_times()
+        serial_ms += clip_ms / KSTEPS
+        if kt_acc is None:
+            kt_acc = {k: [0.0, 0] for k in kt}
+        for k, (ms, n) in kt.items():
+            kt_acc[k][0] += ms
+            kt_acc[k][1] += n
+    ctx.set_lane_groups(groups)
     me_ms, me_n = kt_acc["me"]
+    me_ms_all = [None] * world
+    if world > 1:
+        dist.all_gather_object(me_ms_all, me_ms / max(1, me_n))
+        me_ms, me_n = max(me_ms_all) * me_n, me_n          # slowest rank
     px_per_launch = ctx.me_work_per_frame(1) * args.lanes        # one launch = frame k of every GOP lane
     me_avg_s = me_ms / max(1, me_n) * 1e-3
     achieved = px_per_launch / me_avg_s if me_avg_s > 0 else 0.0
@@ -262,7 +289,7 @@ def main():
         "warmup": max(3, args.warmup), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 SAD / int16 residual / f64 DCT", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_frames_per_step": world * NFRAMES,
-                   "parallelism": f"GOP-sharded: {world} rank(s) x {args.lanes} GOP lanes, no collective on the data path",
+                   "parallelism": f"GOP-sharded: {world} rank(s) x {args.lanes} GOP lanes in {groups} lane groups, no collective on the data path",
                    "l2": "inputs larger than L2 (1.25 GB clip per rank, 42 MB of planes per launch)"},
         "device_ms_per_step": dev_ms / args.steps,
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes),
@@ -272,17 +299,24 @@ def main():
         "roofline": {
             "kernel": "me_tiled_kernel<16,4> (full-search SAD, VABSDIFF4.U8.ACC)", "bound": "int-simd",
             "achieved": achieved / 1e12, "peak": peaks["px_per_s"] / 1e12, "unit": "Tpx-absdiff/s",
-            "frac": achieved / peaks["px_per_s"], "traffic": None,
+            "frac": achieved / peaks["px_per_s"], "traffic": ME_TRAFFIC_BYTES_PER_LANE * args.lanes,
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 20-lane launch / 20 (profiles/r1_ncu_me_kernel.csv); "
+                              "algorithmic: 2 planes of 2.09 MB per lane",
+            "algorithmic_bytes": 2 * W * H * args.lanes + 16 * (W // BS) * (H // BS) * args.lanes,
             "peak_source": peaks["int_src"], "launch_ms": me_avg_s * 1e3, "launches": me_n,
+            "per_rank_launch_ms": me_ms_all if world > 1 else None,
             "gpos_per_s": achieved / (BS * BS) / 1e9, "share_of_kernel_time": share["me"] / tot,
         },
         "roofline_transform": {
             "kernel": "tq_pframe_kernel<16> (residual+DCT+quant+IDCT+recon+entropy, fp64)", "bound": "hbm",
             "achieved": tq_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tq_gbs / peaks["hbm_gbs"],
-            "peak_source": peaks["hbm_src"], "traffic": None, "share_of_kernel_time": share["tq_p"] / tot,
+            "peak_source": peaks["hbm_src"], "traffic": TQ_TRAFFIC_BYTES_PER_LANE * args.lanes,
+            "share_of_kernel_time": share["tq_p"] / tot,
             "note": "fp64-pipe bound (32 DFMA/px), not HBM bound: see DESIGN.md",
         },
-        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt_acc.items()},
+        "kernel_ms_per_step": {k: v[0] / KSTEPS for k, v in kt_acc.items()},
+        "kernel_timing": f"{KSTEPS} extra passes with one lane group (kernels serialised on one stream, {serial_ms:.2f} ms per pass); "
+                         "the timed steps overlap kernel tails across lane groups",
         "bitstream_bytes_per_step": int(nbytes),
     }
 

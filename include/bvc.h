@@ -119,6 +119,12 @@ int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
 int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
                              uint8_t *recon);
 
+/* Lane groups of the clip path: the max_lanes GOP lanes of a step are split into `groups` (1..4) groups with
+ * their own CUDA streams, so that the tail of one group's motion search is filled by the other groups' kernels.
+ * 1 = every kernel of a step back to back on one stream (the per-kernel timings of bvc_last_kernel_times are
+ * exclusive only then).  Default 2 (environment override: BVC_LANE_GROUPS).  The output does not depend on it. */
+int bvc_set_lane_groups(bvc_ctx *ctx, int groups);
+
 /* instrumentation --------------------------------------------------------------------------- */
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t bvc_launch_count(const bvc_ctx *ctx);

@@ -353,3 +353,25 @@ def test_error_mapping():
             ctx.encode_pframe(np.zeros((32, 32), np.uint8), [])       # empty reference window
         with pytest.raises(MemoryError):
             ctx.encode_clip(np.zeros((2, 32, 32), np.uint8), out_capacity=4)
+
+
+def test_lane_groups_do_not_change_the_stream():
+    """bvc_set_lane_groups only changes which CUDA streams the lanes of a step run on: same bytes for 1..4 groups,
+    including a short last GOP, more groups than lanes, and half-pel planes (which add a kernel to the post chain)."""
+    ob = _ob()
+    H, W, bs, r, qp, ip, n = 64, 96, 16, 8, 3, 4, 27
+    frames = synth.moving_clip(21, H, W, n, step=4, clamp=24)
+    for frac, nref in ((False, 2), (True, 1)):
+        cfg = ob.make_config(W, H, bs, r, qp, nref=nref, frac=frac, i_period=ip)
+        want, want_recon = ob.encode_clip(cfg, frames)
+        for lanes, groups in ((7, 1), (7, 2), (7, 3), (7, 4), (2, 4), (1, 2)):
+            with _ctx(W, H, bs, r, qp, nref, False, frac, ip, lanes=lanes) as ctx:
+                ctx.set_lane_groups(groups)
+                data, recon = ctx.encode_clip(frames, want_recon=True)
+            assert data == want, f"frac={frac} lanes={lanes} groups={groups}"
+            assert np.array_equal(recon, want_recon)
+    with _ctx(W, H, bs, r, qp, 1, False, False, ip, lanes=2) as ctx:
+        with pytest.raises(ValueError):
+            ctx.set_lane_groups(0)
+        with pytest.raises(ValueError):
+            ctx.set_lane_groups(5)
