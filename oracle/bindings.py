@@ -203,3 +203,27 @@ def encode_clip(cfg: Config, frames: np.ndarray, nthreads: int = 1, want_recon: 
     if rc != 0:
         raise RuntimeError(f"bvo_encode_clip rc={rc}")
     return data, recon
+
+
+def decode_clip(cfg: Config, data: bytes, max_frames: int, details: bool = False):
+    """decode_video (decoder.py:26-87).  Returns decoded planes (n,H,W) [, levels, pred, qp_rows, kinds]."""
+    L = lib()
+    H, W, bs = cfg.height, cfg.width, cfg.block
+    nblk, rows = (W // bs) * (H // bs), H // bs
+    buf = np.frombuffer(data, dtype=np.uint8)
+    frames = np.zeros((max_frames, H, W), np.uint8)
+    n = C.c_int(0)
+    lev = np.zeros((max_frames, H, W), np.int16) if details else None
+    pred = np.zeros((max_frames, nblk, 3), np.int32) if details else None
+    qps = np.zeros((max_frames, rows), np.int32) if details else None
+    kinds = np.zeros(max_frames, np.uint8) if details else None
+    L.bvo_decode_clip.restype = C.c_int
+    rc = L.bvo_decode_clip(C.byref(cfg), _p(buf), C.c_size_t(buf.size), int(max_frames), _p(frames), C.byref(n),
+                           _p(lev) if details else None, _p(pred) if details else None, _p(qps) if details else None,
+                           _p(kinds) if details else None)
+    if rc != 0:
+        raise ValueError("malformed stream")
+    k = n.value
+    if details:
+        return frames[:k], lev[:k], pred[:k], qps[:k], kinds[:k]
+    return frames[:k]

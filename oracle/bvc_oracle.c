@@ -642,4 +642,196 @@ int bvo_encode_clip(const bvo_config *cfg, const uint8_t *frames, int nframes, i
     return rc;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Decoder: decode_video (decoder.py:26-87).  Restated so that the GPU decoder has a CPU  */
+/* checker; pinned by running the reference's own decode_video on the golden streams                       */
+/* (oracle/gen_golden_decode.py, tests/golden/decode_ref.json).                                            */
+
+typedef struct { const uint8_t *d; size_t nbits, pos; } bitrd;
+static inline int rd_bit(const bitrd *r, size_t i) { return (r->d[i >> 3] >> (7 - (i & 7))) & 1; }
+/* exp_golomb_decode, entropy_encoder.py:32-62.  Returns 1 = symbol, 0 = end of stream (fewer than 8 zero
+ * bits of byte padding left, :40-44), -1 = "Not enough bits" (ValueError, :45-46). */
+static int rd_eg(bitrd *r, int32_t *out)
+{
+    size_t m = 0, left = r->nbits - r->pos;
+    while (m < left && !rd_bit(r, r->pos + m)) m++;
+    if (m >= left) return left < 8 ? 0 : -1;
+    if (r->pos + 2 * m + 1 > r->nbits || m > 30) return -1; /* the reference would index past the end (IndexError) */
+    uint32_t value = 1;
+    for (size_t i = 1; i <= m; i++) value = (value << 1) | (uint32_t)rd_bit(r, r->pos + m + i);
+    value -= 1;
+    *out = (value % 2 == 0) ? -(int32_t)(value / 2) : (int32_t)((value + 1) / 2); /* :57 */
+    r->pos += 2 * m + 1;
+    return 1;
+}
+
+/* Frame.entropy_decode_dct_coffs, Frame.py:81-110: symbols -> blocks at every EOB marker -> rle_decode
+ * (entropy_encoder.py:91-112) -> pad to bs*bs -> inverse_zigzag_order (:138-160) -> merge_blocks (raster). */
+static int decode_coefs(const bvo_config *cfg, const uint8_t *data, size_t nbytes, int16_t *levels)
+{
+    const int W = cfg->width, H = cfg->height, bs = cfg->block, bw = W / bs, nblk = bw * (H / bs), n = bs * bs;
+    bitrd r = {data, nbytes * 8, 0};
+    int32_t *sym = (int32_t *)malloc(sizeof(int32_t) * (2 * (size_t)n + 8));
+    int16_t zz[BVO_MAX_BS * BVO_MAX_BS];
+    int nsym = 0, b = 0, rc = 0;
+    memset(levels, 0, sizeof(int16_t) * (size_t)W * H);
+    for (;;) {
+        int32_t v;
+        int k = rd_eg(&r, &v);
+        if (k == 0) break;
+        if (k < 0) { rc = -1; break; }
+        if (v != BVO_EOB) {
+            if (nsym >= 2 * n + 8) { rc = -1; break; }
+            sym[nsym++] = v;
+            continue;
+        }
+        if (b >= nblk) { rc = -1; break; }
+        /* rle_decode */
+        int len = 0;
+        memset(zz, 0, sizeof zz);
+        for (int i = 0; i < nsym; i++) {
+            int32_t c = sym[i];
+            if (c == 0) break;
+            if (c > 0) { len += c; continue; }            /* run of zeros */
+            for (int j = 0; j < -c && i + 1 + j < nsym; j++, len++)
+                if (len < n) zz[len] = (int16_t)sym[i + 1 + j];
+            i += -c;
+        }
+        nsym = 0;
+        /* inverse zig-zag into block b (raster order) */
+        const int ox = (b % bw) * bs, oy = (b / bw) * bs;
+        int idx = 0;
+        for (int sd = 0; sd < 2 * bs - 1; sd++)
+            for (int i = 0; i <= sd; i++) {
+                if (i >= bs || sd - i >= bs) continue;
+                const int rr = (sd % 2 == 0) ? i : sd - i, cc = (sd % 2 == 0) ? sd - i : i;
+                levels[(size_t)(oy + rr) * W + ox + cc] = zz[idx++];
+            }
+        b++;
+    }
+    free(sym);
+    if (rc == 0 && b != nblk) rc = -1;
+    return rc;
+}
+
+/* PFrame / IFrame.entropy_decode_prediction_data (PFrame.py:166-228, IFrame.py:132-166): per block row the QP
+ * difference to the base QP, then per block the MV difference to the previous block in raster order
+ * (chained from (0,0,0)) or the intra mode.  pred: nblk*3 (mvx,mvy,ref | mode,0,0). */
+static int decode_pred(const bvo_config *cfg, const uint8_t *data, size_t nbytes, int intra, int32_t *pred, int32_t *qp_rows)
+{
+    const int bs = cfg->block, bw = cfg->width / bs, bh = cfg->height / bs, nblk = bw * bh;
+    bitrd r = {data, nbytes * 8, 0};
+    int32_t prev[3] = {0, 0, 0}, v;
+    for (int b = 0; b < nblk; b++) {
+        if (b % bw == 0) {
+            if (rd_eg(&r, &v) != 1) return -1;
+            qp_rows[b / bw] = cfg->qp + v;
+        }
+        if (intra) {
+            if (rd_eg(&r, &v) != 1) return -1;
+            pred[3 * b] = v; pred[3 * b + 1] = 0; pred[3 * b + 2] = 0;
+            if (v != 0 && v != 1) return -1;             /* find_intra_predict_block raises ValueError, IFrame.py:175-182 */
+        } else {
+            for (int k = 0; k < (cfg->nref > 1 ? 3 : 2); k++) {
+                if (rd_eg(&r, &v) != 1) return -1;
+                prev[k] += v;
+            }
+            pred[3 * b] = prev[0]; pred[3 * b + 1] = prev[1]; pred[3 * b + 2] = prev[2];
+        }
+    }
+    return 0;
+}
+
+static void dequant_idct(const int16_t *lev, int stride, int bs, int qp, double *id)
+{
+    double resc[BVO_MAX_BS * BVO_MAX_BS];
+    for (int u = 0; u < bs; u++)
+        for (int v = 0; v < bs; v++) resc[u * bs + v] = ldexp((double)lev[(size_t)u * stride + v], bvo_q_shift(bs, qp, u, v));
+    bvo_idct(resc, bs, id);
+}
+
+int bvo_decode_clip(const bvo_config *cfg, const uint8_t *data, size_t len, int max_frames, uint8_t *frames_out,
+                    int *nframes_out, int16_t *levels_out, int32_t *pred_out, int32_t *qp_out, uint8_t *kinds_out)
+{
+    const int W = cfg->width, H = cfg->height, bs = cfg->block, bw = W / bs, bh = H / bs, nblk = bw * bh;
+    const size_t P = (size_t)W * H;
+    const int nref = cfg->nref;
+    /* reference window, decoder.py:34-38: starts with one 128-filled frame; an I frame clears it (:57-58) */
+    uint8_t **refs = (uint8_t **)calloc((size_t)nref, sizeof *refs), **hps = (uint8_t **)calloc((size_t)nref, sizeof *hps);
+    for (int k = 0; k < nref; k++) { refs[k] = (uint8_t *)malloc(P); hps[k] = cfg->frac ? (uint8_t *)malloc(4 * P) : NULL; }
+    int navail = 1;
+    memset(refs[0], 128, P);
+    if (cfg->frac) bvo_halfpel_plane(refs[0], W, H, hps[0]);
+    int16_t *levels = (int16_t *)malloc(sizeof(int16_t) * P);
+    int32_t *pred = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)nblk), *qps = (int32_t *)malloc(sizeof(int32_t) * (size_t)bh);
+    uint8_t *cur = (uint8_t *)malloc(P);
+    double id[BVO_MAX_BS * BVO_MAX_BS];
+    size_t o = 0;
+    int n = 0, rc = 0;
+    while (n < max_frames && o < len) {
+        if (o + 3 > len) { rc = -1; break; }
+        const int mode = data[o];
+        const size_t pl = ((size_t)data[o + 1] << 8) | data[o + 2];
+        if (o + 3 + pl + 3 > len) { rc = -1; break; }
+        const uint8_t *pd = data + o + 3;
+        const size_t cl = ((size_t)pd[pl] << 16) | ((size_t)pd[pl + 1] << 8) | pd[pl + 2];
+        const uint8_t *cd = pd + pl + 3;
+        if (o + 6 + pl + cl > len) { rc = -1; break; }
+        o += 6 + pl + cl;
+        const int intra = (mode == 1); /* PredictionMode.INTRA_FRAME.value, decoder.py:55 */
+        if (intra) navail = 0;
+        if (decode_pred(cfg, pd, pl, intra, pred, qps) || decode_coefs(cfg, cd, cl, levels)) { rc = -1; break; }
+        memset(cur, 0, P);
+        for (int by = 0; by < bh && rc == 0; by++)
+            for (int bx = 0; bx < bw; bx++) {
+                const int b = by * bw + bx, ox = bx * bs, oy = by * bs;
+                dequant_idct(levels + (size_t)oy * W + ox, W, bs, qps[by], id);
+                for (int y = 0; y < bs; y++)
+                    for (int x = 0; x < bs; x++) {
+                        int pv;
+                        if (intra) {   /* find_intra_predict_block IFrame.py:175-213 on the frame being rebuilt */
+                            if (pred[3 * b] == 0) pv = ox > 0 ? cur[(size_t)(oy + x) * W + ox - 1] : 128;
+                            else pv = oy > 0 ? cur[(size_t)(oy - 1) * W + ox + y] : 128;
+                        } else {       /* find_mv_predicted_block PFrame.py:230-244 */
+                            const int k = navail > 1 ? pred[3 * b + 2] : 0;
+                            const int mx = pred[3 * b], my = pred[3 * b + 1];
+                            if (k < 0 || k >= navail) { rc = -1; break; }
+                            if (!cfg->frac) {
+                                if (ox + mx < 0 || oy + my < 0 || ox + mx + bs > W || oy + my + bs > H) { rc = -1; break; }
+                                pv = refs[k][(size_t)(oy + my + y) * W + ox + mx + x];
+                            } else {
+                                if (2 * ox + mx < 0 || 2 * oy + my < 0 || 2 * ox + mx + 2 * bs > 2 * W || 2 * oy + my + 2 * bs > 2 * H) { rc = -1; break; }
+                                pv = hps[k][(size_t)(2 * oy + my + 2 * y) * (2 * W) + 2 * ox + mx + 2 * x];
+                            }
+                        }
+                        /* PFrame.py:305-308 / IFrame.py:107-108: round(idct + pred) -> int16 -> clip -> uint8 */
+                        const double rr = rint(id[y * bs + x] + (double)pv);
+                        const int v = (int)(int16_t)rr;
+                        cur[(size_t)(oy + y) * W + ox + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                    }
+            }
+        if (rc) break;
+        memcpy(frames_out + (size_t)n * P, cur, P);
+        if (levels_out) memcpy(levels_out + (size_t)n * P, levels, sizeof(int16_t) * P);
+        if (pred_out) memcpy(pred_out + (size_t)n * 3 * nblk, pred, sizeof(int32_t) * 3 * (size_t)nblk);
+        if (qp_out) memcpy(qp_out + (size_t)n * bh, qps, sizeof(int32_t) * (size_t)bh);
+        if (kinds_out) kinds_out[n] = (uint8_t)intra;
+        /* reference_frames.append(decoded_frame): deque(maxlen=nRefFrames), decoder.py:84-85 */
+        if (navail == nref) {
+            uint8_t *t = refs[0], *h = hps[0];
+            for (int k = 1; k < nref; k++) { refs[k - 1] = refs[k]; hps[k - 1] = hps[k]; }
+            refs[nref - 1] = t; hps[nref - 1] = h;
+            navail--;
+        }
+        memcpy(refs[navail], cur, P);
+        if (cfg->frac) bvo_halfpel_plane(cur, W, H, hps[navail]);
+        navail++;
+        n++;
+    }
+    *nframes_out = n;
+    for (int k = 0; k < nref; k++) { free(refs[k]); free(hps[k]); }
+    free(refs); free(hps); free(levels); free(pred); free(qps); free(cur);
+    return rc;
+}
+
 void bvo_free(void *p) { free(p); }

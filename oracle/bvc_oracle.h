@@ -130,6 +130,13 @@ void bvo_encode_iframe(const bvo_config *cfg, const uint8_t *cur, const int32_t 
  * (OpenMP); the byte stream is identical.  Returns 0 on success. */
 int bvo_encode_clip(const bvo_config *cfg, const uint8_t *frames, int nframes, int first_index,
                     uint8_t **out, size_t *out_len, uint8_t *recon_out, int nthreads);
+/* decode_video (decoder.py:26-87): parses the container, entropy-decodes both streams of every frame
+ * (Frame.py:81-110, PFrame.py:166-228, IFrame.py:132-166) and rebuilds the frames (PFrame.py:252-317,
+ * IFrame.py:85-114).  frames_out: max_frames planes.  Optional per-frame outputs: levels_out (H*W int16),
+ * pred_out (nblk*3: mvx,mvy,ref or mode,0,0), qp_out (rows), kinds_out (1 = I).  Returns 0, or -1 for a
+ * malformed stream (ValueError / IndexError in the reference). */
+int bvo_decode_clip(const bvo_config *cfg, const uint8_t *data, size_t len, int max_frames, uint8_t *frames_out,
+                    int *nframes_out, int16_t *levels_out, int32_t *pred_out, int32_t *qp_out, uint8_t *kinds_out);
 void bvo_free(void *p);
 
 #ifdef __cplusplus

@@ -163,3 +163,41 @@ def test_dct_is_orthonormal_dct2():
         assert np.max(np.abs(ref - got)) < 1e-9
         back = ob.idct(got)
         assert np.max(np.abs(back - x)) < 1e-9
+
+
+@pytest.mark.parametrize("name", gu.names())
+def test_decoder_oracle_matches_reference_decoder(name):
+    """bvo_decode_clip (decode_video restated) against what the reference's own decode_video produced from the
+    same container bytes (oracle/gen_golden_decode.py -> tests/golden/decode_ref.json), and against the
+    encoder's reconstruction (decode == recon is the reference's own decoder test, tests/test_decoder.py:37-78)."""
+    import json
+    import os
+    ref = json.load(open(os.path.join(gu.GOLD, "decode_ref.json")))[name]
+    g = gu.load(name)
+    n, H, W = g["frames"].shape
+    cfg = _cfg(g["meta"], W, H)
+    dec, lev, pred, qps, kinds = ob.decode_clip(cfg, g["encoded"], n + 3, details=True)
+    assert dec.shape[0] == ref["frames"] == n
+    assert hashlib.sha256(dec.tobytes()).hexdigest() == ref["decoded_sha256"]
+    if "recon" in g:
+        assert np.array_equal(dec, g["recon"])
+    if "levels" in g:
+        assert np.array_equal(lev, g["levels"])
+    assert kinds[0] == 1
+    # max_frames cuts the loop like frames_to_process (decoder.py:49)
+    assert ob.decode_clip(cfg, g["encoded"], 2).shape[0] == 2
+
+
+def test_decoder_oracle_rejects_malformed_streams():
+    g = gu.load("fs_i8_r4_qp3")
+    n, H, W = g["frames"].shape
+    cfg = _cfg(g["meta"], W, H)
+    data = bytearray(g["encoded"])
+    with pytest.raises(ValueError):
+        ob.decode_clip(cfg, bytes(data[:len(data) - 40]), n)          # truncated record
+    bad = bytearray(data)
+    bad[3] ^= 0xFF                                                    # garbage in the first prediction symbols
+    try:
+        ob.decode_clip(cfg, bytes(bad), n)
+    except ValueError:
+        pass
