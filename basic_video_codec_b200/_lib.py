@@ -14,7 +14,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
-    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame",
 ]
 
 
@@ -71,6 +71,10 @@ def load_library():
     L.bvc_clip_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.bvc_set_lane_groups.argtypes = [C.c_void_p, C.c_int]
+    L.bvc_decode_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.bvc_decode_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bvc_launch_count.argtypes = [C.c_void_p]
     L.bvc_launch_count.restype = C.c_int64
     L.bvc_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -252,6 +256,38 @@ class Context:
         ln = C.c_size_t(0)
         self._check(self._L.bvc_encode_clip(self._h, _p(frames), frames.shape[0], _p(out), out.size, C.byref(ln), _p(recon)))
         return int(ln.value)
+
+    # ---- decoder ---------------------------------------------------------------------------------
+    def decode_clip(self, data, max_frames, details=False, out=None):
+        """decode_video on container bytes.  Returns the decoded planes (n,H,W); with details=True also
+        (levels, pred (n,nblk,3), qp_rows (n,rows), kinds)."""
+        buf = np.frombuffer(bytes(data) if not isinstance(data, np.ndarray) else data, dtype=np.uint8)
+        frames = out if out is not None else np.empty((max_frames, self.H, self.W), np.uint8)
+        n = C.c_int(0)
+        lev = np.zeros((max_frames, self.H, self.W), np.int16) if details else None
+        pred = np.zeros((max_frames, self.nblk, 3), np.int32) if details else None
+        qps = np.zeros((max_frames, self.rows), np.int32) if details else None
+        kinds = np.zeros(max_frames, np.uint8) if details else None
+        self._check(self._L.bvc_decode_clip(self._h, _p(buf), buf.size, int(max_frames), _p(frames), C.byref(n), _p(lev), _p(pred),
+                                            _p(qps), _p(kinds)))
+        k = n.value
+        if details:
+            return frames[:k], lev[:k], pred[:k], qps[:k], kinds[:k]
+        return frames[:k]
+
+    def decode_frame(self, intra, pred_bytes, coef_bytes, refs=None):
+        """One container record -> (recon, levels, pred (nblk,3), qp_rows)."""
+        pb = np.frombuffer(bytes(pred_bytes), dtype=np.uint8)
+        cb = np.frombuffer(bytes(coef_bytes), dtype=np.uint8)
+        refs = [np.ascontiguousarray(r, dtype=np.uint8) for r in (refs or [])]
+        arr = (C.c_void_p * max(1, len(refs)))(*[r.ctypes.data for r in refs])
+        recon = np.empty((self.H, self.W), np.uint8)
+        lev = np.empty((self.H, self.W), np.int16)
+        pred = np.zeros((self.nblk, 3), np.int32)
+        qps = np.zeros(self.rows, np.int32)
+        self._check(self._L.bvc_decode_frame(self._h, int(bool(intra)), _p(pb), pb.size, _p(cb), cb.size, arr, len(refs), _p(recon),
+                                             _p(lev), _p(pred), _p(qps)))
+        return recon, lev, pred, qps
 
     def clip_upload(self, frames):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)

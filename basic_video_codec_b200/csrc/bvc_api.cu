@@ -84,6 +84,11 @@ struct bvc_ctx {
     uint8_t** d_hp_dst = nullptr;
     size_t hp_desc_cap = 0;
 
+    // decoder scratch (grow-only device buffers, see dbuf())
+    struct DBuf { void* p = nullptr; size_t cap = 0; };
+    DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
+        dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress;
+
     // host staging
     void* h_desc = nullptr;       // pinned descriptor staging
     size_t h_desc_cap = 0;
@@ -275,6 +280,10 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container);
+    for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
+                             &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
+                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress})
+        cudaFree(b->p);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
@@ -773,6 +782,263 @@ extern "C" int bvc_dct_quant_recon(int device, const int16_t* residual, const in
     int rc = run();
     if (rc != BVC_OK) g_create_error = tmp.err;
     return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// decoder: decode_video (decoder.py:26-87)
+template <typename T>
+static int dbuf(bvc_ctx* c, bvc_ctx::DBuf& b, size_t n, T** out) {
+    const size_t bytes = n * sizeof(T) + 256;   // slack: the tokenizer stages aligned words a little past a stream's end
+    if (bytes > b.cap) {
+        if (b.p) CK(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+        CK(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    *out = reinterpret_cast<T*>(b.p);
+    return BVC_OK;
+}
+
+struct DecRecord { int intra; size_t pred_off, pred_len, coef_off, coef_len; };
+
+// init_refs / n_init: reference window the first frame sees (deque order, oldest first).  n_init < 0: the decoder's
+// own start-up window, one plane filled with 128 (decoder.py:34-38).
+static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_frames, const uint8_t* const* init_refs, int n_init,
+                       uint8_t* frames_out, int* nframes_out, int16_t* levels_out, int32_t* pred_out, int32_t* qp_out,
+                       uint8_t* kinds_out) {
+    const Geom& g = c->g;
+    CK(cudaSetDevice(c->device));
+    if (!data || !nframes_out || max_frames < 0) return fail(c, BVC_ERR_INVALID, "bad arguments");
+    *nframes_out = 0;
+    // ---- container records (decoder.py:46-69) ----
+    std::vector<DecRecord> recs;
+    for (size_t o = 0; o < len && (int)recs.size() < max_frames;) {
+        if (o + 3 > len) return fail(c, BVC_ERR_INVALID, "truncated frame record");
+        DecRecord r;
+        r.intra = data[o] == 1;   // PredictionMode.INTRA_FRAME.value; anything else is decoded as a P frame
+        r.pred_len = ((size_t)data[o + 1] << 8) | data[o + 2];
+        r.pred_off = o + 3;
+        if (r.pred_off + r.pred_len + 3 > len) return fail(c, BVC_ERR_INVALID, "truncated frame record");
+        const uint8_t* q = data + r.pred_off + r.pred_len;
+        r.coef_len = ((size_t)q[0] << 16) | ((size_t)q[1] << 8) | q[2];
+        r.coef_off = r.pred_off + r.pred_len + 3;
+        if (r.coef_off + r.coef_len > len) return fail(c, BVC_ERR_INVALID, "truncated frame record");
+        o = r.coef_off + r.coef_len;
+        recs.push_back(r);
+    }
+    const int n = (int)recs.size();
+    if (n == 0) return BVC_OK;
+    const size_t nb = (size_t)g.nblk;
+    int rc;
+
+    // ---- streams and chunk map ----
+    const int CB = eg_chunk_bits();
+    std::vector<EgStream> streams(2 * (size_t)n);
+    std::vector<uint8_t> intra(n);
+    long long nchunks = 0;
+    for (int f = 0; f < n; f++) {
+        intra[f] = (uint8_t)recs[f].intra;
+        for (int k = 0; k < 2; k++) {
+            EgStream& s = streams[2 * f + k];
+            s.byte0 = (long long)(k ? recs[f].coef_off : recs[f].pred_off);
+            s.nbits = 8LL * (long long)(k ? recs[f].coef_len : recs[f].pred_len);
+            s.chunk0 = nchunks;
+            s.sym0 = 0; s.nsym = 0; s.neob = 0; s.frame = f; s.kind = k;
+            nchunks += (s.nbits + CB - 1) / CB;
+        }
+    }
+    std::vector<int> chunk_stream((size_t)nchunks);
+    for (size_t si = 0; si < streams.size(); si++) {
+        const long long nc = (streams[si].nbits + CB - 1) / CB;
+        std::fill(chunk_stream.begin() + streams[si].chunk0, chunk_stream.begin() + streams[si].chunk0 + nc, (int)si);
+    }
+    uint8_t *d_in, *d_exit, *d_neob, *d_entry, *d_intra;
+    uint16_t* d_nsym;
+    EgStream* d_streams;
+    int *d_chunk_stream, *d_symbase, *d_eobbase, *d_blk_start, *d_progress;
+    int4* d_mv;
+    int32_t *d_modes, *d_qp;
+    long long* d_sym0;
+    int16_t *d_syms, *d_levels = nullptr;
+    FrameLane* d_lanes;
+    if ((rc = dbuf(c, c->dec_in, len, &d_in)) || (rc = dbuf(c, c->dec_streams, streams.size(), &d_streams)) ||
+        (rc = dbuf(c, c->dec_chunk_stream, (size_t)nchunks, &d_chunk_stream)) || (rc = dbuf(c, c->dec_exit, (size_t)nchunks * 32, &d_exit)) ||
+        (rc = dbuf(c, c->dec_nsym, (size_t)nchunks * 32, &d_nsym)) || (rc = dbuf(c, c->dec_neob, (size_t)nchunks * 32, &d_neob)) ||
+        (rc = dbuf(c, c->dec_entry, (size_t)nchunks, &d_entry)) || (rc = dbuf(c, c->dec_symbase, (size_t)nchunks, &d_symbase)) ||
+        (rc = dbuf(c, c->dec_eobbase, (size_t)nchunks, &d_eobbase)) || (rc = dbuf(c, c->dec_intra, (size_t)n, &d_intra)) ||
+        (rc = dbuf(c, c->dec_mv, (size_t)n * nb, &d_mv)) || (rc = dbuf(c, c->dec_modes, (size_t)n * nb, &d_modes)) ||
+        (rc = dbuf(c, c->dec_qp, (size_t)n * g.bh, &d_qp)) || (rc = dbuf(c, c->dec_blk_start, (size_t)n * (nb + 1), &d_blk_start)) ||
+        (rc = dbuf(c, c->dec_sym0, (size_t)n, &d_sym0)) || (rc = dbuf(c, c->dec_progress, (size_t)c->max_lanes * g.bh, &d_progress)))
+        return rc;
+    if (levels_out && (rc = dbuf(c, c->dec_levels, (size_t)n * g.W * g.H, &d_levels))) return rc;
+    CK(cudaMemsetAsync(d_in + len, 0, 256, c->st));
+    CK(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(d_streams, streams.data(), streams.size() * sizeof(EgStream), cudaMemcpyHostToDevice, c->st));
+    if (nchunks) CK(cudaMemcpyAsync(d_chunk_stream, chunk_stream.data(), (size_t)nchunks * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(d_intra, intra.data(), (size_t)n, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st));   // reused as the decoder's error flag
+
+    // ---- D1/D2: tokenize (speculative walk + chain); symbol totals come back to size the symbol array ----
+    CK(launch_eg_tokenize_spec(d_in, d_streams, (int)streams.size(), d_chunk_stream, nchunks, d_exit, d_nsym, d_neob, d_entry, d_symbase,
+                               d_eobbase, c->d_overflow, c->st));
+    c->launches += 2;
+    int err = 0;
+    CK(cudaMemcpyAsync(streams.data(), d_streams, streams.size() * sizeof(EgStream), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(&err, c->d_overflow, sizeof err, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (err) return fail(c, BVC_ERR_INVALID, "malformed exp-Golomb stream (not enough bits / code too long)");
+    long long total_syms = 0;
+    std::vector<long long> sym0(n);
+    for (size_t si = 0; si < streams.size(); si++) {
+        streams[si].sym0 = total_syms;
+        total_syms += streams[si].nsym;
+        if (streams[si].kind == 1) {
+            sym0[streams[si].frame] = streams[si].sym0;
+            if (streams[si].neob != g.nblk) return fail(c, BVC_ERR_INVALID, "coefficient stream does not hold one EOB-terminated run per block");
+        }
+    }
+    if ((rc = dbuf(c, c->dec_syms, (size_t)total_syms + 8, &d_syms))) return rc;
+    CK(cudaMemcpyAsync(d_streams, streams.data(), streams.size() * sizeof(EgStream), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(d_sym0, sym0.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->st));
+    // ---- D3/D4: symbols, block starts, motion vectors / modes / row QPs of every frame ----
+    CK(launch_eg_tokenize_emit(d_in, d_streams, d_chunk_stream, nchunks, d_entry, d_symbase, d_eobbase, d_syms, d_blk_start, g.nblk, c->st));
+    CK(launch_pred_decode(d_streams, d_syms, d_intra, n, d_mv, d_modes, d_qp, g.bw, g.bh, c->p.qp, c->p.nref_frames > 1, c->d_overflow, c->st));
+    c->launches += 2;
+
+    // ---- GOP lanes: a GOP starts at every I frame (the window is cleared, decoder.py:55-58) ----
+    struct Gop { int first, count, virt0; };
+    std::vector<Gop> gops;
+    for (int f = 0; f < n; f++) {
+        if (intra[f] || gops.empty()) gops.push_back({f, 0, 0});
+        gops.back().count++;
+    }
+    const int nin = n_init < 0 ? 1 : n_init;
+    if (!intra[0]) gops[0].virt0 = nin;     // leading P frames see the start-up window
+    if (!intra[0] && nin < 1) return fail(c, BVC_ERR_INVALID, "P frame without a reference frame");
+    if (nin > c->p.nref_frames) return fail(c, BVC_ERR_INVALID, "more initial references than nref_frames");
+    const int G = c->max_lanes;
+    std::vector<FrameLane> frl;
+    struct DStep { size_t off_i, n_i, off_p, n_p; std::vector<int> frames, outplanes; };
+    std::vector<DStep> steps;
+    for (size_t g0 = 0; g0 < gops.size(); g0 += G) {
+        const size_t g1 = std::min(gops.size(), g0 + G);
+        int maxlen = 0;
+        for (size_t gi = g0; gi < g1; gi++) maxlen = std::max(maxlen, gops[gi].count);
+        for (int k = 0; k < maxlen; k++) {
+            DStep st{};
+            std::vector<FrameLane> li, lp;
+            std::vector<int> fi, fp, oi, op;
+            for (size_t gi = g0; gi < g1; gi++) {
+                if (k >= gops[gi].count) continue;
+                const int lane = (int)(gi - g0), f = gops[gi].first + k, vk = k + gops[gi].virt0;
+                FrameLane fl{};
+                fl.cur_plane = 0; fl.slot = f;
+                fl.out_plane = ring_plane(c, lane, vk % c->slots);
+                const int nav = intra[f] ? 0 : std::min(vk, c->p.nref_frames);
+                fl.nref = nav;
+                for (int j = 0; j < nav; j++) fl.ref_plane[j] = ring_plane(c, lane, (vk - nav + j) % c->slots);
+                (intra[f] ? li : lp).push_back(fl);
+                (intra[f] ? fi : fp).push_back(f);
+                (intra[f] ? oi : op).push_back(fl.out_plane);
+            }
+            st.off_i = frl.size(); st.n_i = li.size();
+            frl.insert(frl.end(), li.begin(), li.end());
+            st.off_p = frl.size(); st.n_p = lp.size();
+            frl.insert(frl.end(), lp.begin(), lp.end());
+            st.frames = fi; st.frames.insert(st.frames.end(), fp.begin(), fp.end());
+            st.outplanes = oi; st.outplanes.insert(st.outplanes.end(), op.begin(), op.end());
+            steps.push_back(std::move(st));
+        }
+    }
+    if ((rc = dbuf(c, c->dec_lanes, frl.size(), &d_lanes))) return rc;
+    CK(cudaMemcpyAsync(d_lanes, frl.data(), frl.size() * sizeof(FrameLane), cudaMemcpyHostToDevice, c->st));
+    if (c->p.frac_me) {
+        if ((rc = ensure_lane_desc(c, frl.size() + (size_t)nin)) != BVC_OK) return rc;
+        for (auto& st : steps)
+            if ((rc = upload_halfpel_desc(c, st.outplanes, st.off_i)) != BVC_OK) return rc;
+    }
+    // start-up window of lane 0
+    if (gops[0].virt0) {
+        std::vector<int> hp;
+        for (int j = 0; j < nin; j++) {
+            const int pl = ring_plane(c, 0, j);
+            if (n_init < 0) CK(launch_fill_plane(plane_ptr(c, pl), g.plane_bytes, 128, c->st));
+            else if ((rc = upload_plane(c, plane_ptr(c, pl), init_refs[j])) != BVC_OK) return rc;
+            hp.push_back(pl);
+        }
+        if (c->p.frac_me) {
+            if ((rc = upload_halfpel_desc(c, hp, frl.size())) != BVC_OK) return rc;
+            if ((rc = enqueue_halfpel(c, frl.size(), nin)) != BVC_OK) return rc;
+        }
+    }
+    // ---- D5/D6 step by step ----
+    DecArgs a{};
+    a.ref_base = c->ref_pool; a.ref_plane_bytes = g.plane_bytes; a.ref_pitch = g.pitch;
+    a.mv_all = d_mv; a.modes_all = d_modes; a.qp_all = d_qp; a.syms = d_syms; a.coef_sym0 = d_sym0; a.blk_start = d_blk_start;
+    a.levels_out = d_levels; a.progress = d_progress; a.err_flag = c->d_overflow;
+    a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
+    for (auto& st : steps) {
+        if (st.n_i) {
+            CK(cudaMemsetAsync(d_progress, 0, st.n_i * g.bh * sizeof(int), c->st));
+            a.lanes = d_lanes + st.off_i;
+            CK(launch_dec_iframe(a, (int)st.n_i, c->st));
+            c->launches += 1;
+        }
+        if (st.n_p) {
+            a.lanes = d_lanes + st.off_p;
+            CK(launch_dec_pframe(a, (int)st.n_p, c->st));
+            c->launches += 1;
+        }
+        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) return rc;
+        if (frames_out)
+            for (size_t l = 0; l < st.frames.size(); l++)
+                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]))) != BVC_OK) return rc;
+    }
+    CK(cudaMemcpyAsync(&err, c->d_overflow, sizeof err, cudaMemcpyDeviceToHost, c->st));
+    if (levels_out) CK(cudaMemcpyAsync(levels_out, d_levels, (size_t)n * g.W * g.H * sizeof(int16_t), cudaMemcpyDeviceToHost, c->st));
+    std::vector<int4> hmv;
+    std::vector<int32_t> hmodes;
+    if (pred_out) {
+        hmv.resize((size_t)n * nb); hmodes.resize((size_t)n * nb);
+        CK(cudaMemcpyAsync(hmv.data(), d_mv, hmv.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hmodes.data(), d_modes, hmodes.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    }
+    if (qp_out) CK(cudaMemcpyAsync(qp_out, d_qp, (size_t)n * g.bh * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    if (err) return fail(c, BVC_ERR_INVALID, "malformed stream (missing prediction symbols, bad intra mode or motion vector out of range)");
+    if (pred_out)
+        for (int f = 0; f < n; f++)
+            for (size_t b = 0; b < nb; b++) {
+                int32_t* o = pred_out + ((size_t)f * nb + b) * 3;
+                if (intra[f]) { o[0] = hmodes[(size_t)f * nb + b]; o[1] = 0; o[2] = 0; }
+                else { const int4 m = hmv[(size_t)f * nb + b]; o[0] = m.x; o[1] = m.y; o[2] = m.z; }
+            }
+    if (kinds_out) memcpy(kinds_out, intra.data(), (size_t)n);
+    *nframes_out = n;
+    return BVC_OK;
+}
+
+extern "C" int bvc_decode_clip(bvc_ctx* c, const uint8_t* data, size_t len, int max_frames, uint8_t* frames_out, int* nframes_out,
+                               int16_t* levels_out, int32_t* pred_out, int32_t* qp_rows_out, uint8_t* kinds_out) {
+    if (!c) return BVC_ERR_INVALID;
+    return decode_impl(c, data, len, max_frames, nullptr, -1, frames_out, nframes_out, levels_out, pred_out, qp_rows_out, kinds_out);
+}
+
+extern "C" int bvc_decode_frame(bvc_ctx* c, int intra, const uint8_t* pred, size_t pred_len, const uint8_t* coef, size_t coef_len,
+                                const uint8_t* const* refs, int nref_avail, uint8_t* recon, int16_t* levels, int32_t* pred_out,
+                                int32_t* qp_rows_out) {
+    if (!c) return BVC_ERR_INVALID;
+    if (pred_len > 0xFFFF || coef_len > 0xFFFFFF || (pred_len && !pred) || (coef_len && !coef)) return fail(c, BVC_ERR_INVALID, "bad payload");
+    if (!intra && (nref_avail < 1 || !refs)) return fail(c, BVC_ERR_INVALID, "nref_avail must be 1..nref_frames");
+    std::vector<uint8_t> rec(6 + pred_len + coef_len);
+    rec[0] = intra ? 1 : 0;
+    rec[1] = (uint8_t)(pred_len >> 8); rec[2] = (uint8_t)pred_len;
+    if (pred_len) memcpy(&rec[3], pred, pred_len);
+    rec[3 + pred_len] = (uint8_t)(coef_len >> 16); rec[4 + pred_len] = (uint8_t)(coef_len >> 8); rec[5 + pred_len] = (uint8_t)coef_len;
+    if (coef_len) memcpy(&rec[6 + pred_len], coef, coef_len);
+    int n = 0;
+    return decode_impl(c, rec.data(), rec.size(), 1, refs, intra ? 0 : nref_avail, recon, &n, levels, pred_out, qp_rows_out, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

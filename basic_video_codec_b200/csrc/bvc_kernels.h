@@ -120,6 +120,47 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
 // prediction symbols (row QP symbol included).  out: device long long[lanes].
 cudaError_t launch_row_bits(const PackArgs& a, int lanes, int row, long long* out, cudaStream_t st);
 
+// ---- decoder (decode.cu) -------------------------------------------------------------------------
+// One exp-Golomb bit stream inside the container image (two per frame: 2f = prediction data, 2f+1 = coefficients).
+struct EgStream {
+    long long byte0;     // first byte of the stream in the container
+    long long nbits;     // 8 * payload bytes
+    long long chunk0;    // first 512-bit chunk of this stream in the chunk tables
+    long long sym0;      // first symbol of this stream in the symbol array (host fills it after the chain pass)
+    int nsym, neob;      // symbols / end-of-block markers found (chain pass)
+    int frame, kind;     // kind: 0 prediction data, 1 coefficients
+};
+struct DecArgs {
+    uint8_t* ref_base;             // reference pool: predictions are read from it, decoded frames written into it
+    size_t ref_plane_bytes;
+    int ref_pitch;
+    const FrameLane* lanes;        // device [lanes]; slot = frame index in the clip
+    const int4* mv_all;            // [nframes][nblk]
+    const int32_t* modes_all;      // [nframes][nblk]
+    const int32_t* qp_all;         // [nframes][bh]
+    const int16_t* syms;           // all symbols of the clip
+    const long long* coef_sym0;    // [nframes] first symbol of the frame's coefficient stream
+    const int* blk_start;          // [nframes][nblk+1] first symbol of every block, relative to coef_sym0
+    int16_t* levels_out;           // [nframes][H][W] or null
+    int* progress;                 // I frames: [lanes][bh] wavefront counters (zeroed)
+    int* err_flag;
+    int W, H, bs, bw, bh, nblk;
+    int frac;
+};
+int eg_chunk_bits();
+cudaError_t launch_eg_tokenize_spec(const uint8_t* data, const EgStream* streams, int nstreams, const int* chunk_stream,
+                                    long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab, uint8_t* entry_tab,
+                                    int* symbase, int* eobbase, int* err_flag, cudaStream_t st);
+cudaError_t launch_eg_tokenize_emit(const uint8_t* data, const EgStream* streams, const int* chunk_stream, long long nchunks,
+                                    const uint8_t* entry_tab, const int* symbase, const int* eobbase, int16_t* syms, int* blk_start,
+                                    int nblk, cudaStream_t st);
+cudaError_t launch_pred_decode(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags, int nframes, int4* mv_all,
+                               int32_t* modes_all, int32_t* qp_all, int bw, int bh, int base_qp, int with_ref, int* err_flag,
+                               cudaStream_t st);
+cudaError_t launch_dec_pframe(const DecArgs& a, int lanes, cudaStream_t st);
+cudaError_t launch_dec_iframe(const DecArgs& a, int lanes, cudaStream_t st);
+cudaError_t launch_fill_plane(uint8_t* p, size_t n, uint8_t v, cudaStream_t st);
+
 // ---- container assembly ---------------------------------------------------------------------------
 struct ContainerArgs {
     const long long* frame_bits;   // device [nframes][2]

@@ -119,6 +119,25 @@ int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
 int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
                              uint8_t *recon);
 
+/* decoder ------------------------------------------------------------------------------------------ */
+/* decode_video (decoder.py:26-87): parses the container (`data`, encoded.bin layout), entropy-decodes both streams
+ * of every frame (Frame.entropy_decode_dct_coffs encoder/Frame.py:81-110, PFrame / IFrame.entropy_decode_prediction_data
+ * encoder/PFrame.py:166-228, encoder/IFrame.py:132-166) and rebuilds the frames (construct_frame_from_dct_and_mv
+ * encoder/PFrame.py:252-317, IFrame.decode_mc_q_dct encoder/IFrame.py:85-114).  At most max_frames frames
+ * (frames_to_process) are decoded; GOPs (I-frame boundaries) are decoded max_lanes at a time.  The context supplies
+ * width/height/block_size, the base qp, nref_frames and frac_me exactly like params.encoder_config does.
+ * frames_out: max_frames planes (H*W each) or NULL.  Optional per-frame outputs, any may be NULL: levels_out (H*W int16,
+ * quantized_dct_residual_frame), pred_out (nblk*3 int32: mvx,mvy,ref for P frames / mode,0,0 for I frames),
+ * qp_rows_out (H/i int32: rc_qp_per_row), kinds_out (1 = I frame).  A malformed stream (ValueError / IndexError in
+ * the reference) returns BVC_ERR_INVALID. */
+int bvc_decode_clip(bvc_ctx *ctx, const uint8_t *data, size_t len, int max_frames, uint8_t *frames_out, int *nframes_out,
+                    int16_t *levels_out, int32_t *pred_out, int32_t *qp_rows_out, uint8_t *kinds_out);
+/* One frame: Frame.entropy_decode_prediction_data + entropy_decode_dct_coffs + decode_mc_q_dct on the payloads of one
+ * container record.  refs: the reference window in deque order (index 0 = oldest), ignored for an I frame. */
+int bvc_decode_frame(bvc_ctx *ctx, int intra, const uint8_t *pred, size_t pred_len, const uint8_t *coef, size_t coef_len,
+                     const uint8_t *const *refs, int nref_avail, uint8_t *recon, int16_t *levels, int32_t *pred_out,
+                     int32_t *qp_rows_out);
+
 /* Lane groups of the clip path: the max_lanes GOP lanes of a step are split into `groups` (1..4) groups with
  * their own CUDA streams, so that the tail of one group's motion search is filled by the other groups' kernels.
  * 1 = every kernel of a step back to back on one stream (the per-kernel timings of bvc_last_kernel_times are
