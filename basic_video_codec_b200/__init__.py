@@ -10,5 +10,6 @@ from .encoder.params import EncoderConfig  # noqa: F401
 from .input_parameters import InputParameters  # noqa: F401
 from ._lib import Context, BvcError, library_path, load_library  # noqa: F401
 from .clip import encode_clip  # noqa: F401
+from .decoder import decode_video, decode_video_framewise  # noqa: F401
 
-__all__ = ["EncoderConfig", "InputParameters", "Context", "BvcError", "encode_clip", "library_path", "load_library"]
+__all__ = ["EncoderConfig", "InputParameters", "Context", "BvcError", "encode_clip", "decode_video", "decode_video_framewise", "library_path", "load_library"]

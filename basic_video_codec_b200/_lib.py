@@ -275,6 +275,14 @@ class Context:
             return frames[:k], lev[:k], pred[:k], qps[:k], kinds[:k]
         return frames[:k]
 
+    def decode_prediction_data(self, intra, pred_bytes):
+        """entropy_decode_prediction_data on its own -> (pred (nblk,3), qp_rows)."""
+        pb = np.frombuffer(bytes(pred_bytes), dtype=np.uint8)
+        pred = np.zeros((self.nblk, 3), np.int32)
+        qps = np.zeros(self.rows, np.int32)
+        self._check(self._L.bvc_decode_frame(self._h, int(bool(intra)), _p(pb), pb.size, None, 0, None, 0, None, None, _p(pred), _p(qps)))
+        return pred, qps
+
     def decode_frame(self, intra, pred_bytes, coef_bytes, refs=None):
         """One container record -> (recon, levels, pred (nblk,3), qp_rows)."""
         pb = np.frombuffer(bytes(pred_bytes), dtype=np.uint8)

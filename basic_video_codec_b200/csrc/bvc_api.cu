@@ -804,9 +804,10 @@ struct DecRecord { int intra; size_t pred_off, pred_len, coef_off, coef_len; };
 
 // init_refs / n_init: reference window the first frame sees (deque order, oldest first).  n_init < 0: the decoder's
 // own start-up window, one plane filled with 128 (decoder.py:34-38).
+// pred_only: stop after the prediction data (Frame.entropy_decode_prediction_data on its own).
 static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_frames, const uint8_t* const* init_refs, int n_init,
                        uint8_t* frames_out, int* nframes_out, int16_t* levels_out, int32_t* pred_out, int32_t* qp_out,
-                       uint8_t* kinds_out) {
+                       uint8_t* kinds_out, bool pred_only = false) {
     const Geom& g = c->g;
     CK(cudaSetDevice(c->device));
     if (!data || !nframes_out || max_frames < 0) return fail(c, BVC_ERR_INVALID, "bad arguments");
@@ -895,7 +896,8 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
         total_syms += streams[si].nsym;
         if (streams[si].kind == 1) {
             sym0[streams[si].frame] = streams[si].sym0;
-            if (streams[si].neob != g.nblk) return fail(c, BVC_ERR_INVALID, "coefficient stream does not hold one EOB-terminated run per block");
+            if (streams[si].neob != g.nblk && !pred_only)
+                return fail(c, BVC_ERR_INVALID, "coefficient stream does not hold one EOB-terminated run per block");
         }
     }
     if ((rc = dbuf(c, c->dec_syms, (size_t)total_syms + 8, &d_syms))) return rc;
@@ -978,6 +980,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     a.mv_all = d_mv; a.modes_all = d_modes; a.qp_all = d_qp; a.syms = d_syms; a.coef_sym0 = d_sym0; a.blk_start = d_blk_start;
     a.levels_out = d_levels; a.progress = d_progress; a.err_flag = c->d_overflow;
     a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
+    if (pred_only) steps.clear();
     for (auto& st : steps) {
         if (st.n_i) {
             CK(cudaMemsetAsync(d_progress, 0, st.n_i * g.bh * sizeof(int), c->st));
@@ -1030,7 +1033,9 @@ extern "C" int bvc_decode_frame(bvc_ctx* c, int intra, const uint8_t* pred, size
                                 int32_t* qp_rows_out) {
     if (!c) return BVC_ERR_INVALID;
     if (pred_len > 0xFFFF || coef_len > 0xFFFFFF || (pred_len && !pred) || (coef_len && !coef)) return fail(c, BVC_ERR_INVALID, "bad payload");
-    if (!intra && (nref_avail < 1 || !refs)) return fail(c, BVC_ERR_INVALID, "nref_avail must be 1..nref_frames");
+    const bool pred_only = coef == nullptr;
+    if (pred_only) { coef_len = 0; refs = nullptr; nref_avail = intra ? 0 : 1; recon = nullptr; levels = nullptr; }
+    else if (!intra && (nref_avail < 1 || !refs)) return fail(c, BVC_ERR_INVALID, "nref_avail must be 1..nref_frames");
     std::vector<uint8_t> rec(6 + pred_len + coef_len);
     rec[0] = intra ? 1 : 0;
     rec[1] = (uint8_t)(pred_len >> 8); rec[2] = (uint8_t)pred_len;
@@ -1038,7 +1043,8 @@ extern "C" int bvc_decode_frame(bvc_ctx* c, int intra, const uint8_t* pred, size
     rec[3 + pred_len] = (uint8_t)(coef_len >> 16); rec[4 + pred_len] = (uint8_t)(coef_len >> 8); rec[5 + pred_len] = (uint8_t)coef_len;
     if (coef_len) memcpy(&rec[6 + pred_len], coef, coef_len);
     int n = 0;
-    return decode_impl(c, rec.data(), rec.size(), 1, refs, intra ? 0 : nref_avail, recon, &n, levels, pred_out, qp_rows_out, nullptr);
+    return decode_impl(c, rec.data(), rec.size(), 1, refs, intra ? 0 : (pred_only ? -1 : nref_avail), recon, &n, levels, pred_out,
+                       qp_rows_out, nullptr, pred_only);
 }
 
 // ---------------------------------------------------------------------------------------------

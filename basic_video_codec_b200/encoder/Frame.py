@@ -153,6 +153,43 @@ class Frame:
         self.avg_mae = r.avg_mae
         self.total_mae_comparisons = r.mae_comparisons
 
+    # ---- decoder side (reference Frame.py:81-110, PFrame.py:133-134,166-228, IFrame.py:85-114,132-166) ---------
+    def _dec_ctx(self, params):
+        ec = params.encoder_config
+        bs = ec.block_size
+        W, H = params.width + (-params.width) % bs, params.height + (-params.height) % bs
+        return context_for(ec, W, H, self.device)
+
+    def entropy_decode_prediction_data(self, enc, params):
+        """Motion vectors / intra modes and the per-row QPs of one frame from its prediction payload."""
+        ec = params.encoder_config
+        ctx = self._dec_ctx(params)
+        self._pred_payload = bytes(enc)
+        pred, qps = ctx.decode_prediction_data(self.is_iframe(), self._pred_payload)
+        self.rc_qp_per_row = [int(q) for q in qps]
+        bs, bw = ec.block_size, ctx.W // ec.block_size
+        if self.is_iframe():
+            self.intra_modes = [int(m) for m in pred[:, 0]]
+            return self.intra_modes
+        self.mv_field = {((b % bw) * bs, (b // bw) * bs): (int(pred[b, 0]), int(pred[b, 1]), int(pred[b, 2])) for b in range(pred.shape[0])}
+        return self.mv_field
+
+    def entropy_decode_dct_coffs(self, params):
+        """quantized_dct_residual_frame from self.entropy_encoded_DCT_coffs (bytes).  The GPU call decodes and
+        rebuilds the frame in one go; decode_mc_q_dct then returns the rebuilt frame."""
+        ctx = self._dec_ctx(params)
+        refs = None if self.is_iframe() else [np.ascontiguousarray(r) for r in self.reference_frames]
+        rec, lev, _, _ = ctx.decode_frame(self.is_iframe(), getattr(self, "_pred_payload", b""), bytes(self.entropy_encoded_DCT_coffs), refs)
+        self.quantized_dct_residual_frame = lev
+        self._decoded = rec
+        return lev
+
+    def decode_mc_q_dct(self, frame_shape, encoder_config):
+        if getattr(self, "_decoded", None) is None:
+            raise ValueError("call entropy_decode_prediction_data and entropy_decode_dct_coffs first")
+        self.curr_frame = self._decoded
+        return self._decoded
+
     def is_iframe(self):
         return self.prediction_mode == PredictionMode.INTRA_FRAME
 

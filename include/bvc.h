@@ -133,7 +133,8 @@ int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out
 int bvc_decode_clip(bvc_ctx *ctx, const uint8_t *data, size_t len, int max_frames, uint8_t *frames_out, int *nframes_out,
                     int16_t *levels_out, int32_t *pred_out, int32_t *qp_rows_out, uint8_t *kinds_out);
 /* One frame: Frame.entropy_decode_prediction_data + entropy_decode_dct_coffs + decode_mc_q_dct on the payloads of one
- * container record.  refs: the reference window in deque order (index 0 = oldest), ignored for an I frame. */
+ * container record.  refs: the reference window in deque order (index 0 = oldest), ignored for an I frame.
+ * coef == NULL: prediction data only (entropy_decode_prediction_data on its own): fills pred_out / qp_rows_out. */
 int bvc_decode_frame(bvc_ctx *ctx, int intra, const uint8_t *pred, size_t pred_len, const uint8_t *coef, size_t coef_len,
                      const uint8_t *const *refs, int nref_avail, uint8_t *recon, int16_t *levels, int32_t *pred_out,
                      int32_t *qp_rows_out);

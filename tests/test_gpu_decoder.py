@@ -133,3 +133,56 @@ def test_decode_malformed_streams_raise_value_error():
             pass
         # the context still works afterwards
         assert np.array_equal(ctx.decode_clip(data, n), g["recon"])
+
+
+@pytest.mark.parametrize("name", ["fs_i8_r4_qp3", "frac_fastme_i8_nref3", "fs_i16_r2_nref4"])
+def test_decode_video_dropin(name, tmp_path):
+    """decode_video(InputParameters) reads encoded.bin written by encode_video and writes mc_decoded.yuv == the
+    reconstruction (what the reference's decoder logs as psnr = inf); both the clip call and the frame-object loop."""
+    import basic_video_codec_b200 as bvc
+    from tests.test_gpu_parity import _run_encode_video
+    g = gu.load(name)
+    out = _run_encode_video(tmp_path, g)
+    e = g["meta"]["enc"]
+    n, H, W = g["frames"].shape
+    ec = bvc.EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e.get("nref", 1), fastME=e.get("fastme", False),
+                           fracMeEnabled=e.get("frac", False), resolution=(W, H))
+    params = bvc.InputParameters(str(tmp_path / "clip.y"), W, H, ec, frames_to_process=n)
+    for fn in (bvc.decode_video, bvc.decode_video_framewise):
+        path = os.path.join(out, "mc_decoded.yuv")
+        if os.path.exists(path):
+            os.unlink(path)
+        fn(params)
+        assert open(path, "rb").read() == g["recon"].tobytes(), fn.__name__
+
+
+def test_frame_objects_decode_protocol():
+    """IFrame / PFrame.entropy_decode_prediction_data -> entropy_decode_dct_coffs -> decode_mc_q_dct (decoder.py:60-69)."""
+    from collections import deque
+    import basic_video_codec_b200 as bvc
+    from basic_video_codec_b200.encoder.IFrame import IFrame
+    from basic_video_codec_b200.encoder.PFrame import PFrame
+    g = gu.load("fs_i16_r2_nref4")
+    e = g["meta"]["enc"]
+    n, H, W = g["frames"].shape
+    ec = bvc.EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e["nref"], resolution=(W, H))
+    params = bvc.InputParameters("unused.y", W, H, ec, frames_to_process=n)
+    refs = deque(maxlen=e["nref"])
+    for idx, (mode, pred, coef) in enumerate(gu.split_container(g["encoded"])[:4]):
+        det = g["meta"]["frames"][idx]
+        fr = IFrame() if mode == 1 else PFrame(reference_frames=refs, interpolated_reference_frames=None)
+        if mode == 1:
+            refs.clear()
+        got = fr.entropy_decode_prediction_data(pred, params)
+        if mode == 1:
+            assert got == det["modes"] == fr.intra_modes
+        else:
+            assert [list(v) for v in got.values()] == det["mv"]
+            assert list(got.keys())[:2] == [(0, 0), (e["block"], 0)]
+        assert fr.rc_qp_per_row == [e["qp"]] * (H // e["block"])
+        fr.entropy_encoded_DCT_coffs = coef
+        lev = fr.entropy_decode_dct_coffs(params)
+        assert np.array_equal(lev, g["levels"][idx]) and fr.get_quat_dct_coffs_extremes() == [lev.min(), lev.max()]
+        dec = fr.decode_mc_q_dct((H, W), ec)
+        assert np.array_equal(dec, g["recon"][idx])
+        refs.append(dec)
