@@ -14,7 +14,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
-    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library():
     L.bvc_clip_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.bvc_set_lane_groups.argtypes = [C.c_void_p, C.c_int]
+    L.bvc_clip_upload_i420.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.bvc_decode_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]
     L.bvc_decode_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int,
@@ -300,6 +301,14 @@ class Context:
     def clip_upload(self, frames):
         frames = np.ascontiguousarray(frames, dtype=np.uint8)
         self._check(self._L.bvc_clip_upload(self._h, _p(frames), frames.shape[0]))
+
+    def clip_upload_i420(self, yuv, src_w, src_h, nframes):
+        """Upload the luma planes of an I420 buffer (padded to the context size with 128 on the device)."""
+        yuv = np.ascontiguousarray(np.frombuffer(yuv, dtype=np.uint8) if not isinstance(yuv, np.ndarray) else yuv, dtype=np.uint8)
+        need = nframes * (src_w * src_h + 2 * (src_w // 2) * (src_h // 2))
+        if yuv.size < need:
+            raise ValueError(f"I420 buffer holds {yuv.size} bytes, {need} needed for {nframes} frames")
+        self._check(self._L.bvc_clip_upload_i420(self._h, _p(yuv), int(src_w), int(src_h), int(nframes)))
 
     def encode_clip_resident(self, nframes, out=None):
         if out is None:

@@ -1067,6 +1067,32 @@ extern "C" int bvc_clip_upload(bvc_ctx* c, const uint8_t* frames, int nframes) {
     return BVC_OK;
 }
 
+// Input stage (assign1/ex2.py:14-46 read_y_component + common.pad_frame common.py:22-32): the luma planes of an I420
+// (YUV 4:2:0 planar) file image go straight to HBM -- a strided copy skips the chroma planes, no host-side repacking --
+// and frames whose size is not a multiple of the block size are padded bottom / right with 128 on the device.
+extern "C" int bvc_clip_upload_i420(bvc_ctx* c, const uint8_t* yuv, int src_w, int src_h, int nframes) {
+    if (!c || !yuv || nframes < 1) return BVC_ERR_INVALID;
+    const Geom& g = c->g;
+    if (src_w < 1 || src_h < 1 || src_w > g.W || src_h > g.H || g.W - src_w >= g.bs || g.H - src_h >= g.bs)
+        return fail(c, BVC_ERR_INVALID, "context size must be the source size rounded up to the block size");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+    const size_t ysz = (size_t)src_w * src_h, fsz = ysz + 2 * ((size_t)(src_w / 2) * (src_h / 2));
+    if (src_w == g.W && src_h == g.H && g.pitch == g.W) {
+        // one 2-D copy: "row" f = the luma plane of frame f, source pitch = a whole I420 frame
+        CK(cudaMemcpy2DAsync(c->in_pool, g.plane_bytes, yuv, fsz, ysz, (size_t)nframes, cudaMemcpyHostToDevice, c->st));
+    } else {
+        if (src_w != g.W || src_h != g.H) CK(launch_fill_plane(c->in_pool, (size_t)nframes * g.plane_bytes, 128, c->st));
+        for (int f = 0; f < nframes; f++)
+            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, yuv + (size_t)f * fsz, src_w, src_w, src_h,
+                                 cudaMemcpyHostToDevice, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    c->resident_frames = nframes;
+    return BVC_OK;
+}
+
 static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
                             uint8_t* recon) {
     const Geom& g = c->g;

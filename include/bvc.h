@@ -118,6 +118,10 @@ int bvc_encode_clip(bvc_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *o
 int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
 int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
                              uint8_t *recon);
+/* Input stage: like bvc_clip_upload, for an I420 (YUV 4:2:0 planar) file image of src_w x src_h frames.  Only the luma
+ * planes are transferred (read_y_component, assign1/ex2.py:14-28) and they are padded bottom / right with 128 to the
+ * context's width / height (pad_frame, common.py:22-32), which must be src_w / src_h rounded up to block_size. */
+int bvc_clip_upload_i420(bvc_ctx *ctx, const uint8_t *yuv, int src_w, int src_h, int nframes);
 
 /* decoder ------------------------------------------------------------------------------------------ */
 /* decode_video (decoder.py:26-87): parses the container (`data`, encoded.bin layout), entropy-decodes both streams

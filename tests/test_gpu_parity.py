@@ -375,3 +375,31 @@ def test_lane_groups_do_not_change_the_stream():
             ctx.set_lane_groups(0)
         with pytest.raises(ValueError):
             ctx.set_lane_groups(5)
+
+
+def test_i420_input_stage_pads_and_skips_chroma(tmp_path):
+    """bvc_clip_upload_i420: luma planes straight from an I420 file image, padded with 128 on the device, encode to the
+    same stream as the oracle fed with pad_frame()'d Y planes; aligned sizes take the single strided copy."""
+    from basic_video_codec_b200 import EncoderConfig
+    from basic_video_codec_b200 import input_stage as ist
+    ob = _ob()
+    rng = np.random.default_rng(11)
+    for (w, h, bs) in ((90, 58, 8), (96, 64, 16)):
+        n, ip, qp, r = 7, 3, 3, 4
+        W, H = w + (-w) % bs, h + (-h) % bs
+        ys = synth.moving_clip(13, H, W, n, step=3, clamp=16)[:, :h, :w]
+        path = tmp_path / f"c_{w}.yuv"
+        with open(path, "wb") as fh:
+            for y in ys:
+                fh.write(np.ascontiguousarray(y).tobytes())
+                fh.write(rng.integers(0, 256, 2 * (w // 2) * (h // 2), dtype=np.uint8).tobytes())
+        padded = np.stack([ist.pad_frame(y, bs) for y in ys])
+        want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=2, i_period=ip), padded)
+        ec = EncoderConfig(bs, r, ip, qp, nRefFrames=2, resolution=(W, H))
+        assert ist.encode_yuv_file(str(path), w, h, ec) == want
+        assert ist.encode_yuv_file(str(path), w, h, ec, frames_to_process=4) == ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=2, i_period=ip), padded[:4])[0]
+    with _ctx(96, 64, 16, 4, 3, 1, False, False, 3, lanes=1) as ctx:
+        with pytest.raises(ValueError):
+            ctx.clip_upload_i420(np.zeros(100, np.uint8), 96, 64, 2)          # buffer too small
+        with pytest.raises(ValueError):
+            ctx.clip_upload_i420(np.zeros(10 ** 5, np.uint8), 64, 64, 2)      # not the context's size

@@ -70,3 +70,26 @@ def test_dct_tables_agree_with_oracle():
         mw = re.search(rf"#define BVC_W{bs}_INIT \{{(.*?)\}}", hdr)
         wv = [float.fromhex(t) for t in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+", mw.group(1))]
         assert set(float(x).hex() for x in w.ravel()) <= set(v.hex() for v in wv)
+
+
+def test_input_stage_file_helpers(tmp_path):
+    """read_y_component / save_y_frames_to_file / calculate_num_frames (assign1/ex2.py:14-46, common.py:13-19)."""
+    import numpy as np
+    from basic_video_codec_b200 import input_stage as ist
+    from basic_video_codec_b200 import EncoderConfig, InputParameters
+    w, h, n = 36, 22, 5
+    rng = np.random.default_rng(3)
+    ys = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    with open(tmp_path / "clip.yuv", "wb") as fh:
+        for y in ys:
+            fh.write(y.tobytes())
+            fh.write(rng.integers(0, 256, 2 * (w // 2) * (h // 2), dtype=np.uint8).tobytes())
+    assert ist.calculate_num_frames(str(tmp_path / "clip.yuv"), w, h) == n
+    got = list(ist.read_y_component(str(tmp_path / "clip.yuv"), w, h, n))
+    assert all(np.array_equal(a, b) for a, b in zip(got, ys))
+    params = InputParameters(str(tmp_path / "clip.y"), w, h, EncoderConfig(4, 2, 2, 3, resolution=(w, h)), frames_to_process=n)
+    params.yuv_file = None
+    ist.save_y_frames_to_file(params)
+    assert open(tmp_path / "clip.y", "rb").read() == ys.tobytes()
+    p = ist.pad_frame(ys[0], 8)
+    assert p.shape == (24, 40) and np.array_equal(p[:h, :w], ys[0]) and (p[h:, :] == 128).all() and (p[:, w:] == 128).all()
