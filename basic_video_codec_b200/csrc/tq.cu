@@ -32,62 +32,12 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a) {
     __syncthreads();
     WarpTile<BS>& t = sm.w[warp];
     const int fl = blockIdx.y;
-    const FrameLane& L = a.lanes[fl];
-    const int q = lane / BS, x = lane % BS;
+    const int q = lane / BS;
     const int blk_begin = a.row_begin * a.bw, blk_end = (a.row_begin + a.row_count) * a.bw;
     const int b = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + q;
     const bool valid = b < blk_end;
     const int bb = valid ? b : blk_end - 1;
-    const int bx = bb % a.bw, by = bb / a.bw;
-    const int ox = bx * BS, oy = by * BS;
-
-    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(oy + x) * a.cur_pitch + ox;
-    const int4 mv = a.mv[(size_t)fl * a.nblk + bb];
-    // find_mv_predicted_block PFrame.py:230-244: refs[mv[2]] only when more than one reference is present
-    const int k = (L.nref > 1) ? mv.z : 0;
-    int plane = L.ref_plane[k];
-    int dx = mv.x, dy = mv.y;
-    if (a.frac) {  // half-pel MV = integer offset on one of the four phase planes
-        plane += (mv.x & 1) | ((mv.y & 1) << 1);
-        dx = mv.x >> 1;
-        dy = mv.y >> 1;
-    }
-    const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(oy + dy + x) * a.ref_pitch + (ox + dx);
-    {
-        uint32_t cw[BS / 4], pw[BS / 4];
-        load_row_aligned<BS>(cur, cw);
-        load_row_unaligned<BS>(pr, pw);
-        stage_row<BS>(t, q, x, cw, pw);
-    }
-    if (a.resid_nomc && valid) {
-        // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
-        const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(oy + x) * a.ref_pitch + ox;
-        int8_t* d = a.resid_nomc + ((size_t)fl * a.H + oy + x) * a.W + ox;
-#pragma unroll
-        for (int i = 0; i < BS; i++) d[i] = (int8_t)((int)cur[i] - (int)r0[i]);
-    }
-    __syncwarp();
-
-    TqOut o;
-    o.levels = a.levels ? a.levels + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
-    o.lev_pitch = a.W;
-    o.recon = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes + (size_t)oy * a.ref_pitch + ox;
-    o.rec_pitch = a.ref_pitch;
-    o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
-    o.resid_pitch = a.W;
-    o.idct_out = nullptr;
-    o.coef_out = nullptr;
-    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
-    tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, false);
-
-    // entropy-code the warp's blocks one after the other
-    for (int qq = 0; qq < NBW; qq++) {
-        const int b2 = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + qq;
-        if (b2 >= blk_end) break;
-        uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b2) * a.blk_words;
-        const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], sm.zz, t.bits, lane, gout);
-        if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b2] = nb;
-    }
+    tq_pframe_warp<BS>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
 }
 
 // ---------------------------------------------------------------------------------------------

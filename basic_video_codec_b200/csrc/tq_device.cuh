@@ -12,6 +12,7 @@
 #pragma once
 #include "bvc_common.cuh"
 #include "bvc_dct_tables.h"
+#include "bvc_kernels.h"
 
 namespace bvc {
 
@@ -363,6 +364,69 @@ __device__ __forceinline__ int entropy_block_warp(const int16_t* lev, const uint
     for (int w = lane; w < nwords; w += 32) gout[w] = bits[w];
     __syncwarp();
     return nbits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp task of the P-frame path: NBW blocks (lane -> block `b` of lane group `fl`, motion vector `mv`; lanes of
+// the same block pass the same values; !valid lanes pass any in-range block and produce nothing).  Stages current and
+// predicted pixels, forms the residual, transforms / quantises / reconstructs and entropy-codes the blocks
+// (PFrame.process_block PFrame.py:99-125,230-249; Frame.py:61-75,190-202).
+template <int BS>
+__device__ __forceinline__ void tq_pframe_warp(const TqArgs& a, int fl, WarpTile<BS>& t, const uint8_t* zz, int lane, int b, bool valid,
+                                               int4 mv) {
+    constexpr int NBW = 32 / BS;
+    const FrameLane& L = a.lanes[fl];
+    const int q = lane / BS, x = lane % BS;
+    const int bx = b % a.bw, by = b / a.bw;
+    const int ox = bx * BS, oy = by * BS;
+    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(oy + x) * a.cur_pitch + ox;
+    // find_mv_predicted_block PFrame.py:230-244: refs[mv[2]] only when more than one reference is present
+    const int k = (L.nref > 1) ? mv.z : 0;
+    int plane = L.ref_plane[k];
+    int dx = mv.x, dy = mv.y;
+    if (a.frac) {  // half-pel MV = integer offset on one of the four phase planes
+        plane += (mv.x & 1) | ((mv.y & 1) << 1);
+        dx = mv.x >> 1;
+        dy = mv.y >> 1;
+    }
+    const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(oy + dy + x) * a.ref_pitch + (ox + dx);
+    {
+        uint32_t cw[BS / 4], pw[BS / 4];
+        load_row_aligned<BS>(cur, cw);
+        load_row_unaligned<BS>(pr, pw);
+        stage_row<BS>(t, q, x, cw, pw);
+    }
+    if (a.resid_nomc && valid) {
+        // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
+        const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(oy + x) * a.ref_pitch + ox;
+        int8_t* d = a.resid_nomc + ((size_t)fl * a.H + oy + x) * a.W + ox;
+#pragma unroll
+        for (int i = 0; i < BS; i++) d[i] = (int8_t)((int)cur[i] - (int)r0[i]);
+    }
+    __syncwarp();
+
+    TqOut o;
+    o.levels = a.levels ? a.levels + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+    o.lev_pitch = a.W;
+    o.recon = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes + (size_t)oy * a.ref_pitch + ox;
+    o.rec_pitch = a.ref_pitch;
+    o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
+    o.resid_pitch = a.W;
+    o.idct_out = nullptr;
+    o.coef_out = nullptr;
+    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
+    tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, false);
+
+    // entropy-code the warp's blocks one after the other
+#pragma unroll 1
+    for (int qq = 0; qq < NBW; qq++) {
+        const int b2 = __shfl_sync(0xffffffffu, b, qq * BS);
+        const int v2 = __shfl_sync(0xffffffffu, (int)valid, qq * BS);
+        if (!v2) continue;
+        uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b2) * a.blk_words;
+        const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], zz, t.bits, lane, gout);
+        if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b2] = nb;
+    }
 }
 
 }  // namespace bvc

@@ -81,6 +81,17 @@ def _plane_array(planes):
     return arr, keep
 
 
+def full_search_block(cur: np.ndarray, refs, ox: int, oy: int, bs: int, search_range: int, frac: bool = False):
+    """find_lowest_mae_block for one block (block_predictor.py:61-91) -> ((mvx, mvy, ref), SAD).  refs: integer planes, or
+    half-pel planes (2H x 2W) when frac."""
+    cur = np.ascontiguousarray(cur, dtype=np.uint8)
+    H, W = cur.shape
+    arr, keep = _plane_array(refs)
+    mv = (C.c_int32 * 3)()
+    sad = lib().bvo_full_search_block(_p(cur), W, H, int(ox), int(oy), int(bs), arr, len(refs), int(search_range), int(bool(frac)), mv, None)
+    return (int(mv[0]), int(mv[1]), int(mv[2])), int(sad)
+
+
 def me_frame(cfg: Config, cur: np.ndarray, planes):
     """Frame-level motion estimation.  planes: integer planes, or half-pel planes when cfg.frac."""
     nblk = (cfg.width // cfg.block) * (cfg.height // cfg.block)

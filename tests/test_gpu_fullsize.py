@@ -1,0 +1,47 @@
+"""BASELINE.json's full sizes: oracle comparisons where the CPU finishes in seconds, size-independent properties
+(decode(encode(x)) == reconstruction, GOP streams concatenate, spot-checked motion vectors) where it does not."""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_1080p_r32_gop_matches_oracle_and_roundtrips():
+    """configs[3]: 1920x1088, i=16, r=32 full search.  One I + two P frames against the oracle (bit-exact stream and
+    reconstruction), then 2 GOPs x 3 frames through GOP lanes and lane groups: decode == reconstruction."""
+    import basic_video_codec_b200 as bvc
+    from oracle import bindings as ob
+    W, H, bs, r, qp = 1920, 1088, 16, 32, 4
+    frames = synth.moving_clip(1080, H, W, 6, step=6, clamp=96, noise=2)
+    cfg = ob.make_config(W, H, bs, r, qp, nref=1, i_period=3)
+    want, want_recon = ob.encode_clip(cfg, frames[:3], nthreads=1)
+    with bvc.Context(W, H, bs, r, qp, 1, False, False, 3, device=0, max_lanes=2) as ctx:
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+        assert data[:len(want)] == want
+        assert np.array_equal(recon[:3], want_recon)
+        assert np.array_equal(ctx.decode_clip(data, 6), recon)
+        ctx.set_lane_groups(1)
+        assert ctx.encode_clip(frames)[0] == data
+
+
+def test_4k_r64_4refs_spot_checks_and_roundtrip():
+    """configs[4]: 3840x2160, i=16, r=64, 4 references.  One GOP of 4 frames: motion vectors / SADs of sampled blocks
+    (corners, edges, interior) of the 3-reference P frame against the oracle's full search; decode == reconstruction."""
+    import basic_video_codec_b200 as bvc
+    from oracle import bindings as ob
+    W, H, bs, r, qp = 3840, 2160, 16, 64, 4
+    frames = synth.moving_clip(2160, H, W, 4, step=3, clamp=48, noise=2)
+    with bvc.Context(W, H, bs, r, qp, 4, False, False, 8, device=0, max_lanes=1) as ctx:
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+        assert np.array_equal(ctx.decode_clip(data, 4), recon)
+        mv, sad, _ = ctx.me_search(frames[3], [recon[0], recon[1], recon[2]])
+    bw, bh = W // bs, H // bs
+    rng = np.random.default_rng(5)
+    picks = [(0, 0), (bw - 1, 0), (0, bh - 1), (bw - 1, bh - 1), (bw // 2, 0), (0, bh // 2)] + \
+            [(int(rng.integers(bw)), int(rng.integers(bh))) for _ in range(10)]
+    for bx, by in picks:
+        omv, osad = ob.full_search_block(frames[3], [recon[0], recon[1], recon[2]], bx * bs, by * bs, bs, r)
+        b = by * bw + bx
+        assert mv[b].tolist() == list(omv) and int(sad[b]) == osad, (bx, by)
