@@ -31,7 +31,7 @@ template <> struct DctC<8>  { static __device__ __forceinline__ double ct(int i)
 template <> struct DctC<16> { static __device__ __forceinline__ double ct(int i) { return c_ct16[i]; } static __device__ __forceinline__ double w(int i) { return c_w16[i]; } };
 
 template <int BS>
-constexpr int blk_words_for() {
+__host__ __device__ constexpr int blk_words_for() {
     // worst case: every coefficient non-zero with the largest magnitude 255*BS
     return BS == 16 ? 208 : BS == 8 ? 48 : 12;
 }
@@ -276,90 +276,150 @@ __device__ __forceinline__ void put_bits_smem(uint32_t* buf, int off, unsigned l
 }
 
 // Entropy-code one block (levels in smem tile `lev`, BS x BS) cooperatively by one warp.
-// Returns the number of bits; the bits are left in t.bits (big-endian words) and copied to `gout`.
+// Returns the number of bits; the bits are left in `bits` (big-endian words) and copied to `gout`.
+//
+// M[i] = ballot of the non-zero levels at zig-zag positions 32*i + lane; a run starts where the non-zero state flips
+// (position 0 always starts one) and ends where the next one starts.  "Events" are the positions that emit symbols
+// (run starts and non-zero values).  A block with at most 32 events (the usual case after quantisation) is coded in
+// one pass with lane j on event j -- the j-th set bit of the 256-bit event mask -- so the work is balanced whatever
+// the positions are; denser blocks take the position-parallel loop, 32 positions per iteration.
 template <int BS>
 __device__ __forceinline__ int entropy_block_warp(const int16_t* lev, const uint8_t* zz, uint32_t* bits, int lane,
                                                   uint32_t* gout) {
     constexpr int N = BS * BS;
-    constexpr int PL = N >= 32 ? N / 32 : 1;   // positions per lane
-    constexpr int AL = N / PL;                 // active lanes
+    constexpr int NI = N >= 32 ? N / 32 : 1;   // iterations
+    constexpr int AL = N >= 32 ? 32 : N;       // positions (= active lanes) per iteration
+    constexpr uint32_t ALMASK = AL == 32 ? 0xffffffffu : ((1u << AL) - 1u);
     const bool act = lane < AL;
-    const int p0 = lane * PL;
-    int c[PL];
-    uint32_t nz = 0;
+    int c[NI];
+    uint32_t M[NI];
+    int nnz = 0;
 #pragma unroll
-    for (int i = 0; i < PL; i++) {
-        c[i] = act ? (int)lev[zz[p0 + i]] : 0;
-        nz |= (c[i] != 0 ? 1u : 0u) << i;
+    for (int i = 0; i < NI; i++) {
+        c[i] = act ? (int)lev[zz[i * AL + lane]] : 0;
+        M[i] = __ballot_sync(0xffffffffu, c[i] != 0);
+        nnz += __popc(M[i]);
     }
-    // run starts: position 0, or state differs from the previous position
-    uint32_t lastbit = (nz >> (PL - 1)) & 1u;
-    uint32_t prev = __shfl_up_sync(0xffffffffu, lastbit, 1);
-    uint32_t start = (nz ^ ((nz << 1) | prev)) & ((1u << PL) - 1u);
-    if (lane == 0) start |= 1u;
-    if (!act) start = 0;
-    // first run start strictly after this lane's chunk (N if none)
-    int first = start ? p0 + (__ffs(start) - 1) : N;
-    int sfx = first;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_down_sync(0xffffffffu, sfx, d);
-        if (lane + d < 32) sfx = min(sfx, o);
+    // zero what the block can need: <= 31 bits per value, <= 19 per run header, <= 2*nnz+1 runs, 27 for the end marker
+    {
+        constexpr int WCAP = blk_words_for<BS>() + 4;
+        const int wmax = min(WCAP, ((69 * nnz + 46 + 31) >> 5) + 2);
+        for (int w = lane; w < wmax; w += 32) bits[w] = 0;
     }
-    int next = __shfl_down_sync(0xffffffffu, sfx, 1);
-    if (lane == 31) next = N;
-    // per position code (header and/or value), computed back to front so run lengths are known
-    unsigned long long code[PL];
-    int len[PL];
-    int total = 0;
+    __syncwarp();
+    int base = 0;
+    // events = positions that emit symbols (run starts and non-zero values), in scan order
+    uint32_t S[NI], EV[NI];
+    int P[NI];
+    int E = 0;
 #pragma unroll
-    for (int i = PL - 1; i >= 0; i--) {
-        const int p = p0 + i;
+    for (int i = 0; i < NI; i++) {
+        const uint32_t carry = (i == 0) ? ((~M[0]) & 1u) : (M[i > 0 ? i - 1 : 0] >> (AL - 1)) & 1u;
+        S[i] = (M[i] ^ ((M[i] << 1) | carry)) & ALMASK;
+        EV[i] = S[i] | M[i];
+        P[i] = E;
+        E += __popc(EV[i]);
+    }
+    if (E <= 32) {
+        // fast path (sparse block): lane j codes event j -- one pass, balanced over the lanes
+        const bool on = lane < E;
+        int wi = 0, pb = 0;
+        uint32_t evw = EV[0], mw = M[0], sw = S[0];
+#pragma unroll
+        for (int i = 1; i < NI; i++)
+            if (lane >= P[i]) { wi = i; pb = P[i]; evw = EV[i]; mw = M[i]; sw = S[i]; }
+        // position of the (lane - pb)-th set bit of evw
+        int n = lane - pb, bit = 0;
+        {
+            uint32_t w = evw;
+            int k = __popc(w & 0xffffu);
+            if (n >= k) { n -= k; bit += 16; w >>= 16; }
+            k = __popc(w & 0xffu);
+            if (n >= k) { n -= k; bit += 8; w >>= 8; }
+            k = __popc(w & 0xfu);
+            if (n >= k) { n -= k; bit += 4; w >>= 4; }
+            k = __popc(w & 0x3u);
+            if (n >= k) { n -= k; bit += 2; w >>= 2; }
+            if (n >= (int)(w & 1u)) bit += 1;
+        }
+        const int p = on ? wi * AL + bit : 0;
+        const bool isnz = on && ((mw >> bit) & 1u);
+        const bool st = on && ((sw >> bit) & 1u);
+        // a run ends where the next one starts: the next start among the events (they are in scan order)
+        const uint32_t sb = __ballot_sync(0xffffffffu, st) & ~((2u << lane) - 1u);
+        const int pn = __shfl_sync(0xffffffffu, p, sb ? __ffs(sb) - 1 : 0);
+        const int next = sb ? pn : N;
         unsigned long long cd = 0;
         int ln = 0;
-        const bool st = (start >> i) & 1u;
-        const bool isnz = (nz >> i) & 1u;
-        int runlen = 0;
-        bool to_end = false;
-        if (st) { runlen = next - p; to_end = (next == N); next = p; }
-        if (isnz) {
-            if (st) {  // rle_encode: -count then the values (entropy_encoder.py:78-86)
-                const uint32_t e = eg_code(-runlen);
-                ln = eg_len_of_code(e);
-                cd = e;
-            }
-            const uint32_t e = eg_code(c[i]);
-            const int l2 = eg_len_of_code(e);
-            cd = (cd << l2) | e;
-            ln += l2;
-        } else if (st) {  // zero run: count, or 0 when it reaches the end (entropy_encoder.py:68-76)
-            const uint32_t e = eg_code(to_end ? 0 : runlen);
+        if (st) {
+            const int runlen = next - p;
+            const uint32_t e = eg_code(isnz ? -runlen : (next == N ? 0 : runlen));
             ln = eg_len_of_code(e);
             cd = e;
         }
-        code[i] = cd;
-        len[i] = ln;
-        total += ln;
-    }
-    // exclusive scan of lane totals
-    int incl = total;
+        if (isnz) {
+            const uint32_t e = eg_code((int)lev[zz[p]]);
+            const int l2 = eg_len_of_code(e);
+            cd = (cd << l2) | e;
+            ln += l2;
+        }
+        int incl = ln;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (ln) put_bits_smem(bits, incl - ln, cd, ln);
+        base = __shfl_sync(0xffffffffu, incl, 31);
+    } else {
+        // dense block: position-parallel, 32 positions per iteration
+#pragma unroll 1
+        for (int i = 0; i < NI; i++) {
+            uint32_t Mi = 0, Si = 0;
+            int ci = 0;
+#pragma unroll
+            for (int k = 0; k < NI; k++)
+                if (k == i) { Mi = M[k]; Si = S[k]; ci = c[k]; }
+            if ((Si | Mi) == 0) continue;
+            const bool isnz = (Mi >> lane) & 1u;
+            const bool st = act && ((Si >> lane) & 1u);
+            const int p = i * AL + lane;
+            unsigned long long cd = 0;
+            int ln = 0;
+            if (st) {
+                const uint32_t inv = isnz ? 0xffffffffu : 0u;
+                const uint32_t w = ((Mi ^ inv) & ALMASK) & ~((2u << lane) - 1u);
+                int next = w ? i * AL + __ffs(w) - 1 : -1;
+#pragma unroll
+                for (int j = 1; j < NI; j++) {
+                    const uint32_t x = (M[j] ^ inv) & ALMASK;
+                    if (j > i && next < 0 && x) next = j * AL + __ffs(x) - 1;
+                }
+                if (next < 0) next = N;
+                const int runlen = next - p;
+                const uint32_t e = eg_code(isnz ? -runlen : (next == N ? 0 : runlen));
+                ln = eg_len_of_code(e);
+                cd = e;
+            }
+            if (isnz) {
+                const uint32_t e = eg_code(ci);
+                const int l2 = eg_len_of_code(e);
+                cd = (cd << l2) | e;
+                ln += l2;
+            }
+            int incl = ln;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (ln) put_bits_smem(bits, base + incl - ln, cd, ln);
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
-    int off = incl - total;
-    const int body_bits = __shfl_sync(0xffffffffu, incl, 31);
-    const int nbits = body_bits + 27;  // + EG(8190) end-of-block marker (Frame.py:75)
+    const int nbits = base + 27;  // + EG(8190) end-of-block marker (Frame.py:75)
     const int nwords = (nbits + 31) >> 5;
-    for (int w = lane; w < nwords + 2; w += 32) bits[w] = 0;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < PL; i++) {
-        if (len[i]) put_bits_smem(bits, off, code[i], len[i]);
-        off += len[i];
-    }
-    if (lane == 0) put_bits_smem(bits, body_bits, (unsigned long long)eg_code(BVC_EOB_MARKER), 27);
+    if (lane == 0) put_bits_smem(bits, base, (unsigned long long)eg_code(BVC_EOB_MARKER), 27);
     __syncwarp();
     for (int w = lane; w < nwords; w += 32) gout[w] = bits[w];
     __syncwarp();
