@@ -63,7 +63,7 @@ struct bvc_ctx {
 
     int4* d_mv = nullptr;
     int32_t *d_modes = nullptr, *d_isad = nullptr, *d_qp_rows = nullptr, *d_blk_nbits = nullptr;
-    int16_t* d_levels = nullptr;       // lane 0 only (frame API)
+    int16_t* d_levels = nullptr;       // [lanes][H][W]: I frames (all lanes) and the frame-level calls (lane 0)
     int8_t *d_resid_mc = nullptr, *d_resid_nomc = nullptr;
     uint32_t* d_blk_bits = nullptr;
     int blk_words = 0;
@@ -233,7 +233,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_qp_rows, L * g.bh));
         CK(dalloc(&c->d_blk_nbits, L * nb));
         CK(dalloc(&c->d_blk_bits, L * nb * c->blk_words));
-        CK(dalloc(&c->d_levels, (size_t)g.W * g.H));
+        CK(dalloc(&c->d_levels, L * (size_t)g.W * g.H));   // every lane: I frames hand their levels to the entropy kernel
         CK(dalloc(&c->d_resid_mc, (size_t)g.W * g.H));
         CK(dalloc(&c->d_resid_nomc, (size_t)g.W * g.H));
         CK(dalloc(&c->d_coef_off, L * (nb + 1)));
@@ -420,7 +420,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.ref_base = c->ref_pool; t.ref_plane_bytes = g.plane_bytes; t.ref_pitch = g.pitch;
     t.lanes = c->d_fr_lanes + sp.desc_off + L0;
     t.mv = c->d_mv + L0 * nb; t.modes = c->d_modes + L0 * nb; t.isad = c->d_isad + L0 * nb; t.qp_rows = c->d_qp_rows + L0 * g.bh;
-    t.levels = frame_api ? c->d_levels : nullptr;
+    t.levels = (frame_api || sp.intra) ? c->d_levels + L0 * (size_t)g.W * g.H : nullptr;
     t.resid_mc = frame_api ? c->d_resid_mc : nullptr;
     t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
     t.blk_bits = c->d_blk_bits + L0 * nb * c->blk_words; t.blk_nbits = c->d_blk_nbits + L0 * nb; t.blk_words = c->blk_words;
@@ -432,7 +432,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         const int e0 = tick(c, st_post);
         CK(launch_tq_iframe(t, nl, st_post));
         span(c, BVC_K_TQ_I, e0, tick(c, st_post));
-        c->launches += 1;
+        c->launches += 2;
     } else {
         MeArgs m{};
         m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;

@@ -136,16 +136,39 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         __threadfence();
         __syncwarp();
         if (valid && x == 0) atomicExch(prog_me, bx + 1);
-
-        for (int qq = 0; qq < NBW; qq++) {
-            const int f2 = grp * NBW + qq;
-            if (f2 >= lanes) break;
-            const int b2 = by * a.bw + bx;
-            uint32_t* gout = a.blk_bits + ((size_t)f2 * a.nblk + b2) * a.blk_words;
-            const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], sm.zz, t.bits, lane, gout);
-            if (lane == 0) a.blk_nbits[(size_t)f2 * a.nblk + b2] = nb;
-        }
     }
+}
+
+// Entropy coding of I-frame blocks from the level plane the wavefront kernel wrote (frame layout, a.levels): one warp
+// per block, every block independent -- kept out of the wavefront so that the serial chain through a frame is only
+// predict -> transform -> reconstruct.  grid = (ceil(blocks / TQ_WARPS), lanes)
+template <int BS>
+__global__ void __launch_bounds__(TQ_WARPS * 32) entropy_levels_kernel(TqArgs a) {
+    struct ESmem {
+        __align__(16) int16_t lev[TQ_WARPS][BS * BS];
+        uint32_t bits[TQ_WARPS][blk_words_for<BS>() + 4];
+        uint8_t zz[BS * BS];
+    };
+    __shared__ ESmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    build_zigzag<BS>(sm.zz, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int fl = blockIdx.y;
+    const int blk_begin = a.row_begin * a.bw, blk_end = (a.row_begin + a.row_count) * a.bw;
+    const int b = blk_begin + blockIdx.x * TQ_WARPS + warp;
+    if (b >= blk_end) return;
+    const int ox = (b % a.bw) * BS, oy = (b / a.bw) * BS;
+    const int16_t* src = a.levels + ((size_t)fl * a.H + oy) * a.W + ox;
+    if constexpr (BS == 16) {   // 16 rows x 32 bytes: lane -> (row, half)
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)(lane >> 1) * a.W + (lane & 1) * 8);
+        *reinterpret_cast<uint4*>(&sm.lev[warp][lane * 8]) = v;
+    } else {
+        for (int e = lane; e < BS * BS; e += 32) sm.lev[warp][e] = src[(size_t)(e / BS) * a.W + (e % BS)];
+    }
+    __syncwarp();
+    uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b) * a.blk_words;
+    const int nb = entropy_block_warp<BS>(sm.lev[warp], sm.zz, sm.bits[warp], lane, gout);
+    if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b] = nb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -203,7 +226,12 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         once = true;
     }
+    if (!a.levels) return cudaErrorInvalidValue;   // the level plane feeds the entropy kernel
     tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.row_count * a.bw + TQ_WARPS - 1) / TQ_WARPS, lanes);
+    entropy_levels_kernel<BS><<<grid, TQ_WARPS * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
