@@ -23,7 +23,7 @@ struct TqCtaSmem {
 // ---------------------------------------------------------------------------------------------
 // P frames: every block independent.  grid = (ceil(nblk / (TQ_WARPS*NBW)), lanes)
 template <int BS>
-__global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a) {
+__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
     constexpr int NBW = 32 / BS;
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);

@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
 # DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r1_ncu_*.csv)
 ME_TRAFFIC_BYTES_PER_LANE = (83.670784e6 + 5.514240e6) / 20
-TQ_TRAFFIC_BYTES_PER_LANE = (89.095168e6 + 26.661120e6) / 20
+TQ_TRAFFIC_BYTES_PER_LANE = (43.443712e6 + 3.874816e6) / 10     # 10-lane launch (two lane groups)
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
 

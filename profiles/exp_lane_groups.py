@@ -10,7 +10,7 @@ out=np.empty(N*W*H//2,np.uint8)
 ctx=bvc.Context(W,H,BS,R,QP,1,False,False,IP,device=0,max_lanes=lanes)
 ctx.clip_upload(frames)
 ref=None
-for g,fu in ((1,0),(2,0)):
+for g in (1, 2, 3, 4):
     ctx.set_lane_groups(g)
     for _ in range(2): ctx.encode_clip_resident(N,out)
     torch.cuda.synchronize(); t0=time.perf_counter()
@@ -19,4 +19,4 @@ for g,fu in ((1,0),(2,0)):
     h=hashlib.sha256(out[:ln].tobytes()).hexdigest()[:12]
     if ref is None: ref=h
     kt,clip=ctx.last_kernel_times()
-    print(f"lanes={lanes} groups={g} fused={fu}: {dt*1e3:.2f} ms/clip {N/dt:.0f} f/s same={h==ref} dev={clip:.2f} me={kt['me'][0]:.1f} tq={kt['tq_p'][0]:.1f}",flush=True)
+    print(f"lanes={lanes} groups={g}: {dt*1e3:.2f} ms/clip {N/dt:.0f} f/s same={h==ref} dev={clip:.2f} me={kt['me'][0]:.1f} tq={kt['tq_p'][0]:.1f}",flush=True)
