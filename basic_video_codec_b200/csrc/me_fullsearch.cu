@@ -190,6 +190,12 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
+        // the first window is requested before anything else, so the TMA latency hides behind the staging of the
+        // current blocks and the candidate table
+        if (L.nref > 0) {
+            mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
+            tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[0]);
+        }
     }
     for (int i = tid; i < NB * NBY; i += blockDim.x) sbest[i / NB][i % NB] = ~0ull;
     {   // stage the current blocks (NB*BS x NBY*BS bytes) in shared memory, 16 B per thread-iteration
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     for (int r = 0; r < L.nref; r++) {
         for (int ph = 0; ph < a.nphase; ph++) {
             const int px = ph & 1, py = ph >> 1;
-            if (tid == 0) {
+            if (tid == 0 && (r | ph) != 0) {
                 mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
                 // box origin: 16-byte aligned column (bx0*BS - R - win_lm), rows <= 256
                 tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r] + ph);
@@ -250,12 +256,16 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                 uint32_t* c1 = reinterpret_cast<uint32_t*>(smem + copy_stride);
                 uint32_t* c2 = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)copy_stride);
                 uint32_t* c3 = reinterpret_cast<uint32_t*>(smem + 3 * (size_t)copy_stride);
-                const int nw = (WW * rows) >> 2;
-                for (int w = tid; w < nw; w += blockDim.x) {
-                    const uint32_t lo = c0[w], hi = c0[w + 1];
-                    c1[w] = __funnelshift_r(lo, hi, 8);
-                    c2[w] = __funnelshift_r(lo, hi, 16);
-                    c3[w] = __funnelshift_r(lo, hi, 24);
+                const int nq = (WW * rows) >> 4;   // 16-byte groups (WW is a multiple of 16)
+                for (int g4 = tid; g4 < nq; g4 += blockDim.x) {
+                    const uint4 v = reinterpret_cast<const uint4*>(c0)[g4];
+                    const uint32_t nx = c0[4 * g4 + 4];   // first word of the next group (the 32-byte gap after the last one)
+                    reinterpret_cast<uint4*>(c1)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 8), __funnelshift_r(v.y, v.z, 8),
+                                                                  __funnelshift_r(v.z, v.w, 8), __funnelshift_r(v.w, nx, 8));
+                    reinterpret_cast<uint4*>(c2)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16),
+                                                                  __funnelshift_r(v.z, v.w, 16), __funnelshift_r(v.w, nx, 16));
+                    reinterpret_cast<uint4*>(c3)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 24), __funnelshift_r(v.y, v.z, 24),
+                                                                  __funnelshift_r(v.z, v.w, 24), __funnelshift_r(v.w, nx, 24));
                 }
             }
             __syncthreads();
