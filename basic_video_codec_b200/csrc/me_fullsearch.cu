@@ -420,23 +420,30 @@ cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream
 }
 
 // Tile shape: NB blocks side by side (NB*BS a multiple of 16 so the left margin of the aligned TMA box is
-// the same for every CTA) and NBY stacked.  Constraints: <= 544 threads (two CTAs per SM at 96 registers),
-// TMA box <= 256 x 256, four window copies <= ~100 KB so that two CTAs fit an SM.
+// the same for every CTA) and NBY stacked.  Constraints: <= 544 threads, TMA box <= 256 x 256, four window copies
+// <= 110 KB; shapes that let two CTAs share an SM are preferred.
 struct TileShape { int nb, nby; };
 TileShape pick_shape(int bs, int R) {
     const int cand16[] = {4, 2, 1}, cand8[] = {8, 4, 2}, cand4[] = {8, 4, 4};
     const int* c = bs == 16 ? cand16 : bs == 8 ? cand8 : cand4;
     const int lm = (16 - R % 16) % 16;
     const int nseg = (2 * R + 1 + bs) / (bs + 1);
-    for (int i = 0; i < 3; i++) {
-        const int nb = c[i];
-        const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
-        const int nbys[] = {4, 2, 1};
-        for (int j = 0; j < 3; j++) {
-            const int nby = nbys[j];
-            const int rows = nby * bs + 2 * R;
-            const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
-            if (threads <= 544 && pitch <= 256 && rows <= 256 && 4 * pitch * rows + nb * nby * bs * bs <= 110 * 1024) return {nb, nby};
+    // pass 0: shapes that leave room for two CTAs per SM (<= 341 threads at 96 registers, <= 106 KB of shared memory each):
+    // at r = 64 that is 2 x 2 blocks (0.85 of the VABSDIFF4 peak on the 4K workload) instead of 4 x 1 in one 544-thread
+    // CTA (0.80); pass 1: anything that fits.
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < 3; i++) {
+            const int nb = c[i];
+            const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
+            const int nbys[] = {4, 2, 1};
+            for (int j = 0; j < 3; j++) {
+                const int nby = nbys[j];
+                const int rows = nby * bs + 2 * R;
+                const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
+                const int smem = 4 * pitch * rows + nb * nby * bs * bs;
+                if (pitch > 256 || rows > 256) continue;
+                if (pass == 0 ? (threads <= 341 && smem <= 106 * 1024) : (threads <= 544 && smem <= 110 * 1024)) return {nb, nby};
+            }
         }
     }
     return {0, 0};
