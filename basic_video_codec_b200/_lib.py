@@ -14,7 +14,7 @@ BVC_OK, BVC_ERR_INVALID, BVC_ERR_CUDA, BVC_ERR_OVERFLOW, BVC_ERR_NOMEM, BVC_ERR_
 EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
-    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420",
+    "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420", "bvc_set_fastme_direct",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library():
     L.bvc_clip_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.bvc_encode_clip_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.bvc_set_lane_groups.argtypes = [C.c_void_p, C.c_int]
+    L.bvc_set_fastme_direct.argtypes = [C.c_void_p, C.c_int]
     L.bvc_clip_upload_i420.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.bvc_decode_clip.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p]
@@ -322,6 +323,10 @@ class Context:
         """Lane groups of the clip path (bvc_set_lane_groups): 1 = serial, default 2."""
         self._check(self._L.bvc_set_lane_groups(self._h, int(groups)))
         self.lane_groups = int(groups)
+
+    def set_fastme_direct(self, on: bool):
+        """FastME candidates evaluated directly instead of from the SAD map (bvc_set_fastme_direct); default off."""
+        self._check(self._L.bvc_set_fastme_direct(self._h, int(bool(on))))
 
     def launch_count(self):
         return int(self._L.bvc_launch_count(self._h))

@@ -86,6 +86,8 @@ struct bvc_ctx {
 
     // decoder scratch (grow-only device buffers, see dbuf())
     struct DBuf { void* p = nullptr; size_t cap = 0; };
+    DBuf sad_map;         // FastME look-up table (uint16 [lanes][nref][phase][blk][n1*n1])
+    int fastme_direct = 0;  // 1: evaluate FastME candidates directly (bvc_set_fastme_direct) instead of from the SAD map
     DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
         dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress;
 
@@ -148,8 +150,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static int make_ref_map(bvc_ctx* c) {
     c->have_map = false;
-    if (c->p.fast_me) return BVC_OK;
-    const int R = c->p.search_range;
+    // FastME: the tiled kernel fills the SAD map of radius 16 MV units (launch_fastme_any); its TMA box is sized for that
+    const int R = c->p.fast_me ? (c->p.frac_me ? 8 : 16) : c->p.search_range;
+    if (c->p.fast_me && !me_can_map(c->g.bs, R)) return BVC_OK;
     MeTileCfg cfg = me_tile_config(c->g.bs, R);
     if (!cfg.tiled) return BVC_OK;
     void* fn = nullptr;
@@ -282,7 +285,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->d_overflow); cudaFree(c->d_container);
     for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
                              &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
-                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress})
+                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->sad_map})
         cudaFree(b->p);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -319,6 +322,12 @@ extern "C" int bvc_set_qp(bvc_ctx* c, int qp) {
 extern "C" int bvc_set_lane_groups(bvc_ctx* c, int groups) {
     if (!c || groups < 1 || groups > BVC_MAX_GROUPS) return BVC_ERR_INVALID;
     c->ngroups = groups;
+    return BVC_OK;
+}
+
+extern "C" int bvc_set_fastme_direct(bvc_ctx* c, int on) {
+    if (!c) return BVC_ERR_INVALID;
+    c->fastme_direct = on ? 1 : 0;
     return BVC_OK;
 }
 
@@ -408,6 +417,37 @@ struct StepPlan {
     size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
 };
 
+// FastME for lanes [L0, L0+nl): SAD map by the tiled search kernel + table walk, or the direct kernel.
+static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cudaStream_t st) {
+    const Geom& g = c->g;
+    const int Rm = c->p.frac_me ? 8 : 16;   // 16 MV units around the block: where the walk can look before it stops
+    if (!c->fastme_direct && c->have_map && me_can_map(g.bs, Rm)) {
+        const size_t n1 = 2 * (size_t)Rm + 1;
+        const size_t stride = (n1 * n1 + 7) / 8 * 8;   // 16-byte multiples: the walk stages a block's table with cp.async
+        const size_t per_lane = (size_t)c->p.nref_frames * m.nphase * g.nblk * stride;
+        const size_t need = per_lane * (size_t)c->max_lanes * sizeof(uint16_t) + 256;
+        if (need > c->sad_map.cap) {
+            if (c->sad_map.p) CK(cudaFree(c->sad_map.p));
+            c->sad_map.p = nullptr; c->sad_map.cap = 0;
+            CK(cudaMalloc(&c->sad_map.p, need));
+            c->sad_map.cap = need;
+        }
+        MeArgs mm = m;
+        mm.R = Rm;
+        mm.Rh = Rm * m.sc;
+        mm.sad_map = reinterpret_cast<uint16_t*>(c->sad_map.p) + L0 * per_lane;
+        mm.max_refs = c->p.nref_frames;
+        mm.map_stride = (int)stride;
+        CK(cudaMemsetAsync(mm.sad_map, 0xFF, (size_t)nl * per_lane * sizeof(uint16_t), st));
+        CK(launch_me_fullsearch(&c->ref_map, mm, nl, c->ref_pool, g.plane_bytes, g.pitch, st));
+        CK(launch_fastme_walk(mm, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
+        c->launches += 1;
+        return BVC_OK;
+    }
+    CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
+    return BVC_OK;
+}
+
 // Enqueue the kernels of lanes [l0, l0+nl) of one step: the motion search on `st_me`, everything after it on
 // `st_post` (the same stream for the frame-level calls).  Per-lane scratch arrays are indexed by the lane
 // inside a launch, so a lane group simply gets base pointers advanced by l0 lanes.
@@ -445,7 +485,8 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.Rh = c->p.search_range * m.sc;
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
-            CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st_me));
+            int rcf = launch_fastme_any(c, m, nl, L0, st_me);
+            if (rcf != BVC_OK) return rcf;
         } else {
             CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, st_me));
         }
@@ -552,7 +593,7 @@ static int launch_me_lane0(bvc_ctx* c) {
     m.lanes = c->d_me_lanes; m.out = c->d_mv;
     m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
     m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
-    if (c->p.fast_me) CK(launch_fastme(m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp, c->st));
+    if (c->p.fast_me) { int rcf = launch_fastme_any(c, m, 1, 0, c->st); if (rcf != BVC_OK) return rcf; }
     else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
     c->launches += 1;
     return BVC_OK;
@@ -1170,9 +1211,17 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps : 0);
     auto enqueue_upload = [&](size_t s) -> int {
         if (!host_frames || s >= nsteps) return BVC_OK;
-        for (int f : step_frames[s])
-            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
+        const std::vector<int>& fr = step_frames[s];
+        if (g.pitch == g.W && fr.size() > 1) {
+            // the frames of a step are IP apart (frame k of consecutive GOPs): one strided copy, "row" = one plane
+            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)fr[0] * g.plane_bytes, (size_t)IP * g.plane_bytes,
+                                 host_frames + (size_t)fr[0] * g.W * g.H, (size_t)IP * g.W * g.H, (size_t)g.W * g.H, fr.size(),
                                  cudaMemcpyHostToDevice, c->st_h2d));
+        } else {
+            for (int f : fr)
+                CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
+                                     cudaMemcpyHostToDevice, c->st_h2d));
+        }
         CK(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventRecord(ev_h2d[s], c->st_h2d));
         return BVC_OK;

@@ -27,6 +27,12 @@ struct MeArgs {
     int Rh;                        // range in MV units (= R*sc)
     int win_pitch, win_copy_bytes, win_lm; // filled by the launcher
     int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
+    // SAD map (FastME): when non-null the tiled kernel stores the SAD of every in-range candidate instead of reducing
+    // them: uint16 [lane][ref][phase][blk][map_stride >= (2R+1)^2] (row = vertical offset + R, column = horizontal offset + R),
+    // pre-filled with 0xFFFF = "leaves the plane".  max_refs = the ref stride (nRefFrames).
+    uint16_t* sad_map;
+    int max_refs;
+    int map_stride;                // uint16 elements per (lane, ref, phase, block): (2R+1)^2 rounded up to a multiple of 8
 };
 struct MeTileCfg {
     bool tiled;
@@ -43,6 +49,12 @@ cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args,
 // ---- K4 FastME ---------------------------------------------------------------------------------
 cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
                           long long* cmp_out, cudaStream_t st);
+// FastME on a precomputed SAD map (a.sad_map, radius a.R plane units around the block, filled by launch_me_fullsearch):
+// the serial MVP chain becomes table look-ups; candidates outside the map are evaluated directly.
+cudaError_t launch_fastme_walk(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                               long long* cmp_out, cudaStream_t st);
+// true when the tiled search kernel can produce the SAD map for (block size, map radius in plane units)
+bool me_can_map(int bs, int R);
 
 // ---- K2 half-pel phase planes ----------------------------------------------------------------
 // src: one W x H plane; dst: 4 consecutive phase planes (P00 = copy, P10 = horizontal, P01 = vertical,

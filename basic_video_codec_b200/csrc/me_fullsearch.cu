@@ -95,10 +95,11 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 //            when the vertical offset leaves the plane, so a finished candidate costs one LDS, two IMAD
 //            (FMA pipe) and ONE ALU-pipe instruction (VIMNMX); no compare, select or branch.
 //   general: per-thread arithmetic (used only when SAD | L1 | m does not fit 31 bits).
-template <int BS, int MODE, bool PACKED>
+//   SADMAP : additionally store the SAD of every in-range candidate to smap[m * n1] (FastME's look-up table).
+template <int BS, int MODE, bool PACKED, bool SADMAP>
 __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp, int wpitch,
                                         int mbase, const uint32_t* utab_m, int mlo, int mhi, int mvy0, int sc, uint32_t tthr,
-                                        uint32_t one, const KeyCfg kc, uint32_t& best, uint32_t& bestm) {
+                                        uint32_t one, const KeyCfg kc, uint32_t& best, uint32_t& bestm, uint16_t* smap, int n1) {
     constexpr int WPR = BS / 4;
 #pragma unroll
     for (int t = 0; t < BS; t++) {
@@ -127,6 +128,7 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
             if (PACKED) {
                 const uint32_t u = utab_m[t];   // utab_m = utab + mbase (per thread)
                 best = min(best, imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr)));
+                if (SADMAP && !(u >> 31)) smap[(mbase + t) * n1] = (uint16_t)acc[slot];
             } else {
                 const int m = mbase + t;
                 const uint32_t amvy = (uint32_t)abs(mvy0 + sc * m);
@@ -146,7 +148,7 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
 // vertical segments of BS+1 candidates (ramp-up + ramp-down body only) and all NB*NBY*nseg segments are
 // packed into extra warps that run once per window, so lane utilisation stays ~98 % and -- with NBY
 // stacked rows per CTA -- the extra warps weigh little against the main warps of their SM sub-partition.
-template <int BS, int NB, int NBY, bool PACKED>
+template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
 __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -289,21 +291,27 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < BS; i++) acc[i] = 0;
                     uint32_t best = 0xFFFFFFFFu, bestm = 0;
+                    const int n1 = 2 * R + 1;
+                    uint16_t* smap = nullptr;
+                    if (SADMAP) {
+                        const size_t blk = (size_t)(by0 + yy) * a.bw + bx0 + b;
+                        smap = a.sad_map + ((((size_t)lane * a.max_refs + r) * a.nphase + ph) * a.nblk + blk) * (size_t)a.map_stride + (dx + R);
+                    }
                     const uint32_t* rowp = colp + (yy * BS + m0) * wpitch;
                     int mbase = m0 - (BS - 1);
                     const uint32_t* ut = &utab[yy][0] + BS + mbase;
                     const int nm = is_extra ? 0 : nmid;
-                    me_body<BS, BODY_FIRST, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                    me_body<BS, BODY_FIRST, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                     rowp += BS * wpitch;
                     mbase += BS;
                     ut += BS;
                     for (int i = 0; i < nm; i++) {
-                        me_body<BS, BODY_MID, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                        me_body<BS, BODY_MID, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                         rowp += BS * wpitch;
                         mbase += BS;
                         ut += BS;
                     }
-                    me_body<BS, BODY_LAST, PACKED>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm);
+                    me_body<BS, BODY_LAST, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                     if (PACKED ? (best < 0x80000000u) : (best != 0xFFFFFFFFu)) {
                         uint32_t hi;
                         if (PACKED) {
@@ -382,8 +390,8 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     }
 }
 
-template <int BS, int NB, int NBY, bool PACKED>
-cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
+cudaError_t launch_tiled_pm(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     const int R = a.R;
     const int nmain = NB * 2 * R;
     const int nseg = (2 * R + 1 + BS) / (BS + 1);
@@ -395,16 +403,24 @@ cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStre
     const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + (size_t)NBY * BS * NB * BS + 16;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // largest shared-memory carve-out: CTAs of other kernels (another lane group's tail) never wait for a re-partition
-        e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, lanes);
-    me_tiled_kernel<BS, NB, NBY, PACKED><<<grid, threads, smem, st>>>(map, a);
+    me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP><<<grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
+}
+template <int BS, int NB, int NBY, bool PACKED>
+cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+    if (a.sad_map) {
+        if (!PACKED) return cudaErrorInvalidValue;   // me_can_map() guarantees the packed key
+        return launch_tiled_pm<BS, NB, NBY, true, true>(map, a, lanes, st);
+    }
+    return launch_tiled_pm<BS, NB, NBY, PACKED, false>(map, a, lanes, st);
 }
 
 static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
@@ -491,9 +507,16 @@ cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args,
             return launch_by_nby<4, 4>(cfg, *ref_map, a, lanes, st);
         }
     }
+    if (a.sad_map) return cudaErrorInvalidValue;   // callers ask me_can_map() first
     dim3 grid(a.bw, a.bh, lanes);
     me_generic_kernel<<<grid, 256, 0, st>>>(a, ref_base, ref_plane_bytes, ref_pitch);
     return cudaGetLastError();
+}
+
+bool me_can_map(int bs, int R) {
+    if (!me_tile_config(bs, R).tiled || R > 128) return false;
+    // the packed key (SAD | L1 | m in 31 bits) must fit; R here is already in plane units, L1 in MV units <= 4R
+    return bitlen(255u * bs * bs) + bitlen(4u * R) + bitlen(2u * R) <= 31;
 }
 
 }  // namespace bvc

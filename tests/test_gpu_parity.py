@@ -403,3 +403,26 @@ def test_i420_input_stage_pads_and_skips_chroma(tmp_path):
             ctx.clip_upload_i420(np.zeros(100, np.uint8), 96, 64, 2)          # buffer too small
         with pytest.raises(ValueError):
             ctx.clip_upload_i420(np.zeros(10 ** 5, np.uint8), 64, 64, 2)      # not the context's size
+
+
+@pytest.mark.parametrize("frac,bs,nref", [(False, 16, 2), (True, 8, 3), (False, 8, 1), (False, 4, 6)])
+def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
+    """FastME from the SAD map (default) and with direct evaluation (bvc_set_fastme_direct) against the oracle, on
+    content whose motion exceeds the +-16 MV-unit map: a smooth gradient shifted 21 pixels makes the predictor drift
+    past 16 from block to block, so the walk leaves the map and the warp-evaluated fallback is exercised."""
+    ob = _ob()
+    H, W = 96, 160
+    yy, xx = np.mgrid[0:H, 0:W + 64]
+    base = ((np.sin(xx / 23.0) * 0.5 + 0.5) * 180 + (yy % 32) * 2).astype(np.uint8)      # smooth in x: SAD falls monotonically
+    rng = np.random.default_rng(9)
+    refs = [np.ascontiguousarray(base[:, 21 + 2 * i: 21 + 2 * i + W]) for i in range(nref)]
+    cur = np.clip(base[:, :W].astype(np.int16) + rng.integers(-1, 2, (H, W)), 0, 255).astype(np.uint8)
+    cfg = ob.make_config(W, H, bs, 4, 3, nref=nref, fastme=True, frac=frac)
+    planes = [ob.halfpel_plane(x) for x in refs] if frac else refs
+    mv_o, sad_o, cmp_o = ob.me_frame(cfg, cur, planes)
+    assert np.abs(mv_o[:, 0]).max() > 16, "the case must leave the SAD map (+-16 MV units)"
+    for direct in (False, True):
+        with _ctx(W, H, bs, 4, 3, nref, True, frac) as ctx:
+            ctx.set_fastme_direct(direct)
+            mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
+        assert np.array_equal(mv_g, mv_o) and np.array_equal(sad_g, sad_o) and cmp_g == cmp_o, f"direct={direct}"
