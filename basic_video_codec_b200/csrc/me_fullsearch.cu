@@ -148,7 +148,10 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
 // vertical segments of BS+1 candidates (ramp-up + ramp-down body only) and all NB*NBY*nseg segments are
 // packed into extra warps that run once per window, so lane utilisation stays ~98 % and -- with NBY
 // stacked rows per CTA -- the extra warps weigh little against the main warps of their SM sub-partition.
-template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
+// WPC: window pitch in words when it is known at compile time (the headline shapes), 0 = read it from the arguments.
+// With a constant pitch every LDS of an unrolled body takes an immediate offset from one base register: no address
+// arithmetic (VIADD, ALU pipe) between the VABSDIFF4s.
+template <int BS, int NB, int NBY, bool PACKED, bool SADMAP, int WPC>
 __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
 
     // this thread's window column (left edge of the candidate) and the aligned copy it reads
     const int X = a.win_lm + b * BS + dx + R;
-    const int wpitch = WW >> 2;
+    const int wpitch = WPC ? WPC : (WW >> 2);
     const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2);
 
     uint32_t one;
@@ -390,8 +393,8 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     }
 }
 
-template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
-cudaError_t launch_tiled_pm(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+template <int BS, int NB, int NBY, bool PACKED, bool SADMAP, int WPC>
+cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     const int R = a.R;
     const int nmain = NB * 2 * R;
     const int nseg = (2 * R + 1 + BS) / (BS + 1);
@@ -403,16 +406,26 @@ cudaError_t launch_tiled_pm(const CUtensorMap& map, MeArgs a, int lanes, cudaStr
     const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + (size_t)NBY * BS * NB * BS + 16;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // largest shared-memory carve-out: CTAs of other kernels (another lane group's tail) never wait for a re-partition
-        e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, lanes);
-    me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP><<<grid, threads, smem, st>>>(map, a);
+    me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC><<<grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
+}
+template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
+cudaError_t launch_tiled_pm(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
+    // constant-pitch instantiations for the two headline shapes: 1080p r=32 (4x4 blocks, 128-byte window rows) and
+    // 4K r=64 (2x2 blocks, 160-byte rows)
+    if constexpr (BS == 16 && PACKED && !SADMAP && ((NB == 4 && NBY == 4) || (NB == 2 && NBY == 2))) {
+        constexpr int WP = (NB == 4) ? 32 : 40;
+        if (me_tile_config(BS, a.R).win_pitch == WP * 4) return launch_tiled_pmw<BS, NB, NBY, PACKED, SADMAP, WP>(map, a, lanes, st);
+    }
+    return launch_tiled_pmw<BS, NB, NBY, PACKED, SADMAP, 0>(map, a, lanes, st);
 }
 template <int BS, int NB, int NBY, bool PACKED>
 cudaError_t launch_tiled_p(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
