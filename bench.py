@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=20, help="GOPs encoded in lock-step per GPU")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-decode", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -249,6 +250,25 @@ def main():
     dt_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_val = world * NFRAMES * e2e_steps / dt_e2e
 
+    # ---- decoder, reported beside the headline: the stream just written, host buffers in and out ----
+    decoder = None
+    if not args.skip_decode:
+        container = out_buf[:e2e_bytes].copy()
+        dec_t = torch.empty((NFRAMES, H, W), dtype=torch.uint8, pin_memory=True)
+        dec = dec_t.numpy()
+        ctx.decode_clip(container, NFRAMES, out=dec)      # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        DSTEPS = 2
+        for _ in range(DSTEPS):
+            ctx.decode_clip(container, NFRAMES, out=dec)
+        barrier()
+        dt_dec = max_over_ranks(time.perf_counter() - t0)
+        decoder = {"value": world * NFRAMES * DSTEPS / dt_dec, "unit": "decoded frames/s", "ms_per_clip": dt_dec / DSTEPS * 1e3,
+                   "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": int(dec.nbytes),
+                   "note": "bvc_decode_clip on the container written above; bound by the 1.25 GB of decoded planes returned over PCIe"}
+        del dec_t
+
     # ---- roofline of the dominant kernel (motion estimation) ----------------------------------------
     # The timed steps above run two lane groups on separate streams (kernels of different groups overlap, so
     # event spans around a kernel are not exclusive).  Per-kernel launch durations are therefore taken from extra
@@ -314,6 +334,7 @@ def main():
             "share_of_kernel_time": share["tq_p"] / tot,
             "note": "fp64-pipe bound (32 DFMA/px), not HBM bound: see DESIGN.md",
         },
+        "decoder": decoder,
         "kernel_ms_per_step": {k: v[0] / KSTEPS for k, v in kt_acc.items()},
         "kernel_timing": f"{KSTEPS} extra passes with one lane group (kernels serialised on one stream, {serial_ms:.2f} ms per pass); "
                          "the timed steps overlap kernel tails across lane groups",
