@@ -11,6 +11,15 @@
 
 namespace bvc {
 
+// cudaFuncSetAttribute is per device: launchers remember what they configured for each device of the process, so a
+// process that drives several GPUs (one context each) configures every kernel on every device.
+constexpr int BVC_MAX_DEVICES = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < BVC_MAX_DEVICES) ? d : 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Geometry of one stream of frames (all planes of a context share it).
 struct Geom {

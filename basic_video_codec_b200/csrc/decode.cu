@@ -422,7 +422,8 @@ template <int BS>
 cudaError_t launch_dec_p(const DecArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(DecCtaSmem<BS>);
-    static bool once = false;
+    static bool once_dev[BVC_MAX_DEVICES] = {};
+    bool& once = once_dev[current_device_slot()];
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(dec_pframe_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

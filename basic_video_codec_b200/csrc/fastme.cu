@@ -222,7 +222,8 @@ cudaError_t launch_fastme_walk(const MeArgs& a, int lanes, const uint8_t* ref_ba
                                long long* cmp_out, cudaStream_t st) {
     if (!a.sad_map || a.bs > 32 || a.map_stride % 8) return cudaErrorInvalidValue;
     const size_t smem = 2 * (size_t)a.max_refs * a.nphase * a.map_stride * sizeof(uint16_t);
-    static size_t configured = 0;
+    static size_t configured_dev[BVC_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(fastme_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -404,7 +404,8 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
     a.win_lm = cfg.win_lm;
     a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
     const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + (size_t)NBY * BS * NB * BS + 16;
-    static size_t configured = 0;
+    static size_t configured_dev[BVC_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -201,7 +201,8 @@ template <int BS>
 cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(TqCtaSmem<BS>);
-    static bool once = false;
+    static bool once_dev[BVC_MAX_DEVICES] = {};
+    bool& once = once_dev[current_device_slot()];
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -220,7 +221,8 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(WarpTile<BS>) + BS * BS + 2 * NBW * BS + 64;
     const int ngrp = (lanes + NBW - 1) / NBW;
-    static bool once = false;
+    static bool once_dev[BVC_MAX_DEVICES] = {};
+    bool& once = once_dev[current_device_slot()];
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(tq_iframe_kernel<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
@@ -240,7 +242,8 @@ cudaError_t launch_b(const int16_t* res, const int16_t* pred, int nblocks, int q
                      double* idct, double* coef, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(TqCtaSmem<BS>);
-    static bool once = false;
+    static bool once_dev[BVC_MAX_DEVICES] = {};
+    bool& once = once_dev[current_device_slot()];
     if (!once) {
         cudaError_t e = cudaFuncSetAttribute(tq_blocks_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -426,3 +426,30 @@ def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
             ctx.set_fastme_direct(direct)
             mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
         assert np.array_equal(mv_g, mv_o) and np.array_equal(sad_g, sad_o) and cmp_g == cmp_o, f"direct={direct}"
+
+
+def test_two_devices_in_one_process():
+    """One process, one context per GPU (host threads / GOP sharding without torchrun): kernel attributes are configured
+    per device, so the second device must work as well as the first."""
+    import ctypes
+    import basic_video_codec_b200 as bvc
+    try:
+        n = ctypes.c_int(0)
+        ctypes.CDLL("libcudart.so").cudaGetDeviceCount(ctypes.byref(n))
+        ndev = n.value
+    except OSError:
+        import torch
+        ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs two GPUs")
+    ob = _ob()
+    H, W, bs, r, qp, ip, nfr = 128, 192, 16, 32, 3, 3, 6     # r = 32: the tiled kernel with > 48 KB of shared memory
+    frames = synth.moving_clip(41, H, W, nfr, step=4, clamp=24)
+    want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=2, i_period=ip), frames, want_recon=False)
+    for dev in (0, 1):
+        with bvc.Context(W, H, bs, r, qp, 2, False, False, ip, device=dev, max_lanes=2) as ctx:
+            data, recon = ctx.encode_clip(frames, want_recon=True)
+            assert data == want, f"device {dev}"
+            assert np.array_equal(ctx.decode_clip(data, nfr), recon)
+        with bvc.Context(W, H, bs, 4, qp, 2, True, False, ip, device=dev, max_lanes=2) as ctx:
+            assert ctx.encode_clip(frames)[0] == ob.encode_clip(ob.make_config(W, H, bs, 4, qp, nref=2, fastme=True, i_period=ip), frames, want_recon=False)[0]
