@@ -249,7 +249,7 @@ __device__ __forceinline__ void rle_to_tile(const DecArgs& a, int f, int b, cons
 // second half of tq_warp (the encoder's reconstruction), so decode(encode(x)) == the encoder's reconstruction bit for bit.
 template <int BS>
 __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lane, bool valid, int qp, uint8_t* recon, int rec_pitch,
-                                                        int16_t* levels, int lev_pitch) {
+                                                        int16_t* levels, int lev_pitch, uint8_t* last_col = nullptr) {
     const int q = lane / BS, x = lane % BS, u = x;
     double a[BS], r[BS];
     const bool su = (u == 0) || (2 * u == BS);
@@ -289,6 +289,7 @@ __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lan
             if ((i & 3) == 0) ow[i >> 2] = c8; else ow[i >> 2] |= c8 << (8 * (i & 3));
         }
         store_row_words<BS>(recon + (size_t)y * rec_pitch, ow);
+        if (last_col) last_col[q * BS + y] = (uint8_t)(ow[BS / 4 - 1] >> 24);   // right column for the next block of the row
     }
     __syncwarp();
 }
@@ -384,21 +385,24 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
     const int qp = a.qp_all[(size_t)f * a.bh + by];
     volatile int* prog_up = (by > 0) ? a.progress + (size_t)fl * a.bh + (by - 1) : nullptr;
     int* prog_me = a.progress + (size_t)fl * a.bh + by;
+    int seen = 0;   // progress of the row above as last read: re-read only when it does not cover the block (see tq_iframe_kernel)
     for (int bx = 0; bx < a.bw; bx++) {
         const int ox = bx * BS, b = by * a.bw + bx;
         zero_lev<BS>(t, lane);
         __syncwarp();
         if (valid && x == 0) rle_to_tile<BS>(a, f, b, sm.zz, &t.lev[q][0][0]);
         const int mode = a.modes_all[(size_t)f * a.nblk + b];
-        if (by > 0 && valid && x == 0) {
-            while (*prog_up < bx + 1) { __nanosleep(20); }
+        bool polled = false;
+        if (by > 0 && valid && x == 0 && seen < bx + 1) {
+            polled = true;
+            while ((seen = *prog_up) < bx + 1) { __nanosleep(20); }
         }
+        if (__any_sync(0xffffffffu, polled)) __threadfence();
         __syncwarp();
-        __threadfence();
-        // find_intra_predict_block IFrame.py:175-213: mode 0 -> pred[r][c] = recon[oy+c][ox-1]; mode 1 -> recon[oy-1][ox+r]
-        const int lv = (ox > 0) ? (int)__ldcg(recon_plane + (size_t)(oy + x) * a.ref_pitch + ox - 1) : 128;
+        // find_intra_predict_block IFrame.py:175-213: mode 0 -> pred[r][c] = recon[oy+c][ox-1] (the right column this warp's
+        // previous block left in shared memory); mode 1 -> recon[oy-1][ox+r] (from the plane, written by another SM)
         const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
-        sm.left[q][x] = (uint8_t)lv;
+        if (ox == 0) sm.left[q][x] = 128;
         __syncwarp();
         uint32_t pw[BS / 4];
 #pragma unroll
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
         store_row_words<BS>(&t.pred[q][x][0], pw);
         __syncwarp();
         int16_t* lev = a.levels_out ? a.levels_out + ((size_t)f * a.H + oy) * a.W + ox : nullptr;
-        dequant_idct_recon_warp<BS>(t, lane, valid, qp, recon_plane + (size_t)oy * a.ref_pitch + ox, a.ref_pitch, lev, a.W);
+        dequant_idct_recon_warp<BS>(t, lane, valid, qp, recon_plane + (size_t)oy * a.ref_pitch + ox, a.ref_pitch, lev, a.W, &sm.left[0][0]);
         __threadfence();
         __syncwarp();
         if (valid && x == 0) atomicExch(prog_me, bx + 1);

@@ -74,23 +74,31 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     const int qp = a.qp_rows[(size_t)fl * a.bh + by];
     volatile int* prog_up = (by > 0) ? a.progress + (size_t)fl * a.bh + (by - 1) : nullptr;
     int* prog_me = a.progress + (size_t)fl * a.bh + by;
+    int seen = 0;                 // progress of the row above as last read (lane x == 0 of each frame)
+    uint32_t cw_next[BS / 4];     // the next block's current pixels are requested one block ahead
+    load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch, cw_next);
 
     for (int bx = 0; bx < a.bw; bx++) {
         const int ox = bx * BS;
-        // wait until the block above is reconstructed
-        if (by > 0 && valid && x == 0) {
-            while (*prog_up < bx + 1) { __nanosleep(20); }
-        }
-        __syncwarp();
-        __threadfence();
-        // neighbours (bypass L1: lines of the plane are being written by other SMs)
-        const int lv = (ox > 0) ? (int)__ldcg(recon_plane + (size_t)(oy + x) * a.ref_pitch + ox - 1) : 128;
-        const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
-        sm.left[q][x] = (uint8_t)lv;
-        sm.top[q][x] = (uint8_t)tv;
-        const uint8_t* cur = cur_plane + (size_t)(oy + x) * a.cur_pitch + ox;
         uint32_t cw[BS / 4];
-        load_row_aligned<BS>(cur, cw);
+#pragma unroll
+        for (int i = 0; i < BS / 4; i++) cw[i] = cw_next[i];
+        if (bx + 1 < a.bw) load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch + ox + BS, cw_next);
+        // wait until the block above is reconstructed; the row above usually runs several blocks ahead, so the counter is
+        // only read again when the last value seen does not cover this block
+        bool polled = false;
+        if (by > 0 && valid && x == 0 && seen < bx + 1) {
+            polled = true;
+            while ((seen = *prog_up) < bx + 1) { __nanosleep(20); }
+        }
+        if (__any_sync(0xffffffffu, polled)) __threadfence();
+        __syncwarp();
+        // top neighbours come from the plane (bypass L1: written by another SM); the left column was left in shared
+        // memory by this warp's previous block
+        const int lv = (ox > 0) ? (int)sm.left[q][x] : 128;
+        const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
+        if (ox == 0) sm.left[q][x] = 128;
+        sm.top[q][x] = (uint8_t)tv;
         store_row_words<BS>(&t.cur[q][x][0], cw);
         __syncwarp();
         // mode decision, IFrame.py:184-195.  In-frame predictors are uint8, so cur - pred wraps mod 256
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         o.resid_pitch = a.W;
         o.idct_out = nullptr;
         o.coef_out = nullptr;
-        tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, true);
+        tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, true, &sm.left[0][0]);
         // publish: reconstruction of (bx,by) is visible before the counter moves
         __threadfence();
         __syncwarp();

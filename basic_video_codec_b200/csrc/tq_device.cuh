@@ -157,7 +157,8 @@ __device__ __forceinline__ void stage_row(WarpTile<BS>& t, int q, int r, const u
 // plane (IFrame.py:30,57-58).
 template <int BS>
 __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, int qp, const TqOut& o,
-                                        const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid) {
+                                        const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid,
+                                        uint8_t* last_col = nullptr) {
     const int q = lane / BS, x = lane % BS;
     double a[BS], r[BS];
     // ---- forward pass 1: columns (apply_dct_2d transforms columns first, dct.py:12) ----
@@ -244,6 +245,9 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
             if (!intra_u8_resid && o.resid_mc) o.resid_mc[(size_t)y * o.resid_pitch + i] = (int8_t)(int)r[i];
         }
         store_row_words<BS>(o.recon + (size_t)y * o.rec_pitch, ow);
+        // the intra wavefront predicts the next block of the row from this block's right column: hand it over in shared
+        // memory instead of reading it back from the plane
+        if (last_col) last_col[q * BS + y] = (uint8_t)(ow[BS / 4 - 1] >> 24);
     }
     __syncwarp();
 }
