@@ -453,3 +453,24 @@ def test_two_devices_in_one_process():
             assert np.array_equal(ctx.decode_clip(data, nfr), recon)
         with bvc.Context(W, H, bs, 4, qp, 2, True, False, ip, device=dev, max_lanes=2) as ctx:
             assert ctx.encode_clip(frames)[0] == ob.encode_clip(ob.make_config(W, H, bs, 4, qp, nref=2, fastme=True, i_period=ip), frames, want_recon=False)[0]
+
+
+def test_dense_blocks_bs16_qp0():
+    """16x16 blocks with every level non-zero and near the largest magnitude (white noise / checkerboard at qp 0): the
+    entropy coder's dense path (more than 32 symbol positions per block), the per-block bit buffer at its worst case and
+    the container's length fields."""
+    ob = _ob()
+    H, W, bs = 64, 96, 16
+    rng = np.random.default_rng(17)
+    chk = ((np.indices((H, W)).sum(0) % 2) * 255).astype(np.uint8)
+    frames = np.stack([rng.integers(0, 256, (H, W)).astype(np.uint8), chk, rng.integers(0, 256, (H, W)).astype(np.uint8),
+                       255 - chk, rng.integers(0, 2, (H, W)).astype(np.uint8) * 255])
+    for qp, ip in ((0, 5), (0, 1), (2, 3)):
+        cfg = ob.make_config(W, H, bs, 4, qp, nref=1, i_period=ip)
+        want, want_recon = ob.encode_clip(cfg, frames)
+        with _ctx(W, H, bs, 4, qp, 1, False, False, ip, lanes=2) as ctx:
+            got, recon = ctx.encode_clip(frames, want_recon=True)
+            assert got == want and np.array_equal(recon, want_recon), (qp, ip)
+            assert np.array_equal(ctx.decode_clip(got, len(frames)), recon)
+    bits_per_block = len(want) * 8 / (len(frames) * (H // bs) * (W // bs))
+    assert bits_per_block > 600      # the case really is dense
