@@ -22,7 +22,7 @@ struct TqCtaSmem {
 
 // ---------------------------------------------------------------------------------------------
 // P frames: every block independent.  grid = (ceil(nblk / (TQ_WARPS*NBW)), lanes)
-template <int BS>
+template <int BS, bool DBG>
 __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
     constexpr int NBW = 32 / BS;
     extern __shared__ __align__(16) uint8_t smraw[];
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
     const int b = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + q;
     const bool valid = b < blk_end;
     const int bb = valid ? b : blk_end - 1;
-    tq_pframe_warp<BS>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
+    tq_pframe_warp<BS, DBG>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -205,23 +205,29 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) tq_blocks_kernel(const int16_t*
     tq_warp<BS>(t, lane, valid, qp, o, res + (size_t)bb * BS * BS, pred + (size_t)bb * BS * BS, false);
 }
 
-template <int BS>
-cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
+template <int BS, bool DBG>
+cudaError_t launch_pd(const TqArgs& a, int lanes, cudaStream_t st) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(TqCtaSmem<BS>);
     static bool once_dev[BVC_MAX_DEVICES] = {};
     bool& once = once_dev[current_device_slot()];
     if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tq_pframe_kernel<BS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tq_pframe_kernel<BS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(tq_pframe_kernel<BS, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         once = true;
     }
     const int nb = a.row_count * a.bw;
     dim3 grid((nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), lanes);
-    tq_pframe_kernel<BS><<<grid, TQ_WARPS * 32, smem, st>>>(a);
+    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
+}
+template <int BS>
+cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
+    // the debug planes (residuals with / without motion compensation) exist only for the frame-level calls
+    if (a.resid_mc || a.resid_nomc) return launch_pd<BS, true>(a, lanes, st);
+    return launch_pd<BS, false>(a, lanes, st);
 }
 
 template <int BS>

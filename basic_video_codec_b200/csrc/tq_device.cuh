@@ -79,6 +79,17 @@ __device__ __forceinline__ void fold_inv(const double (&v)[BS], double (&out)[BS
     }
 }
 
+// Integer <-> double without the conversion unit (XU pipe: I2F / F2I / FRND.F64 issue at a quarter of the fp64 rate).
+// 1.5 * 2^52 + t rounds t to the nearest integer, ties to even (the ulp there is 1), exactly like rint() for |t| < 2^51;
+// the low mantissa word of that sum is the integer in two's complement.  2^52 + 2^31 + n has n + 2^31 in its low word.
+__device__ __forceinline__ double rint_magic(double t, int& as_int) {
+    const double m = __dadd_rn(t, 6755399441055744.0);
+    as_int = __double2loint(m);
+    return __dsub_rn(m, 6755399441055744.0);
+}
+__device__ __forceinline__ double int_to_double(int n) {   // exact for any int32
+    return __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)n)), 4503601774854144.0);
+}
 __device__ __forceinline__ double pow2_neg(int s) { return __hiloint2double((1023 - s) << 20, 0); }
 __device__ __forceinline__ double pow2_pos(int s) { return __hiloint2double((1023 + s) << 20, 0); }
 
@@ -155,7 +166,8 @@ __device__ __forceinline__ void stage_row(WarpTile<BS>& t, int q, int r, const u
 // warp's trailing blocks.  qp: quantisation parameter of this block row.  Writes the lev tile (smem)
 // and the outputs in `o`.  intra_u8_resid: I frames store the raw int16 residual as uint8 in the debug
 // plane (IFrame.py:30,57-58).
-template <int BS>
+// DBG = false compiles the debug outputs (residual planes, idct / coefficient dumps) out: the clip path never asks for them.
+template <int BS, bool DBG = true>
 __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, int qp, const TqOut& o,
                                         const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid,
                                         uint8_t* last_col = nullptr) {
@@ -163,10 +175,10 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
     double a[BS], r[BS];
     // ---- forward pass 1: columns (apply_dct_2d transforms columns first, dct.py:12) ----
 #pragma unroll
-    for (int y = 0; y < BS; y++) a[y] = (double)(res_override ? (int)res_override[y * BS + x] : (int)t.res[q][y][x]);
-    if (intra_u8_resid && o.resid_mc && valid) {
+    for (int y = 0; y < BS; y++) a[y] = int_to_double(res_override ? (int)res_override[y * BS + x] : (int)t.res[q][y][x]);
+    if (DBG && intra_u8_resid && o.resid_mc && valid) {
 #pragma unroll
-        for (int y = 0; y < BS; y++) o.resid_mc[(size_t)y * o.resid_pitch + x] = (int8_t)(uint8_t)(int)a[y];
+        for (int y = 0; y < BS; y++) o.resid_mc[(size_t)y * o.resid_pitch + x] = (int8_t)(uint8_t)(res_override ? (int)res_override[y * BS + x] : (int)t.res[q][y][x]);
     }
     fold_fwd<BS>(a, r);
 #pragma unroll
@@ -186,12 +198,13 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         const bool sv = (v == 0) || (2 * v == BS);
         const double w = sv ? w_sp : w_nm;
         const double coef = __dmul_rn(r[v], w);
-        if (o.coef_out && valid) o.coef_out[u * BS + v] = coef;
+        if (DBG && o.coef_out && valid) o.coef_out[u * BS + v] = coef;
         // generate_quantization_matrix dct.py:21-32: shift s = qp + {0,1,2} for u+v <,=,> BS-1;
         // quantize_block :35-37 = round half to even of coef * 2^-s (exact scaling)
         const int s = qp + min(max(u + v - (BS - 2), 0), 2);
-        const double lq = rint(__dmul_rn(coef, pow2_neg(s)));
-        lv[v] = (short)(int)lq;
+        int li;
+        const double lq = rint_magic(__dmul_rn(coef, pow2_neg(s)), li);
+        lv[v] = (short)li;
         // rescale_block dct.py:40-42 is exact, so (lq * 2^s) * w == lq * (w * 2^s) with one rounding
         const double wq = __hiloint2double(__double2hiint(w) + (s << 20), __double2loint(w));
         a[v] = __dmul_rn(lq, wq);
@@ -237,12 +250,14 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         for (int i = 0; i < BS; i++) {
             const int pb = pred_override ? (int)pred_override[y * BS + i] : (int)((pw[i >> 2] >> (8 * (i & 3))) & 255u);
             // reconstruct_block Frame.py:197-202: round(idct + pred) -> int16 -> clip -> uint8
-            const int v = (int)(short)(int)rint(__dadd_rn(r[i], (double)pb));
+            int vi;
+            rint_magic(__dadd_rn(r[i], int_to_double(pb)), vi);
+            const int v = (int)(short)vi;
             const uint32_t c8 = (uint32_t)min(max(v, 0), 255);
             if ((i & 3) == 0) ow[i >> 2] = c8; else ow[i >> 2] |= c8 << (8 * (i & 3));
-            if (o.idct_out) o.idct_out[y * BS + i] = r[i];
+            if (DBG && o.idct_out) o.idct_out[y * BS + i] = r[i];
             // PFrame.py:39,63: float64 idct residual stored into an int8 plane (C cast: truncate, wrap)
-            if (!intra_u8_resid && o.resid_mc) o.resid_mc[(size_t)y * o.resid_pitch + i] = (int8_t)(int)r[i];
+            if (DBG && !intra_u8_resid && o.resid_mc) o.resid_mc[(size_t)y * o.resid_pitch + i] = (int8_t)(int)r[i];
         }
         store_row_words<BS>(o.recon + (size_t)y * o.rec_pitch, ow);
         // the intra wavefront predicts the next block of the row from this block's right column: hand it over in shared
@@ -435,7 +450,7 @@ __device__ __forceinline__ int entropy_block_warp(const int16_t* lev, const uint
 // the same block pass the same values; !valid lanes pass any in-range block and produce nothing).  Stages current and
 // predicted pixels, forms the residual, transforms / quantises / reconstructs and entropy-codes the blocks
 // (PFrame.process_block PFrame.py:99-125,230-249; Frame.py:61-75,190-202).
-template <int BS>
+template <int BS, bool DBG = true>
 __device__ __forceinline__ void tq_pframe_warp(const TqArgs& a, int fl, WarpTile<BS>& t, const uint8_t* zz, int lane, int b, bool valid,
                                                int4 mv) {
     constexpr int NBW = 32 / BS;
@@ -460,7 +475,7 @@ __device__ __forceinline__ void tq_pframe_warp(const TqArgs& a, int fl, WarpTile
         load_row_unaligned<BS>(pr, pw);
         stage_row<BS>(t, q, x, cw, pw);
     }
-    if (a.resid_nomc && valid) {
+    if (DBG && a.resid_nomc && valid) {
         // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
         const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(oy + x) * a.ref_pitch + ox;
         int8_t* d = a.resid_nomc + ((size_t)fl * a.H + oy + x) * a.W + ox;
@@ -479,7 +494,7 @@ __device__ __forceinline__ void tq_pframe_warp(const TqArgs& a, int fl, WarpTile
     o.idct_out = nullptr;
     o.coef_out = nullptr;
     const int qp = a.qp_rows[(size_t)fl * a.bh + by];
-    tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, false);
+    tq_warp<BS, DBG>(t, lane, valid, qp, o, nullptr, nullptr, false);
 
     // entropy-code the warp's blocks one after the other
 #pragma unroll 1
