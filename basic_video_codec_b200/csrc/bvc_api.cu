@@ -42,7 +42,7 @@ struct bvc_ctx {
     int max_lanes = 1;
     int pps = 1;          // planes per ring slot
     int slots = 2;        // ring slots per lane (nref + 1)
-    cudaStream_t st = nullptr, st_copy = nullptr, st_h2d = nullptr;
+    cudaStream_t st = nullptr, st_h2d = nullptr;   // compute / frame-level stream, input upload stream
     // clip path: the GOP lanes of a step are split into `ngroups` lane groups with their own streams, so the tail
     // of one group's motion search (a last, partly filled wave of 77 us CTAs) is filled by the other group's
     // kernels.  st_grp: motion search (low priority), st_post: everything after it (high priority).  B200's block
@@ -215,7 +215,6 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
     auto boot = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
@@ -268,7 +267,6 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
-    if (c->st_copy) cudaStreamSynchronize(c->st_copy);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
     for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
         if (c->st_grp[gi]) { cudaStreamSynchronize(c->st_grp[gi]); cudaStreamDestroy(c->st_grp[gi]); }
@@ -290,7 +288,6 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
-    if (c->st_copy) cudaStreamDestroy(c->st_copy);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     delete c;
 }

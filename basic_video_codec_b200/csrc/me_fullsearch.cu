@@ -41,13 +41,6 @@ namespace bvc {
 
 namespace {
 
-struct PassInfo {
-    int R;        // integer range on the (phase) plane
-    int sc;       // 1 = integer-pel, 2 = half-pel units
-    int px, py;   // phase (0/1)
-    int Rh;       // range in output MV units (R*sc)
-};
-
 template <int BS>
 struct CurBlock {
     static constexpr int WPR = BS / 4;  // words per row
