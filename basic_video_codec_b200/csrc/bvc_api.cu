@@ -42,7 +42,7 @@ struct bvc_ctx {
     int max_lanes = 1;
     int pps = 1;          // planes per ring slot
     int slots = 2;        // ring slots per lane (nref + 1)
-    cudaStream_t st = nullptr, st_h2d = nullptr;   // compute / frame-level stream, input upload stream
+    cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;   // compute / frame-level, input upload, decoded-plane download
     // clip path: the GOP lanes of a step are split into `ngroups` lane groups with their own streams, so the tail
     // of one group's motion search (a last, partly filled wave of 77 us CTAs) is filled by the other group's
     // kernels.  st_grp: motion search (low priority), st_post: everything after it (high priority).  B200's block
@@ -216,6 +216,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));   // numerically lower = higher priority
         for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
@@ -268,6 +269,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
+    if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
         if (c->st_grp[gi]) { cudaStreamSynchronize(c->st_grp[gi]); cudaStreamDestroy(c->st_grp[gi]); }
         if (c->st_post[gi]) { cudaStreamSynchronize(c->st_post[gi]); cudaStreamDestroy(c->st_post[gi]); }
@@ -289,6 +291,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->st) cudaStreamDestroy(c->st);
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     delete c;
 }
 
@@ -404,7 +407,8 @@ static int upload_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src) {
     return BVC_OK;
 }
 static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src, cudaStream_t st = nullptr) {
-    CK(cudaMemcpy2DAsync(dst, c->g.W, src, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToHost, st ? st : c->st));
+    if (c->g.pitch == c->g.W) CK(cudaMemcpyAsync(dst, src, (size_t)c->g.W * c->g.H, cudaMemcpyDeviceToHost, st ? st : c->st));
+    else CK(cudaMemcpy2DAsync(dst, c->g.W, src, c->g.pitch, c->g.W, c->g.H, cudaMemcpyDeviceToHost, st ? st : c->st));
     return BVC_OK;
 }
 
@@ -1019,7 +1023,19 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     a.levels_out = d_levels; a.progress = d_progress; a.err_flag = c->d_overflow;
     a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
     if (pred_only) steps.clear();
-    for (auto& st : steps) {
+    // Decoded planes go back on their own stream so that the download of step s overlaps the kernels of step s+1 (the
+    // 1.25 GB of planes of the headline clip are the decoder's bound).  A plane of the reconstruction ring is rewritten
+    // `slots` frames later: the kernels that rewrite it wait for its pending download.
+    std::vector<cudaEvent_t> ev_done(frames_out ? steps.size() : 0), ev_copied(frames_out ? steps.size() : 0);
+    std::vector<int> pending_copy(c->ref_planes, -1);   // plane -> step whose download still reads it
+    auto free_events = [&]() { for (auto e : ev_done) if (e) cudaEventDestroy(e); for (auto e : ev_copied) if (e) cudaEventDestroy(e); };
+    for (size_t si = 0; si < steps.size(); si++) {
+        auto& st = steps[si];
+        if (frames_out) {
+            int wait_for = -1;
+            for (int pl : st.outplanes) wait_for = std::max(wait_for, pending_copy[pl]);
+            if (wait_for >= 0) CK(cudaStreamWaitEvent(c->st, ev_copied[wait_for], 0));
+        }
         if (st.n_i) {
             CK(cudaMemsetAsync(d_progress, 0, st.n_i * g.bh * sizeof(int), c->st));
             a.lanes = d_lanes + st.off_i;
@@ -1031,11 +1047,23 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
             CK(launch_dec_pframe(a, (int)st.n_p, c->st));
             c->launches += 1;
         }
-        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) return rc;
-        if (frames_out)
-            for (size_t l = 0; l < st.frames.size(); l++)
-                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]))) != BVC_OK) return rc;
+        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) { free_events(); return rc; }
+        if (frames_out) {
+            CK(cudaEventCreateWithFlags(&ev_done[si], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_copied[si], cudaEventDisableTiming));
+            CK(cudaEventRecord(ev_done[si], c->st));
+            CK(cudaStreamWaitEvent(c->st_d2h, ev_done[si], 0));
+            for (size_t l = 0; l < st.frames.size(); l++) {
+                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]), c->st_d2h)) != BVC_OK) {
+                    free_events();
+                    return rc;
+                }
+                pending_copy[st.outplanes[l]] = (int)si;
+            }
+            CK(cudaEventRecord(ev_copied[si], c->st_d2h));
+        }
     }
+    if (frames_out && !steps.empty()) CK(cudaStreamWaitEvent(c->st, ev_copied[steps.size() - 1], 0));
     CK(cudaMemcpyAsync(&err, c->d_overflow, sizeof err, cudaMemcpyDeviceToHost, c->st));
     if (levels_out) CK(cudaMemcpyAsync(levels_out, d_levels, (size_t)n * g.W * g.H * sizeof(int16_t), cudaMemcpyDeviceToHost, c->st));
     std::vector<int4> hmv;
@@ -1047,6 +1075,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     }
     if (qp_out) CK(cudaMemcpyAsync(qp_out, d_qp, (size_t)n * g.bh * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+    free_events();
     if (err) return fail(c, BVC_ERR_INVALID, "malformed stream (missing prediction symbols, bad intra mode or motion vector out of range)");
     if (pred_out)
         for (int f = 0; f < n; f++)
