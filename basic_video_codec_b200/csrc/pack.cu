@@ -10,7 +10,7 @@
 // pack_scan_kernel: one CTA per frame.  Exclusive scans of the per-block bit counts (both streams),
 //   per-row bit totals (bits_per_row, PFrame.py:76-83), zeroing of the used part of the output
 //   streams and emission of the (small) prediction stream.
-// pack_emit_kernel: one warp per block, funnel-shifts the block's words to its bit offset and ORs
+// pack_emit_kernel: one thread per block, funnel-shifts the block's words to its bit offset and ORs
 //   them into the coefficient stream.
 #include "bvc_kernels.h"
 
@@ -170,11 +170,12 @@ __global__ void __launch_bounds__(256) pack_row_bits_kernel(PackArgs a, int row,
     if (threadIdx.x == 0) out[fl] = tot;
 }
 
-constexpr int EMIT_WARPS = 8;
-__global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) {
+// One thread per block: after quantisation a block's string is a handful of words (about 125 bits at the headline QP), so
+// a warp per block would leave most lanes idle; dense blocks (up to 203 words) just loop longer.
+constexpr int EMIT_THREADS = 256;
+__global__ void __launch_bounds__(EMIT_THREADS) pack_emit_kernel(PackArgs a) {
     const int fl = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * EMIT_WARPS + warp;
+    const int b = blockIdx.x * EMIT_THREADS + threadIdx.x;
     if (b >= a.nblk) return;
     const int nbits = a.blk_nbits[(size_t)fl * a.nblk + b];
     const long long D = a.coef_off[(size_t)fl * (a.nblk + 1) + b];
@@ -183,11 +184,12 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) pack_emit_kernel(PackArgs a) 
     const int n = (nbits + 31) >> 5;
     const int sh = (int)(D & 31);
     const long long w0 = D >> 5;
-    for (int j = lane; j <= n; j += 32) {
+    uint32_t hi = 0;
+    for (int j = 0; j <= n; j++) {
         const uint32_t lo = (j < n) ? src[j] : 0u;
-        const uint32_t hi = (j > 0) ? src[j - 1] : 0u;
         const uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
         if (v) atomicOr(&dst[w0 + j], __byte_perm(v, 0, 0x0123));
+        hi = lo;
     }
 }
 
@@ -263,8 +265,8 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st) {
     pack_scan_kernel<<<lanes, SCAN_THREADS, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 grid((a.nblk + EMIT_WARPS - 1) / EMIT_WARPS, lanes);
-    pack_emit_kernel<<<grid, EMIT_WARPS * 32, 0, st>>>(a);
+    dim3 grid((a.nblk + EMIT_THREADS - 1) / EMIT_THREADS, lanes);
+    pack_emit_kernel<<<grid, EMIT_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 
