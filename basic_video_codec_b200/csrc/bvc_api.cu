@@ -1264,6 +1264,10 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     // dependency, so the post-ME kernels of one group run while the other groups search.
     const int NG = std::max(1, std::min(c->ngroups, G));
     const int per = (G + NG - 1) / NG;
+    // per-kernel event pairs only make sense when the kernels of a step run back to back on one stream; with lane groups
+    // they would just be ~500 extra event records per clip
+    struct TimingGuard { bvc_ctx* c; bool saved; ~TimingGuard() { c->timing = saved; } } timing_guard{c, c->timing};
+    c->timing = c->timing && NG == 1;
     for (int gi = 0; gi < NG; gi++) {
         CK(cudaStreamWaitEvent(c->st_grp[gi], ev_clip0, 0));
         CK(cudaStreamWaitEvent(c->st_post[gi], ev_clip0, 0));

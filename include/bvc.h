@@ -159,7 +159,9 @@ int bvc_set_fastme_direct(bvc_ctx *ctx, int on);
 int64_t bvc_launch_count(const bvc_ctx *ctx);
 /* Device time of the last clip call, from CUDA events recorded on the context's compute stream around
  * every kernel launch: ms[k] / launches[k] per kernel class (BVC_K_*), and the whole call (first
- * enqueue to last download) in *clip_ms.  Any pointer may be NULL. */
+ * enqueue to last download) in *clip_ms.  The per-class figures are recorded only with one lane group
+ * (bvc_set_lane_groups(ctx, 1)), where kernels run back to back on one stream; otherwise they are 0.
+ * Any pointer may be NULL. */
 #define BVC_K_ME 0       /* motion estimation (full search or FastME) */
 #define BVC_K_TQ_P 1     /* P-frame residual/transform/quantise/reconstruct + per-block entropy */
 #define BVC_K_TQ_I 2     /* I-frame intra wavefront (same body) */
