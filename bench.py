@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
 # DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r1_ncu_*.csv)
-ME_TRAFFIC_BYTES_PER_LANE = (83.670784e6 + 5.514240e6) / 20
-TQ_TRAFFIC_BYTES_PER_LANE = (43.443712e6 + 3.874816e6) / 10     # 10-lane launch (two lane groups)
+ME_TRAFFIC_BYTES_PER_LANE = (41.834240e6 + 0.472576e6) / 10       # 10-lane launch (two lane groups)
+TQ_TRAFFIC_BYTES_PER_LANE = (43.469568e6 + 3.402240e6) / 10
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
 
@@ -320,7 +320,7 @@ def main():
             "kernel": "me_tiled_kernel<16,4> (full-search SAD, VABSDIFF4.U8.ACC)", "bound": "int-simd",
             "achieved": achieved / 1e12, "peak": peaks["px_per_s"] / 1e12, "unit": "Tpx-absdiff/s",
             "frac": achieved / peaks["px_per_s"], "traffic": ME_TRAFFIC_BYTES_PER_LANE * args.lanes,
-            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 20-lane launch / 20 (profiles/r1_ncu_me_kernel.csv); "
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 10-lane launch / 10 (profiles/r1_ncu_me_kernel.csv); "
                               "algorithmic: 2 planes of 2.09 MB per lane",
             "algorithmic_bytes": 2 * W * H * args.lanes + 16 * (W // BS) * (H // BS) * args.lanes,
             "peak_source": peaks["int_src"], "launch_ms": me_avg_s * 1e3, "launches": me_n,
