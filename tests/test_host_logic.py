@@ -93,3 +93,26 @@ def test_input_stage_file_helpers(tmp_path):
     assert open(tmp_path / "clip.y", "rb").read() == ys.tobytes()
     p = ist.pad_frame(ys[0], 8)
     assert p.shape == (24, 40) and np.array_equal(p[:h, :w], ys[0]) and (p[h:, :] == 128).all() and (p[:, w:] == 128).all()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU only): one JSON line with the contract's keys, metric / unit / config of our own arm."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "encoded frames/s" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and "BASELINE configs[3]" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # under torchrun only rank 0 works and prints
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
