@@ -353,6 +353,13 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     if (threadIdx.x == 0) sbest = ~0ull;
     __syncthreads();
     const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)oy * a.cur_pitch + ox;
+    // the current block as 32-bit words in shared memory; reference rows are read as aligned words and funnel-shifted, so a
+    // candidate costs bs*bs/4 VABSDIFF4 instead of bs*bs byte operations
+    __shared__ uint32_t scur[32 * 32 / 4];
+    const int wpr = bs >> 2;
+    for (int i = threadIdx.x; i < bs * wpr; i += blockDim.x)
+        scur[i] = *reinterpret_cast<const uint32_t*>(cur + (size_t)(i / wpr) * a.cur_pitch + 4 * (i % wpr));
+    __syncthreads();
     const int R = a.R, n1 = 2 * R + 1;
     unsigned long long best = ~0ull;
     const int per_plane = n1 * n1;
@@ -364,9 +371,18 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
         const int dy = q / n1 - R, dx = q - (q / n1) * n1 - R;
         if (ox + dx < 0 || oy + dy < 0 || ox + dx + bs > a.W - px || oy + dy + bs > a.H - py || dx > R - px || dy > R - py) continue;
         const uint8_t* ref = ref_base + (size_t)(L.ref_plane[r] + ph) * ref_plane_bytes + (size_t)(oy + dy) * ref_pitch + (ox + dx);
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(ref);
+        const uint32_t sh = (uint32_t)(ad & 3) * 8;      // the same for every row: the pitch is a multiple of 16
+        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
         uint32_t s = 0;
-        for (int y = 0; y < bs; y++)
-            for (int x = 0; x < bs; x++) s += (uint32_t)abs((int)cur[(size_t)y * a.cur_pitch + x] - (int)ref[(size_t)y * ref_pitch + x]);
+        for (int y = 0; y < bs; y++, rowp += ref_pitch >> 2) {
+            uint32_t lo = rowp[0];
+            for (int w = 0; w < wpr; w++) {
+                const uint32_t hi = rowp[w + 1];
+                s = sad4(__funnelshift_r(lo, hi, sh), scur[y * wpr + w], s);
+                lo = hi;
+            }
+        }
         const int mvx = a.sc * dx + px, mvy = a.sc * dy + py;
         const uint32_t hi = (s << 9) + (uint32_t)(abs(mvx) + abs(mvy));
         const uint32_t lo = ((uint32_t)r << 20) | ((uint32_t)(mvy + a.Rh) << 10) | (uint32_t)(mvx + a.Rh);
