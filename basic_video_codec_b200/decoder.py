@@ -15,8 +15,8 @@ from collections import deque
 
 import numpy as np
 
-from ._lib import Context
 from .encoder.encoder import _psnr, output_dir
+from .encoder.Frame import context_for
 from .encoder.IFrame import IFrame
 from .encoder.PFrame import PFrame
 
@@ -33,9 +33,8 @@ def decode_video(params, device: int = 0, max_lanes: int = 16):
     out = output_dir(params)
     W, H = _padded(params)
     data = open(os.path.join(out, "encoded.bin"), "rb").read()
-    with Context(W, H, ec.block_size, ec.search_range, ec.quantization_factor, ec.nRefFrames, ec.fastME, ec.fracMeEnabled,
-                 ec.I_Period, device=device, max_lanes=max_lanes) as ctx:
-        frames = ctx.decode_clip(data, params.frames_to_process)
+    ctx = context_for(ec, W, H, device, max_lanes)       # cached: creating a context allocates the device pools
+    frames = ctx.decode_clip(data, params.frames_to_process)
     rec_path = os.path.join(out, "mc_reconstructed.yuv")
     rec = np.fromfile(rec_path, dtype=np.uint8) if os.path.exists(rec_path) else None
     with open(os.path.join(out, "mc_decoded.yuv"), "wb") as fh:

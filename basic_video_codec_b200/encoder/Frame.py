@@ -41,15 +41,15 @@ _ctx_cache: dict = {}
 _ctx_lock = threading.Lock()
 
 
-def context_for(ec, width, height, device=0) -> Context:
-    """One cached GPU context per (geometry, parameters, device)."""
+def context_for(ec, width, height, device=0, max_lanes=1) -> Context:
+    """One cached GPU context per (geometry, parameters, device, lanes)."""
     key = (width, height, ec.block_size, ec.search_range, ec.quantization_factor, ec.nRefFrames, bool(ec.fastME),
-           bool(ec.fracMeEnabled), ec.I_Period, device)
+           bool(ec.fracMeEnabled), ec.I_Period, device, max_lanes)
     with _ctx_lock:
         ctx = _ctx_cache.get(key)
         if ctx is None:
             ctx = Context(width, height, ec.block_size, ec.search_range, ec.quantization_factor, ec.nRefFrames,
-                          ec.fastME, ec.fracMeEnabled, ec.I_Period, device=device, max_lanes=1)
+                          ec.fastME, ec.fracMeEnabled, ec.I_Period, device=device, max_lanes=max_lanes)
             _ctx_cache[key] = ctx
         return ctx
 
@@ -216,6 +216,7 @@ class Frame:
         quant_dct_coff_fh.write(self.quantized_dct_residual_frame.tobytes())
         reconstructed_fh.write(self.reconstructed_frame.tobytes())
         if self.prediction_mode == PredictionMode.INTER_FRAME:
-            for k in sorted(self.mv_field.keys()):
-                mv_fh.write(f"{k[0]},{k[1]}:{self.mv_field[k][0]},{self.mv_field[k][1]}|")
+            # sorted by (x, y) like file_io.write_mv_to_file; one write instead of one per block
+            mvf = self.mv_field
+            mv_fh.write("".join(f"{k[0]},{k[1]}:{mvf[k][0]},{mvf[k][1]}|" for k in sorted(mvf)))
         mv_fh.write("\n")

@@ -3,6 +3,17 @@ from .Frame import Frame, context_for
 from .PredictionMode import PredictionMode
 
 
+_KEYS = {}
+
+
+def _block_keys(W, H, bs):
+    """[(x, y)] of every block in raster order, cached per geometry."""
+    k = _KEYS.get((W, H, bs))
+    if k is None:
+        k = _KEYS[(W, H, bs)] = [(x, y) for y in range(0, H, bs) for x in range(0, W, bs)]
+    return k
+
+
 class PFrame(Frame):
     def __init__(self, curr_frame=None, reference_frames=None, interpolated_reference_frames=None):
         super().__init__(curr_frame, reference_frames, interpolated_reference_frames)
@@ -21,11 +32,8 @@ class PFrame(Frame):
         self.residual_frame = r.resid_mc
         self.residual_wo_mc_frame = r.resid_nomc
         bs, bw = ec.block_size, W // ec.block_size
-        fast = bool(ec.fastME)
         # raster order (= sorted by (y, x)); full search stores lists, FastME tuples (block_predictor.py:50-56,91)
-        self.mv_field = {}
-        for b in range(r.mv.shape[0]):
-            key = ((b % bw) * bs, (b // bw) * bs)
-            v = (int(r.mv[b, 0]), int(r.mv[b, 1]), int(r.mv[b, 2]))
-            self.mv_field[key] = v if fast else list(v)
+        keys = _block_keys(W, H, bs)
+        vals = r.mv.tolist()
+        self.mv_field = dict(zip(keys, map(tuple, vals))) if ec.fastME else dict(zip(keys, vals))
         return self
