@@ -842,6 +842,17 @@ static int dbuf(bvc_ctx* c, bvc_ctx::DBuf& b, size_t n, T** out) {
     return BVC_OK;
 }
 
+// Events created for the duration of one call; destroyed on every exit path.
+struct EventBag {
+    std::vector<cudaEvent_t> ev;
+    ~EventBag() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+    cudaError_t make(cudaEvent_t* out, unsigned flags = cudaEventDefault) {
+        cudaError_t r = cudaEventCreateWithFlags(out, flags);
+        if (r == cudaSuccess) ev.push_back(*out);
+        return r;
+    }
+};
+
 struct DecRecord { int intra; size_t pred_off, pred_len, coef_off, coef_len; };
 
 // init_refs / n_init: reference window the first frame sees (deque order, oldest first).  n_init < 0: the decoder's
@@ -1026,9 +1037,9 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     // Decoded planes go back on their own stream so that the download of step s overlaps the kernels of step s+1 (the
     // 1.25 GB of planes of the headline clip are the decoder's bound).  A plane of the reconstruction ring is rewritten
     // `slots` frames later: the kernels that rewrite it wait for its pending download.
+    EventBag bag;
     std::vector<cudaEvent_t> ev_done(frames_out ? steps.size() : 0), ev_copied(frames_out ? steps.size() : 0);
     std::vector<int> pending_copy(c->ref_planes, -1);   // plane -> step whose download still reads it
-    auto free_events = [&]() { for (auto e : ev_done) if (e) cudaEventDestroy(e); for (auto e : ev_copied) if (e) cudaEventDestroy(e); };
     for (size_t si = 0; si < steps.size(); si++) {
         auto& st = steps[si];
         if (frames_out) {
@@ -1047,17 +1058,15 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
             CK(launch_dec_pframe(a, (int)st.n_p, c->st));
             c->launches += 1;
         }
-        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) { free_events(); return rc; }
+        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) return rc;
         if (frames_out) {
-            CK(cudaEventCreateWithFlags(&ev_done[si], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_copied[si], cudaEventDisableTiming));
+            CK(bag.make(&ev_done[si], cudaEventDisableTiming));
+            CK(bag.make(&ev_copied[si], cudaEventDisableTiming));
             CK(cudaEventRecord(ev_done[si], c->st));
             CK(cudaStreamWaitEvent(c->st_d2h, ev_done[si], 0));
             for (size_t l = 0; l < st.frames.size(); l++) {
-                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]), c->st_d2h)) != BVC_OK) {
-                    free_events();
+                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]), c->st_d2h)) != BVC_OK)
                     return rc;
-                }
                 pending_copy[st.outplanes[l]] = (int)si;
             }
             CK(cudaEventRecord(ev_copied[si], c->st_d2h));
@@ -1075,7 +1084,6 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     }
     if (qp_out) CK(cudaMemcpyAsync(qp_out, d_qp, (size_t)n * g.bh * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    free_events();
     if (err) return fail(c, BVC_ERR_INVALID, "malformed stream (missing prediction symbols, bad intra mode or motion vector out of range)");
     if (pred_out)
         for (int f = 0; f < n; f++)
@@ -1229,9 +1237,10 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
 
     c->ev_used = 0;
     c->spans.clear();
+    EventBag bag;
     cudaEvent_t ev_clip0, ev_clip1;
-    CK(cudaEventCreate(&ev_clip0));
-    CK(cudaEventCreate(&ev_clip1));
+    CK(bag.make(&ev_clip0));
+    CK(bag.make(&ev_clip1));
     CK(cudaEventRecord(ev_clip0, c->st));
     // ---- input: uploaded step by step on its own stream so the copies overlap compute ----
     std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps : 0);
@@ -1248,7 +1257,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
                 CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
                                      cudaMemcpyHostToDevice, c->st_h2d));
         }
-        CK(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
+        CK(bag.make(&ev_h2d[s], cudaEventDisableTiming));
         CK(cudaEventRecord(ev_h2d[s], c->st_h2d));
         return BVC_OK;
     };
@@ -1321,9 +1330,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     CK(cudaMemcpyAsync(&total, c->d_frame_off + nframes, sizeof total, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(&overflow, c->d_overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    for (auto e : ev_h2d) cudaEventDestroy(e);
-    if (overflow) { cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1); return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field"); }
-    if ((size_t)total > out_cap) { cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1); return fail(c, BVC_ERR_NOMEM, "output buffer too small"); }
+    if (overflow) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
+    if ((size_t)total > out_cap) return fail(c, BVC_ERR_NOMEM, "output buffer too small");
     CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -1339,7 +1347,6 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_clip0, ev_clip1);
         c->last_clip_ms = ms;
-        cudaEventDestroy(ev_clip0); cudaEventDestroy(ev_clip1);
     }
     return BVC_OK;
 }
