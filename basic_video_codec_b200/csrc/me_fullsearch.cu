@@ -158,8 +158,13 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     const int copy_stride = a.win_copy_bytes + 32;  // +32 B: copy k starts 8 banks after copy k-1 (conflict-free LDS)
     const int bx0 = blockIdx.x * NB;
     const int by0 = blockIdx.y * NBY;
-    const int lane = blockIdx.z;
+    // SAD-map mode has no reduction across references, so every (lane, reference) pair gets its own CTAs
+    // (grid.z = lanes * max_refs): small frames (CIF: 30 tiles per lane) then fill the GPU
+    const int lane = SADMAP ? (int)blockIdx.z / a.max_refs : (int)blockIdx.z;
     const MeLane& L = a.lanes[lane];
+    const int r_begin = SADMAP ? (int)blockIdx.z % a.max_refs : 0;
+    const int r_end = SADMAP ? min(r_begin + 1, L.nref) : L.nref;
+    if (r_begin >= r_end) return;
     uint8_t* scur = smem + 4 * (size_t)copy_stride;   // [NBY*BS][NB*BS] current pixels of the CTA's blocks
 
     const int nmain = NB * 2 * R;
@@ -190,10 +195,8 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
         fence_mbar_init();
         // the first window is requested before anything else, so the TMA latency hides behind the staging of the
         // current blocks and the candidate table
-        if (L.nref > 0) {
-            mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
-            tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[0]);
-        }
+        mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
+        tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r_begin]);
     }
     for (int i = tid; i < NB * NBY; i += blockDim.x) sbest[i / NB][i % NB] = ~0ull;
     {   // stage the current blocks (NB*BS x NBY*BS bytes) in shared memory, 16 B per thread-iteration
@@ -226,10 +229,10 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     uint32_t parity = 0;
     const int nmid = (2 * R) / BS - 1;
 
-    for (int r = 0; r < L.nref; r++) {
+    for (int r = r_begin; r < r_end; r++) {
         for (int ph = 0; ph < a.nphase; ph++) {
             const int px = ph & 1, py = ph >> 1;
-            if (tid == 0 && (r | ph) != 0) {
+            if (tid == 0 && (r != r_begin || ph != 0)) {
                 mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
                 // box origin: 16-byte aligned column (bx0*BS - R - win_lm), rows <= 256
                 tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r] + ph);
@@ -423,7 +426,7 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, lanes);
+    dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, SADMAP ? lanes * a.max_refs : lanes);
     me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC><<<grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
 }
