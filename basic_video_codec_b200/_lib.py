@@ -324,9 +324,10 @@ class Context:
         self._check(self._L.bvc_set_lane_groups(self._h, int(groups)))
         self.lane_groups = int(groups)
 
-    def set_fastme_direct(self, on: bool):
-        """FastME candidates evaluated directly instead of from the SAD map (bvc_set_fastme_direct); default off."""
-        self._check(self._L.bvc_set_fastme_direct(self._h, int(bool(on))))
+    def set_fastme_direct(self, on):
+        """FastME evaluation (bvc_set_fastme_direct): 0 / False (default) = SAD map + transfer tables, 1 / True = every
+        candidate evaluated directly, 2 = SAD map + serial walk.  The output does not depend on it."""
+        self._check(self._L.bvc_set_fastme_direct(self._h, int(on)))
 
     def launch_count(self):
         return int(self._L.bvc_launch_count(self._h))

@@ -87,7 +87,8 @@ struct bvc_ctx {
     // decoder scratch (grow-only device buffers, see dbuf())
     struct DBuf { void* p = nullptr; size_t cap = 0; };
     DBuf sad_map;         // FastME look-up table (uint16 [lanes][nref][phase][blk][n1*n1])
-    int fastme_direct = 0;  // 1: evaluate FastME candidates directly (bvc_set_fastme_direct) instead of from the SAD map
+    DBuf fastme_tab;      // FastME transfer tables + per-block predictors (fastme_table_bytes)
+    int fastme_direct = 0;  // bvc_set_fastme_direct: 0 SAD map + transfer tables, 1 direct evaluation, 2 SAD map + serial walk
     DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
         dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress;
 
@@ -285,7 +286,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->d_overflow); cudaFree(c->d_container);
     for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
                              &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
-                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->sad_map})
+                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->sad_map, &c->fastme_tab})
         cudaFree(b->p);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -327,7 +328,7 @@ extern "C" int bvc_set_lane_groups(bvc_ctx* c, int groups) {
 
 extern "C" int bvc_set_fastme_direct(bvc_ctx* c, int on) {
     if (!c) return BVC_ERR_INVALID;
-    c->fastme_direct = on ? 1 : 0;
+    c->fastme_direct = on == 2 ? 2 : (on ? 1 : 0);
     return BVC_OK;
 }
 
@@ -422,7 +423,7 @@ struct StepPlan {
 static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cudaStream_t st) {
     const Geom& g = c->g;
     const int Rm = c->p.frac_me ? 8 : 16;   // 16 MV units around the block: where the walk can look before it stops
-    if (!c->fastme_direct && c->have_map && me_can_map(g.bs, Rm)) {
+    if (c->fastme_direct != 1 && c->have_map && me_can_map(g.bs, Rm)) {
         const size_t n1 = 2 * (size_t)Rm + 1;
         const size_t stride = (n1 * n1 + 7) / 8 * 8;   // 16-byte multiples: the walk stages a block's table with cp.async
         const size_t per_lane = (size_t)c->p.nref_frames * m.nphase * g.nblk * stride;
@@ -441,8 +442,22 @@ static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cud
         mm.map_stride = (int)stride;
         CK(cudaMemsetAsync(mm.sad_map, 0xFF, (size_t)nl * per_lane * sizeof(uint16_t), st));
         CK(launch_me_fullsearch(&c->ref_map, mm, nl, c->ref_pool, g.plane_bytes, g.pitch, st));
-        CK(launch_fastme_walk(mm, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
-        c->launches += 1;
+        if (c->fastme_direct == 2) {
+            CK(launch_fastme_walk(mm, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
+            c->launches += 1;
+            return BVC_OK;
+        }
+        const size_t tneed = fastme_table_bytes(c->max_lanes, g.nblk);
+        if (tneed > c->fastme_tab.cap) {
+            if (c->fastme_tab.p) CK(cudaFree(c->fastme_tab.p));
+            c->fastme_tab.p = nullptr; c->fastme_tab.cap = 0;
+            CK(cudaMalloc(&c->fastme_tab.p, tneed));
+            c->fastme_tab.cap = tneed;
+        }
+        // lane groups run concurrently on their own streams: each gets its own slice of the scratch
+        char* scratch = static_cast<char*>(c->fastme_tab.p) + fastme_table_bytes((int)L0, g.nblk);
+        CK(launch_fastme_table(mm, nl, c->ref_pool, g.plane_bytes, g.pitch, scratch, c->d_cmp + L0, st));
+        c->launches += 3;
         return BVC_OK;
     }
     CK(launch_fastme(m, nl, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));

@@ -53,6 +53,11 @@ cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, s
 // the serial MVP chain becomes table look-ups; candidates outside the map are evaluated directly.
 cudaError_t launch_fastme_walk(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
                                long long* cmp_out, cudaStream_t st);
+// The same with transfer tables: every block's walk tabulated for all predictors within +-15 (parallel), the MVP chain as one
+// look-up per block, then the walks replayed in parallel for SAD / comparison counts.  scratch: fastme_table_bytes().
+size_t fastme_table_bytes(int lanes, int nblk);
+cudaError_t launch_fastme_table(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                                void* scratch, long long* cmp_out, cudaStream_t st);
 // true when the tiled search kernel can produce the SAD map for (block size, map radius in plane units)
 bool me_can_map(int bs, int R);
 

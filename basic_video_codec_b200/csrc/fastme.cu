@@ -92,25 +92,124 @@ __global__ void __launch_bounds__(FM_THREADS) fastme_kernel(MeArgs a, const uint
 // ---------------------------------------------------------------------------------------------
 // FastME on a SAD map.  The candidates of every level lie within one MV unit of the running predictor, and the walk
 // stops once a component reaches 16, so nearly every SAD it can ask for lies within +-16 MV units of the block.  The
-// tiled full-search kernel computes all of those at VABSDIFF4 speed (a.sad_map, radius a.R plane units); the serial MVP
-// chain of a frame is then one warp doing table look-ups: the table of the next block is fetched into shared memory
-// with cp.async while the current block is walked (double buffer), lane c takes candidate c = 6*ref + key, and the
-// first strict minimum in (ref, key) order is a warp min over (SAD << 8 | c).  A candidate outside the map (possible
-// when the predictor has drifted beyond 16) is evaluated directly by the whole warp.  Same results, same comparison
-// count as fastme_kernel above.  grid = lanes, one warp each; dynamic smem = 2 * nref_max * nphase * map_stride * 2 B.
+// tiled full-search kernel computes all of those at VABSDIFF4 speed (a.sad_map, radius a.R plane units).  What is left
+// of find_fast_me_block is table look-ups, organised in one of two ways:
+//
+//   serial walk (fastme_walk_kernel, bvc_set_fastme_direct(ctx, 2)): one warp per frame walks the blocks in raster
+//   order; the table of the next block is fetched into shared memory with cp.async while the current one is walked.
+//
+//   transfer table (default): the walk of a block is a pure function  F_b : predictor -> vector  of the block's SAD
+//   map, and one level of it is a pure function  step_b : predictor -> (predictor' | stop).  fastme_table_kernel (one
+//   CTA per block) evaluates step_b for all 31 x 31 predictors with components in [-15, 15] (their levels only touch
+//   the map: a component of +-16 stops the walk), then follows the step pointers to the fixed point, which gives F_b for
+//   every such predictor -- all blocks and predictors in parallel.  The serial MVP chain of a frame
+//   (mvp_{b+1} = F_b(mvp_b), PFrame.py:34,44,105-110) is then one 2-byte look-up per block (fastme_chain_kernel, tables
+//   staged through a cp.async ring); a predictor outside the table (drifted past 15) is walked on the spot.  Finally
+//   fastme_finish_kernel (one warp per block, all blocks in parallel) replays each block's walk from its now known
+//   predictor for the vector, its SAD and the comparison count.
+//
+// A candidate outside the map is evaluated directly by the warp.  Same results and comparison count as fastme_kernel.
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// per-lane candidate constants: a lane handles candidates c = lane (and lane + 32 when there are more than 32);
+// c = 6 * reference + key, keys in the order origin, pmv_origin, top, right, bottom, left (block_predictor.py:20-47)
+struct WalkLane {
+    int ck[2], cdx[2], cdy[2];
+    bool con[2], corg[2], cfirst[2];
+    __device__ __forceinline__ void init(int lane, int ncand) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int c = lane + 32 * j, p = c % 6;
+            con[j] = c < ncand;
+            ck[j] = con[j] ? c / 6 : 0;
+            corg[j] = p == 0;
+            cdx[j] = (p == 3) - (p == 5);
+            cdy[j] = (p == 4) - (p == 2);
+            cfirst[j] = c < 6;
+        }
+    }
+};
+
+// The walk of one block (find_fast_me_block) by one warp, starting from predictor (mvpx, mvpy).  tab = the block's SAD
+// map, chunk (reference k, phase ph) at tab + (k * nphase + ph) * kp_stride (shared or global memory).
+// Returns the vector in (mvpx, mvpy), its SAD, and adds the comparisons to cmp_total.
+__device__ __forceinline__ void walk_block(const MeArgs& a, const MeLane& L, const WalkLane& wl, const uint8_t* curp,
+                                           const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                                           const uint16_t* tab, size_t kp_stride, int b, int lane, int& mvpx, int& mvpy,
+                                           int& best_sad, long long& cmp_total) {
+    const int bs = a.bs, R = a.R, n1 = 2 * R + 1;
+    const int nref = L.nref, ncand = 6 * nref, tri = nref * (nref + 1) / 2;
+    const int ox = (b % a.bw) * bs, oy = (b / a.bw) * bs;
+    for (;;) {
+        uint32_t key = 0xffffffffu;
+        int nvalid = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (j == 1 && ncand <= 32) break;   // warp-uniform
+            const bool on = wl.con[j];
+            const int k = wl.ck[j];
+            const int cx = wl.corg[j] ? 0 : mvpx + wl.cdx[j];
+            const int cy = wl.corg[j] ? 0 : mvpy + wl.cdy[j];
+            int ph = 0, px = 0, py = 0, dx = cx, dy = cy;
+            if (a.sc == 2) { px = cx & 1; py = cy & 1; ph = px | (py << 1); dx = cx >> 1; dy = cy >> 1; }
+            const bool inmap = dx >= -R && dy >= -R && dx <= R - px && dy <= R - py;
+            int s = -1;
+            if (on && inmap) {
+                const uint16_t v = tab[(size_t)(k * a.nphase + ph) * kp_stride + (dy + R) * n1 + (dx + R)];
+                s = v == 0xffffu ? -1 : (int)v;
+            }
+            // candidates outside the map: the warp evaluates them one by one (is_out_of_range block_predictor.py:116-143)
+            uint32_t need = __ballot_sync(0xffffffffu, on && !inmap);
+            while (need) {
+                const int src = __ffs(need) - 1;
+                need &= need - 1;
+                const int kk = __shfl_sync(0xffffffffu, k, src), pp = __shfl_sync(0xffffffffu, ph, src);
+                const int ddx = __shfl_sync(0xffffffffu, dx, src), ddy = __shfl_sync(0xffffffffu, dy, src);
+                const int phx = pp & 1, phy = pp >> 1;
+                const bool ok = (ox + ddx >= 0) && (oy + ddy >= 0) && (ox + ddx + bs <= a.W - phx) && (oy + ddy + bs <= a.H - phy);
+                int t = -1;
+                if (ok) {
+                    const uint8_t* rp = ref_base + (size_t)(L.ref_plane[kk] + pp) * ref_plane_bytes + (size_t)(oy + ddy) * ref_pitch + (ox + ddx);
+                    t = 0;
+                    for (int i = lane; i < bs * bs; i += 32) {
+                        const int y = i / bs, x = i - y * bs;
+                        t += abs((int)curp[(size_t)(oy + y) * a.cur_pitch + ox + x] - (int)rp[(size_t)y * ref_pitch + x]);
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+                }
+                if (lane == src) s = t;
+            }
+            if (on && s >= 0) key = min(key, ((uint32_t)s << 8) | (uint32_t)(lane + 32 * j));
+            nvalid += __popc(__ballot_sync(0xffffffffu, on && s >= 0 && wl.cfirst[j]));
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
+        cmp_total += (long long)(nvalid * tri);
+        const int best_p = (key == 0xffffffffu) ? 0 : (int)(key & 255u) % 6;
+        best_sad = (key == 0xffffffffu) ? 0x7fffffff : (int)(key >> 8);
+        const int mvx = best_p == 0 ? 0 : mvpx + (best_p == 3) - (best_p == 5);
+        const int mvy = best_p == 0 ? 0 : mvpy + (best_p == 4) - (best_p == 2);
+        const bool stop = (best_p <= 1) || abs(mvx) >= 16 || abs(mvy) >= 16;
+        mvpx = mvx;
+        mvpy = mvy;
+        if (stop) break;
+    }
+}
 
 __global__ void __launch_bounds__(32) fastme_walk_kernel(MeArgs a, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
                                                        long long* cmp_out) {
     extern __shared__ __align__(16) uint16_t s_map[];   // [2][nref][nphase][map_stride]
-    const int bs = a.bs, lane = threadIdx.x, fl = blockIdx.x;
+    const int lane = threadIdx.x, fl = blockIdx.x;
     const MeLane& L = a.lanes[fl];
     const uint8_t* curp = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
-    const int nref = L.nref, ncand = 6 * nref, R = a.R, n1 = 2 * R + 1;
+    const int nref = L.nref;
     const int chunk = a.map_stride;                       // elements per (ref, phase) of one block
     const int buf_elems = a.max_refs * a.nphase * chunk;
     const int vec_per_chunk = chunk / 8, nchunks = nref * a.nphase;
@@ -124,89 +223,215 @@ __global__ void __launch_bounds__(32) fastme_walk_kernel(MeArgs a, const uint8_t
             for (int v = lane; v < vec_per_chunk; v += 32) cp_async16(dst + v * 8, src + v * 8);
         cp_async_commit();
     };
-    // per-lane candidate constants: lane handles candidates c = lane (and lane + 32 when there are more than 32)
-    int ck[2], cdx[2], cdy[2];
-    bool con[2], corg[2], cfirst[2];
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const int c = lane + 32 * j, p = c % 6;
-        con[j] = c < ncand;
-        ck[j] = con[j] ? c / 6 : 0;
-        corg[j] = p == 0;
-        cdx[j] = (p == 3) - (p == 5);
-        cdy[j] = (p == 4) - (p == 2);
-        cfirst[j] = c < 6;
-    }
-    const int tri = nref * (nref + 1) / 2;
+    WalkLane wl;
+    wl.init(lane, 6 * nref);
     long long cmp_total = 0;
     int mvpx = 0, mvpy = 0;   // mv_field = {(0,0): [0,0]}  (PFrame.py:34); carried from block to block
     prefetch(0, 0);
     for (int b = 0; b < a.nblk; b++) {
-        const int ox = (b % a.bw) * bs, oy = (b / a.bw) * bs;
         cp_async_wait_all();
         __syncwarp();
         if (b + 1 < a.nblk) prefetch(b + 1, (b + 1) & 1);
         const uint16_t* tab = s_map + (size_t)(b & 1) * buf_elems;
-        int mvx = 0, mvy = 0, best_sad = 0;
-        for (;;) {
-            uint32_t key = 0xffffffffu;
-            int nvalid = 0;
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                if (j == 1 && ncand <= 32) break;   // warp-uniform
-                const bool on = con[j];
-                const int k = ck[j];
-                const int cx = corg[j] ? 0 : mvpx + cdx[j];
-                const int cy = corg[j] ? 0 : mvpy + cdy[j];
-                int ph = 0, px = 0, py = 0, dx = cx, dy = cy;
-                if (a.sc == 2) { px = cx & 1; py = cy & 1; ph = px | (py << 1); dx = cx >> 1; dy = cy >> 1; }
-                const bool inmap = dx >= -R && dy >= -R && dx <= R - px && dy <= R - py;
-                int s = -1;
-                if (on && inmap) {
-                    const uint16_t v = tab[(k * a.nphase + ph) * chunk + (dy + R) * n1 + (dx + R)];
-                    s = v == 0xffffu ? -1 : (int)v;
-                }
-                // candidates outside the map: the warp evaluates them one by one (is_out_of_range block_predictor.py:116-143)
-                uint32_t need = __ballot_sync(0xffffffffu, on && !inmap);
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int kk = __shfl_sync(0xffffffffu, k, src), pp = __shfl_sync(0xffffffffu, ph, src);
-                    const int ddx = __shfl_sync(0xffffffffu, dx, src), ddy = __shfl_sync(0xffffffffu, dy, src);
-                    const int phx = pp & 1, phy = pp >> 1;
-                    const bool ok = (ox + ddx >= 0) && (oy + ddy >= 0) && (ox + ddx + bs <= a.W - phx) && (oy + ddy + bs <= a.H - phy);
-                    int t = -1;
-                    if (ok) {
-                        const uint8_t* rp = ref_base + (size_t)(L.ref_plane[kk] + pp) * ref_plane_bytes + (size_t)(oy + ddy) * ref_pitch + (ox + ddx);
-                        t = 0;
-                        for (int i = lane; i < bs * bs; i += 32) {
-                            const int y = i / bs, x = i - y * bs;
-                            t += abs((int)curp[(size_t)(oy + y) * a.cur_pitch + ox + x] - (int)rp[(size_t)y * ref_pitch + x]);
-                        }
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-                    }
-                    if (lane == src) s = t;
-                }
-                if (on && s >= 0) key = min(key, ((uint32_t)s << 8) | (uint32_t)(lane + 32 * j));
-                nvalid += __popc(__ballot_sync(0xffffffffu, on && s >= 0 && cfirst[j]));
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
-            cmp_total += (long long)(nvalid * tri);
-            const int best_p = (key == 0xffffffffu) ? 0 : (int)(key & 255u) % 6;
-            best_sad = (key == 0xffffffffu) ? 0x7fffffff : (int)(key >> 8);
-            mvx = best_p == 0 ? 0 : mvpx + (best_p == 3) - (best_p == 5);
-            mvy = best_p == 0 ? 0 : mvpy + (best_p == 4) - (best_p == 2);
-            const bool stop = (best_p <= 1) || abs(mvx) >= 16 || abs(mvy) >= 16;
-            mvpx = mvx;
-            mvpy = mvy;
-            if (stop) break;
-        }
-        if (lane == 0) a.out[(size_t)fl * a.nblk + b] = make_int4(mvx, mvy, 0, best_sad);
+        int best_sad = 0;
+        walk_block(a, L, wl, curp, ref_base, ref_plane_bytes, ref_pitch, tab, (size_t)chunk, b, lane, mvpx, mvpy, best_sad, cmp_total);
+        if (lane == 0) a.out[(size_t)fl * a.nblk + b] = make_int4(mvpx, mvpy, 0, best_sad);
         __syncwarp();   // everyone is done with this block's table before the prefetch after next overwrites it
     }
     if (lane == 0 && cmp_out) cmp_out[fl] = cmp_total;
+}
+
+// ---- transfer-table path ---------------------------------------------------------------------------------------
+// Predictors and vectors with components within +-16 are numbered q = (y + 16) * 33 + (x + 16).  tables[lane][block][q]
+// (uint16) = the q of the vector the block's walk returns when it starts from predictor q; 0xFFFF for the border predictors
+// (a component of +-16), whose first level would look outside the SAD map: those are walked on the spot, as are predictors
+// that have drifted further out.
+constexpr int FT_S = 15;                      // tabulated predictors: components within +-FT_S
+constexpr int FT_P = 2 * (FT_S + 1) + 1;      // 33 positions per axis
+constexpr int FT_Q = FT_P * FT_P;             // 1089
+constexpr int FT_STRIDE = 1096;               // entries per block, 2192 B = 137 x 16 B
+constexpr int FT_CENTER = (FT_S + 1) * FT_P + (FT_S + 1);
+constexpr int FT_THREADS = 256;
+constexpr uint16_t FT_STOP = 1u << 12, FT_NONE = 0xffffu;
+__device__ __forceinline__ int ft_q(int x, int y) { return (y + FT_S + 1) * FT_P + (x + FT_S + 1); }
+__device__ __forceinline__ int ft_x(int q) { return q % FT_P - (FT_S + 1); }
+__device__ __forceinline__ int ft_y(int q) { return q / FT_P - (FT_S + 1); }
+// per-block predictor record written by the chain kernel: q, or bit 31 | (x + 16384) | (y + 16384) << 15 outside the grid
+__device__ __forceinline__ uint32_t ft_far(int x, int y) { return 0x80000000u | (uint32_t)(x + 16384) | ((uint32_t)(y + 16384) << 15); }
+__device__ __forceinline__ void ft_unpack(uint32_t e, int& x, int& y) {
+    if (e & 0x80000000u) { x = (int)(e & 32767u) - 16384; y = (int)((e >> 15) & 32767u) - 16384; }
+    else { x = ft_x((int)e); y = ft_y((int)e); }
+}
+
+// grid = (nblk, lanes).  Phase 1: for every MV position within +-16 the best (SAD, reference) over the references -- the
+// first strict minimum over (reference ascending, key order) is the lexicographic minimum of (SAD, reference, key), so the
+// references can be reduced per position first.  Phase 2: one level from every predictor (origin + 5 positions).
+// Phase 3: follow the step pointers to the fixed point.
+__global__ void __launch_bounds__(FT_THREADS) fastme_table_kernel(MeArgs a, uint16_t* tables) {
+    __shared__ uint32_t s_best[FT_STRIDE];     // (SAD << 8 | reference) of every position, 0xffffffff = leaves the plane
+    __shared__ uint16_t s_step[FT_Q];          // q of the next predictor | FT_STOP
+    const int b = blockIdx.x, fl = blockIdx.y, tid = threadIdx.x;
+    const MeLane& L = a.lanes[fl];
+    const int nref = L.nref, R = a.R, n1 = 2 * R + 1, chunk = a.map_stride, nphase = a.nphase;
+    const size_t kp_stride = (size_t)a.nblk * chunk;
+    const uint16_t* src = a.sad_map + (size_t)fl * a.max_refs * nphase * kp_stride + (size_t)b * chunk;
+    if (a.sc == 1 && chunk == FT_STRIDE) {
+        // integer-pel: the map of a reference *is* the position grid (n1 = 33); 8 positions per 16-byte load, all
+        // references requested before the first one is used
+        for (int v = tid; v < FT_STRIDE / 8; v += FT_THREADS) {
+            uint4 m[BVC_MAX_REFS];
+#pragma unroll
+            for (int k = 0; k < BVC_MAX_REFS; k++)
+                if (k < nref) m[k] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)k * kp_stride) + v);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t best = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < BVC_MAX_REFS; k++) {
+                    if (k < nref) {
+                        const uint32_t w = j < 2 ? m[k].x : j < 4 ? m[k].y : j < 6 ? m[k].z : m[k].w;
+                        const uint32_t val = (j & 1) ? w >> 16 : w & 0xffffu;
+                        if (val != 0xffffu) best = min(best, (val << 8) | (uint32_t)k);
+                    }
+                }
+                s_best[8 * v + j] = best;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int q = tid; q < FT_Q; q += FT_THREADS) {
+            const int cy = ft_y(q), cx = ft_x(q);
+            int ph = 0, dx = cx, dy = cy;
+            if (a.sc == 2) { ph = (cx & 1) | ((cy & 1) << 1); dx = cx >> 1; dy = cy >> 1; }
+            const uint16_t* pos = src + (size_t)ph * kp_stride + (dy + R) * n1 + (dx + R);   // always inside the map
+            uint32_t val[BVC_MAX_REFS];
+#pragma unroll
+            for (int k = 0; k < BVC_MAX_REFS; k++)
+                if (k < nref) val[k] = __ldg(pos + (size_t)k * nphase * kp_stride);
+            uint32_t best = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < BVC_MAX_REFS; k++)
+                if (k < nref && val[k] != 0xffffu) best = min(best, (val[k] << 8) | (uint32_t)k);
+            s_best[q] = best;
+        }
+    }
+    __syncthreads();
+    const uint32_t korg = s_best[FT_CENTER];
+    for (int q = tid; q < FT_Q; q += FT_THREADS) {
+        const int py0 = ft_y(q), px0 = ft_x(q);
+        if (abs(px0) > FT_S || abs(py0) > FT_S) { s_step[q] = FT_NONE; continue; }
+        // key = (SAD, reference, key index); an invalid position stays above every valid one
+        auto mk = [](uint32_t v, uint32_t p) { return v == 0xffffffffu ? v : (v << 3) | p; };   // v < 2^24
+        uint32_t key = mk(korg, 0);
+        key = min(key, mk(s_best[q], 1));
+        key = min(key, mk(s_best[q - FT_P], 2));
+        key = min(key, mk(s_best[q + 1], 3));
+        key = min(key, mk(s_best[q + FT_P], 4));
+        key = min(key, mk(s_best[q - 1], 5));
+        const int best_p = (key == 0xffffffffu) ? 0 : (int)(key & 7u);
+        const int mvx = best_p == 0 ? 0 : px0 + (best_p == 3) - (best_p == 5);
+        const int mvy = best_p == 0 ? 0 : py0 + (best_p == 4) - (best_p == 2);
+        const bool stop = (best_p <= 1) || abs(mvx) >= 16 || abs(mvy) >= 16;
+        s_step[q] = (uint16_t)(ft_q(mvx, mvy) | (stop ? FT_STOP : 0));
+    }
+    __syncthreads();
+    // follow the step pointers to the fixed point (every move lowers (SAD, reference), so there are no cycles; a move
+    // that does not stop lands on a tabulated predictor)
+    uint16_t* out = tables + ((size_t)fl * a.nblk + b) * FT_STRIDE;
+    for (int q = tid; q < FT_Q; q += FT_THREADS) {
+        uint16_t e = s_step[q];
+        if (e != FT_NONE) {
+            for (int guard = 0; !(e & FT_STOP) && guard < FT_Q; guard++) e = s_step[e];
+            e &= FT_STOP - 1;
+        }
+        out[q] = e;
+    }
+}
+
+// grid = lanes, FC_THREADS threads: mvp_in[lane][b] = predictor of block b (q, or ft_far()).
+// Warps 1.. stage the tables of FC_BATCH blocks at a time (cp.async, FC_NBUF buffers); warp 0 walks the batches: one
+// dependent shared-memory look-up per block.  Warp 0 issues no copies: behind a full load/store queue its own cp.async
+// instructions would hold the walk back until the batch has been requested (profiles/microbench/chain_probe.cu:
+// fetch 15.6 us + walk 18.8 us per CIF frame add up to 32 us when warp 0 copies too).
+constexpr int FC_THREADS = 160, FC_BATCH = 16, FC_NBUF = 4;
+__global__ void __launch_bounds__(FC_THREADS) fastme_chain_kernel(MeArgs a, const uint8_t* ref_base, size_t ref_plane_bytes,
+                                                                int ref_pitch, const uint16_t* tables, uint32_t* mvp_in) {
+    extern __shared__ __align__(16) uint16_t s_tab[];   // [FC_NBUF][FC_BATCH][FT_STRIDE]
+    const int tid = threadIdx.x, lane = tid & 31, fl = blockIdx.x;
+    const MeLane& L = a.lanes[fl];
+    const uint8_t* curp = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
+    const uint16_t* tab_lane = tables + (size_t)fl * a.nblk * FT_STRIDE;
+    const size_t kp_stride = (size_t)a.nblk * a.map_stride;
+    const uint16_t* map_lane = a.sad_map + (size_t)fl * a.max_refs * a.nphase * kp_stride;
+    const int nbatch = (a.nblk + FC_BATCH - 1) / FC_BATCH;
+    auto prefetch = [&](int bt) {
+        if (bt < nbatch) {
+            const int nb = min(FC_BATCH, a.nblk - bt * FC_BATCH);
+            const uint16_t* src = tab_lane + (size_t)bt * FC_BATCH * FT_STRIDE;
+            uint16_t* dst = s_tab + (size_t)(bt % FC_NBUF) * FC_BATCH * FT_STRIDE;
+            for (int v = tid - 32; v < nb * (FT_STRIDE / 8); v += FC_THREADS - 32) cp_async16(dst + v * 8, src + v * 8);
+        }
+        cp_async_commit();   // one group per batch, empty past the end, so the wait count below stays constant
+    };
+    WalkLane wl;
+    wl.init(lane, 6 * L.nref);
+    uint32_t* out = mvp_in + (size_t)fl * a.nblk;
+    // mv_field = {(0,0): [0,0]}  (PFrame.py:34); the running predictor lives in warp 0: q inside the grid, else (mvpx, mvpy)
+    int q = FT_CENTER, mvpx = 0, mvpy = 0;
+    bool far = false;
+    if (tid >= 32)
+        for (int bt = 0; bt < FC_NBUF - 1; bt++) prefetch(bt);
+    for (int bt = 0; bt < nbatch; bt++) {
+        if (tid >= 32) cp_async_wait<FC_NBUF - 2>();   // this thread's part of batch bt has landed
+        __syncthreads();                               // ... and everybody else's; batch bt-1 is consumed
+        if (tid >= 32) prefetch(bt + FC_NBUF - 1);     // into the buffer batch bt-1 used
+        if (tid < 32) {
+            const uint16_t* tb = s_tab + (size_t)(bt % FC_NBUF) * FC_BATCH * FT_STRIDE;
+            const int b0 = bt * FC_BATCH, nb = min(FC_BATCH, a.nblk - b0);
+            for (int i = 0; i < nb; i++, tb += FT_STRIDE) {
+                if (!far) {
+                    if (lane == 0) out[b0 + i] = (uint32_t)q;
+                    const uint16_t e = tb[q];
+                    if (e != FT_NONE) { q = e; continue; }
+                    mvpx = ft_x(q);
+                    mvpy = ft_y(q);
+                } else if (lane == 0) {
+                    out[b0 + i] = ft_far(mvpx, mvpy);
+                }
+                // border predictor or outside the grid: walk this block on the spot
+                int sad;
+                long long cmp = 0;
+                walk_block(a, L, wl, curp, ref_base, ref_plane_bytes, ref_pitch, map_lane + (size_t)(b0 + i) * a.map_stride,
+                           kp_stride, b0 + i, lane, mvpx, mvpy, sad, cmp);
+                far = abs(mvpx) > FT_S + 1 || abs(mvpy) > FT_S + 1;
+                if (!far) q = ft_q(mvpx, mvpy);
+            }
+        }
+    }
+}
+
+// one warp per (lane, block): the block's walk from its known predictor
+__global__ void __launch_bounds__(256) fastme_finish_kernel(MeArgs a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes,
+                                                          int ref_pitch, const uint32_t* mvp_in, unsigned long long* cmp_out) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (long long)lanes * a.nblk) return;
+    const int fl = (int)(w / a.nblk), b = (int)(w - (long long)fl * a.nblk);
+    const MeLane& L = a.lanes[fl];
+    const uint8_t* curp = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
+    const size_t kp_stride = (size_t)a.nblk * a.map_stride;
+    const uint16_t* map_lane = a.sad_map + (size_t)fl * a.max_refs * a.nphase * kp_stride;
+    WalkLane wl;
+    wl.init(lane, 6 * L.nref);
+    int mvpx, mvpy, sad = 0;
+    ft_unpack(mvp_in[w], mvpx, mvpy);
+    long long cmp = 0;
+    walk_block(a, L, wl, curp, ref_base, ref_plane_bytes, ref_pitch, map_lane + (size_t)b * a.map_stride, kp_stride, b, lane, mvpx, mvpy,
+               sad, cmp);
+    if (lane == 0) {
+        a.out[w] = make_int4(mvpx, mvpy, 0, sad);
+        if (cmp_out) atomicAdd(cmp_out + fl, (unsigned long long)cmp);
+    }
 }
 
 }  // namespace
@@ -230,6 +455,38 @@ cudaError_t launch_fastme_walk(const MeArgs& a, int lanes, const uint8_t* ref_ba
         configured = smem;
     }
     fastme_walk_kernel<<<lanes, 32, smem, st>>>(a, ref_base, ref_plane_bytes, ref_pitch, cmp_out);
+    return cudaGetLastError();
+}
+
+}  // namespace bvc
+
+namespace bvc {
+
+size_t fastme_table_bytes(int lanes, int nblk) {
+    // a multiple of 16 per lane, so a lane group's slice (offset = the bytes of the lanes before it) stays cp.async-aligned
+    return (size_t)lanes * ((size_t)nblk * FT_STRIDE * sizeof(uint16_t) + ((size_t)nblk * sizeof(uint32_t) + 15) / 16 * 16);
+}
+
+cudaError_t launch_fastme_table(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                                void* scratch, long long* cmp_out, cudaStream_t st) {
+    if (!a.sad_map || a.bs > 32 || a.map_stride % 8 || !scratch) return cudaErrorInvalidValue;
+    uint16_t* tables = static_cast<uint16_t*>(scratch);
+    uint32_t* mvp_in = reinterpret_cast<uint32_t*>(tables + (size_t)lanes * a.nblk * FT_STRIDE);   // FT_STRIDE even: 4-byte aligned
+    const size_t smem = (size_t)FC_NBUF * FC_BATCH * FT_STRIDE * sizeof(uint16_t);
+    static bool configured_dev[BVC_MAX_DEVICES] = {};
+    bool& configured = configured_dev[current_device_slot()];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fastme_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    fastme_table_kernel<<<dim3(a.nblk, lanes), FT_THREADS, 0, st>>>(a, tables);
+    fastme_chain_kernel<<<lanes, FC_THREADS, smem, st>>>(a, ref_base, ref_plane_bytes, ref_pitch, tables, mvp_in);
+    cudaError_t e = cmp_out ? cudaMemsetAsync(cmp_out, 0, (size_t)lanes * sizeof(long long), st) : cudaSuccess;
+    if (e != cudaSuccess) return e;
+    const long long warps = (long long)lanes * a.nblk;
+    fastme_finish_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a, lanes, ref_base, ref_plane_bytes, ref_pitch, mvp_in,
+                                                                       reinterpret_cast<unsigned long long*>(cmp_out));
     return cudaGetLastError();
 }
 

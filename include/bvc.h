@@ -149,9 +149,11 @@ int bvc_decode_frame(bvc_ctx *ctx, int intra, const uint8_t *pred, size_t pred_l
  * exclusive only then).  Default 2 (environment override: BVC_LANE_GROUPS).  The output does not depend on it. */
 int bvc_set_lane_groups(bvc_ctx *ctx, int groups);
 
-/* FastME evaluation: off (default) = the SADs of all candidates within 16 MV units of every block are computed by the
- * tiled full-search kernel and the serial predictor walk (find_fast_me_block, encoder/block_predictor.py:11-58) reads
- * them from that table; on = every candidate is evaluated when the walk reaches it.  The output does not depend on it. */
+/* FastME evaluation.  0 (default): the SADs of all candidates within 16 MV units of every block are computed by the tiled
+ * full-search kernel; the walk of every block (find_fast_me_block, encoder/block_predictor.py:11-58) is tabulated for all
+ * predictors within +-15 in parallel, so the serial predictor chain (encoder/PFrame.py:34,44,105-110) is one look-up per
+ * block.  1: every candidate is evaluated when the serial walk reaches it.  2: SAD map, serial walk reading it.
+ * The output does not depend on the setting. */
 int bvc_set_fastme_direct(bvc_ctx *ctx, int on);
 
 /* instrumentation --------------------------------------------------------------------------- */

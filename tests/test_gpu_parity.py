@@ -421,7 +421,7 @@ def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
     planes = [ob.halfpel_plane(x) for x in refs] if frac else refs
     mv_o, sad_o, cmp_o = ob.me_frame(cfg, cur, planes)
     assert np.abs(mv_o[:, 0]).max() > 16, "the case must leave the SAD map (+-16 MV units)"
-    for direct in (False, True):
+    for direct in (0, 1, 2):     # transfer tables (default), direct evaluation, serial walk on the SAD map
         with _ctx(W, H, bs, 4, 3, nref, True, frac) as ctx:
             ctx.set_fastme_direct(direct)
             mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
