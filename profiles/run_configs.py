@@ -8,6 +8,7 @@ import json
 import os
 import sys
 import time
+import zlib
 
 import numpy as np
 
@@ -26,16 +27,22 @@ WORKLOADS = {
     "c2_cif_halfpel_r4": (352, 288, 296, 16, 4, 3, 8, 1, False, True, 37, dict(step=2, clamp=16)),
     "c4_4k_r64_nref4": (3840, 2160, 512, 16, 64, 4, 8, 4, False, False, 32, dict(step=3, clamp=48)),
     "c3_1080p_r32": (1920, 1088, 600, 16, 32, 4, 30, 1, False, False, 20, dict(step=6, clamp=96)),
+    # not BASELINE configurations: FastME at the headline geometry (a chain of 8160 blocks per frame) and with half-pel
+    "x_1080p_fastme_nref4": (1920, 1088, 600, 16, 16, 4, 30, 4, True, False, 20, dict(step=6, clamp=96)),
+    "x_cif_halfpel_fastme_nref2": (352, 288, 296, 16, 4, 3, 8, 2, True, True, 37, dict(step=2, clamp=16)),
 }
+FASTME_MODE = int(os.environ.get("BVC_FASTME_MODE", "0"))   # bvc_set_fastme_direct: 0 transfer tables, 1 direct, 2 serial walk
 
 
 def run(name):
     W, H, n, bs, r, qp, ip, nref, fastme, frac, lanes, sk = WORKLOADS[name]
     t0 = time.time()
-    frames = synth.moving_clip(abs(hash(name)) % 1000 + 7, H, W, n, **sk)
+    frames = synth.moving_clip(zlib.crc32(name.encode()) % 1000 + 7, H, W, n, **sk)   # same content in every process
     tgen = time.time() - t0
     out = np.empty(n * W * H // 2 + (1 << 20), np.uint8)
     with bvc.Context(W, H, bs, r, qp, nref, fastme, frac, ip, device=0, max_lanes=lanes) as ctx:
+        if fastme:
+            ctx.set_fastme_direct(FASTME_MODE)
         ctx.encode_clip_into(frames, out)                      # warm-up
         reps = 3
         t0 = time.perf_counter()
@@ -68,6 +75,8 @@ def run(name):
             "frames": n, "lanes": lanes, "e2e_frames_per_s": n / dt, "ms_per_clip": dt * 1e3, "device_ms": clip_ms,
             "kernel_ms": {k: v[0] for k, v in kt.items()}, "kernel_launches": {k: v[1] for k, v in kt.items()},
             "bitstream_bytes": ln, "oracle_gops_checked": checked, "oracle_check_s": t_oracle, "synth_s": tgen}
+    if fastme:
+        line["fastme_mode"] = FASTME_MODE
     if not fastme and kt["me"][0] > 0:
         line["me_px_absdiff_per_frame_1ref"] = work
     print(json.dumps(line), flush=True)
