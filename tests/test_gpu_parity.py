@@ -377,6 +377,25 @@ def test_lane_groups_do_not_change_the_stream():
             ctx.set_lane_groups(5)
 
 
+@pytest.mark.parametrize("frac,nref", [(False, 3), (True, 2)])
+def test_fastme_clip_with_lane_groups_and_modes(frac, nref):
+    """FastME through the clip call: 15 blocks per frame (an odd count: the per-group slices of the transfer-table scratch
+    must stay 16-byte aligned), 1..3 lane groups running on their own streams, all three evaluation modes: same bytes as
+    the oracle."""
+    ob = _ob()
+    H, W, bs, qp, ip, n = 48, 80, 16, 3, 4, 23
+    frames = synth.moving_clip(33, H, W, n, step=5, clamp=24, blur=5)
+    cfg = ob.make_config(W, H, bs, 4, qp, nref=nref, fastme=True, frac=frac, i_period=ip)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    for lanes, groups, mode in ((6, 1, 0), (6, 2, 0), (5, 3, 0), (6, 2, 2), (3, 2, 1)):
+        with _ctx(W, H, bs, 4, qp, nref, True, frac, ip, lanes=lanes) as ctx:
+            ctx.set_lane_groups(groups)
+            ctx.set_fastme_direct(mode)
+            data, recon = ctx.encode_clip(frames, want_recon=True)
+        assert data == want, f"lanes={lanes} groups={groups} mode={mode}"
+        assert np.array_equal(recon, want_recon)
+
+
 def test_i420_input_stage_pads_and_skips_chroma(tmp_path):
     """bvc_clip_upload_i420: luma planes straight from an I420 file image, padded with 128 on the device, encode to the
     same stream as the oracle fed with pad_frame()'d Y planes; aligned sizes take the single strided copy."""
