@@ -326,7 +326,8 @@ class Context:
 
     def set_fastme_direct(self, on):
         """FastME evaluation (bvc_set_fastme_direct): 0 / False (default) = SAD map + transfer tables, 1 / True = every
-        candidate evaluated directly, 2 = SAD map + serial walk.  The output does not depend on it."""
+        candidate evaluated directly, 2 = SAD map + serial walk, 3 = serial walk over TMA-staged windows (no SAD map).  The
+        output does not depend on it."""
         self._check(self._L.bvc_set_fastme_direct(self._h, int(on)))
 
     def launch_count(self):

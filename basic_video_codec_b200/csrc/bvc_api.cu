@@ -60,6 +60,8 @@ struct bvc_ctx {
     size_t ref_planes = 0;
     CUtensorMap ref_map{};
     bool have_map = false;
+    CUtensorMap fw_map{};     // FastME window walk: box = fastme_window_box()
+    bool have_fw_map = false;
 
     int4* d_mv = nullptr;
     int32_t *d_modes = nullptr, *d_isad = nullptr, *d_qp_rows = nullptr, *d_blk_nbits = nullptr;
@@ -149,22 +151,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_ref_map(bvc_ctx* c) {
-    c->have_map = false;
-    // FastME: the tiled kernel fills the SAD map of radius 16 MV units (launch_fastme_any); its TMA box is sized for that
-    const int R = c->p.fast_me ? (c->p.frac_me ? 8 : 16) : c->p.search_range;
-    if (c->p.fast_me && !me_can_map(c->g.bs, R)) return BVC_OK;
-    MeTileCfg cfg = me_tile_config(c->g.bs, R);
-    if (!cfg.tiled) return BVC_OK;
+static int encode_map(bvc_ctx* c, CUtensorMap* out, int box_w, int box_h) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, BVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t)c->g.W, (cuuint64_t)c->g.H, (cuuint64_t)c->ref_planes};
     cuuint64_t strides[2] = {(cuuint64_t)c->g.pitch, (cuuint64_t)c->g.plane_bytes};
-    cuuint32_t box[3] = {(cuuint32_t)cfg.win_pitch, (cuuint32_t)cfg.rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ((EncodeTiledFn)fn)(&c->ref_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->ref_pool, dims, strides, box, estr,
+    CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->ref_pool, dims, strides, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -172,6 +168,26 @@ static int make_ref_map(bvc_ctx* c) {
         snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
         return fail(c, BVC_ERR_CUDA, b);
     }
+    return BVC_OK;
+}
+
+static int make_ref_map(bvc_ctx* c) {
+    c->have_map = false;
+    c->have_fw_map = false;
+    if (c->p.fast_me && c->g.bs % 4 == 0 && c->g.bs <= 32) {
+        int bw = 0, bh = 0;
+        fastme_window_box(c->g.bs, &bw, &bh);
+        int rc = encode_map(c, &c->fw_map, bw, bh);
+        if (rc != BVC_OK) return rc;
+        c->have_fw_map = true;
+    }
+    // FastME: the tiled kernel fills the SAD map of radius 16 MV units (launch_fastme_any); its TMA box is sized for that
+    const int R = c->p.fast_me ? (c->p.frac_me ? 8 : 16) : c->p.search_range;
+    if (c->p.fast_me && !me_can_map(c->g.bs, R)) return BVC_OK;
+    MeTileCfg cfg = me_tile_config(c->g.bs, R);
+    if (!cfg.tiled) return BVC_OK;
+    int rc = encode_map(c, &c->ref_map, cfg.win_pitch, cfg.rows);
+    if (rc != BVC_OK) return rc;
     c->have_map = true;
     return BVC_OK;
 }
@@ -328,7 +344,7 @@ extern "C" int bvc_set_lane_groups(bvc_ctx* c, int groups) {
 
 extern "C" int bvc_set_fastme_direct(bvc_ctx* c, int on) {
     if (!c) return BVC_ERR_INVALID;
-    c->fastme_direct = on == 2 ? 2 : (on ? 1 : 0);
+    c->fastme_direct = (on == 2 || on == 3) ? on : (on ? 1 : 0);
     return BVC_OK;
 }
 
@@ -423,6 +439,21 @@ struct StepPlan {
 static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cudaStream_t st) {
     const Geom& g = c->g;
     const int Rm = c->p.frac_me ? 8 : 16;   // 16 MV units around the block: where the walk can look before it stops
+    auto scratch_for = [&](size_t total, size_t offset, char** out) -> int {
+        if (total + 256 > c->fastme_tab.cap) {
+            if (c->fastme_tab.p) CK(cudaFree(c->fastme_tab.p));
+            c->fastme_tab.p = nullptr; c->fastme_tab.cap = 0;
+            CK(cudaMalloc(&c->fastme_tab.p, total + 256));
+            c->fastme_tab.cap = total + 256;
+        }
+        // lane groups run concurrently on their own streams: each gets its own slice of the scratch
+        *out = static_cast<char*>(c->fastme_tab.p) + offset;
+        return BVC_OK;
+    };
+    if (c->fastme_direct == 3 && c->have_fw_map && fastme_window_smem(m, c->p.nref_frames) <= 200 * 1024) {
+        CK(launch_fastme_window(&c->fw_map, m, nl, c->p.nref_frames, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
+        return BVC_OK;
+    }
     if (c->fastme_direct != 1 && c->have_map && me_can_map(g.bs, Rm)) {
         const size_t n1 = 2 * (size_t)Rm + 1;
         const size_t stride = (n1 * n1 + 7) / 8 * 8;   // 16-byte multiples: the walk stages a block's table with cp.async
@@ -447,15 +478,9 @@ static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cud
             c->launches += 1;
             return BVC_OK;
         }
-        const size_t tneed = fastme_table_bytes(c->max_lanes, g.nblk);
-        if (tneed > c->fastme_tab.cap) {
-            if (c->fastme_tab.p) CK(cudaFree(c->fastme_tab.p));
-            c->fastme_tab.p = nullptr; c->fastme_tab.cap = 0;
-            CK(cudaMalloc(&c->fastme_tab.p, tneed));
-            c->fastme_tab.cap = tneed;
-        }
-        // lane groups run concurrently on their own streams: each gets its own slice of the scratch
-        char* scratch = static_cast<char*>(c->fastme_tab.p) + fastme_table_bytes((int)L0, g.nblk);
+        char* scratch = nullptr;
+        int rc = scratch_for(fastme_table_bytes(c->max_lanes, g.nblk), fastme_table_bytes((int)L0, g.nblk), &scratch);
+        if (rc != BVC_OK) return rc;
         CK(launch_fastme_table(mm, nl, c->ref_pool, g.plane_bytes, g.pitch, scratch, c->d_cmp + L0, st));
         c->launches += 3;
         return BVC_OK;

@@ -434,6 +434,190 @@ __global__ void __launch_bounds__(256) fastme_finish_kernel(MeArgs a, int lanes,
     }
 }
 
+// ---- window walk (no SAD map) -------------------------------------------------------------------------------------------
+// The SAD map costs as much as a full search of +-16 although a walk touches a few dozen positions, and the first direct
+// kernel above pays an L2 round trip per candidate and a CTA-wide barrier pair per level.  Here the serial chain stays,
+// but everything a level needs is in shared memory when the walk reaches the block: NS-1 blocks ahead, one thread asks
+// the TMA unit for the block's reference windows (every reference and phase plane, 16 pixels around the block -- where
+// the candidates of a predictor within +-16 lie; rows and columns outside the plane are zero-filled and never read by a
+// valid candidate) and warp 0 copies its current pixels with cp.async, so the fetch costs a handful of instructions
+// instead of a CTA's worth of address arithmetic.  The 6 x nRef candidates of a level are dealt to up to 12 warps (16x16:
+// one lane per half row, two VABSDIFF4 on funnel-shifted shared-memory words, redux.sync for the sum); after one barrier
+// every warp reduces the keys with redux.sync.  What bounds a level is the dependent instruction chain of a warp
+// (~5 cycles per instruction with one warp per scheduler) against the issue slots all warps spend on the same control
+// flow: one warp per reference (6 candidates each) measured 2.3 us per block, 24 warps with copies issued by every thread
+// 2.1 us (profiles/r1_experiments.md).  Candidates outside the window (predictor drifted past 16) read global memory.
+// One CTA per frame; lanes run in parallel.
+constexpr int FW_PITCH = 64, FW_MARGIN = 16, FW_WARPS = 12;
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// candidate outside the staged window (predictor drifted past 16): 16x16 SAD straight from the plane.  Rare: kept out of line.
+__device__ __noinline__ int fw_sad16_global(const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch, int plane, int y, int x,
+                                            uint32_t c0, uint32_t c1) {
+    const uint8_t* pp = ref_base + (size_t)plane * ref_plane_bytes + (size_t)y * ref_pitch + x;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(pp) & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(pp - (sh >> 3));
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = sh ? __ldg(q + 2) : 0u;   // q[2] only when it holds pixels of the block
+    return (int)sad4(__funnelshift_r(w1, w2, sh), c1, sad4(__funnelshift_r(w0, w1, sh), c0, 0u));
+}
+
+template <bool BS16, int NS>   // NS: blocks in flight (ring of window slots): the fetch latency is several block walks long
+__global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __grid_constant__ CUtensorMap win_map, MeArgs a,
+                                                                         const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                                                                         long long* cmp_out) {
+    extern __shared__ __align__(128) uint8_t s_win[];   // [NS][max_refs * nphase][rows][FW_PITCH] | 16 | cur [NS][bs * bs]
+    __shared__ uint64_t bars[NS];
+    __shared__ int s_sad[2][FM_MAXC];
+    __shared__ int s_plane[BVC_MAX_REFS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fl = blockIdx.x;
+    const int bs = a.bs, rows = bs + 2 * FW_MARGIN, nphase = a.nphase;
+    const int nref = a.lanes[fl].nref, ncand = 6 * nref, tri = nref * (nref + 1) / 2, nkp = nref * nphase;
+    const int win_bytes = rows * FW_PITCH, slot_bytes = a.max_refs * nphase * win_bytes;
+    uint8_t* s_cur = s_win + NS * slot_bytes + 16;
+    const uint8_t* curp = a.cur_base + (size_t)a.lanes[fl].cur_plane * a.cur_plane_bytes;
+    if (tid < BVC_MAX_REFS) s_plane[tid] = a.lanes[fl].ref_plane[tid];
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    int pox = 0, poy = 0, pbx = 0, pb = 0;   // the block the next prefetch is for (warp 0)
+    auto prefetch = [&]() {
+        if (warp == 0) {
+            if (pb < a.nblk) {
+                const int slot = pb % NS;
+                if (lane == 0) {
+                    uint8_t* dst = s_win + slot * slot_bytes;
+                    mbar_arrive_expect_tx(&bars[slot], (uint32_t)(nkp * win_bytes));
+                    const int x0 = (pox - FW_MARGIN) & ~15, y0 = poy - FW_MARGIN;
+                    for (int kp = 0; kp < nkp; kp++) {
+                        const int k = nphase == 4 ? kp >> 2 : kp, ph = nphase == 4 ? kp & 3 : 0;
+                        tma_load_3d(dst + kp * win_bytes, &win_map, &bars[slot], x0, y0, s_plane[k] + ph);
+                    }
+                }
+                uint8_t* dc = s_cur + slot * bs * bs;
+                const uint8_t* sc = curp + (size_t)poy * a.cur_pitch + pox;
+                for (int i = lane; i < bs * bs / 4; i += 32) {
+                    const int y = (4 * i) / bs, xx = 4 * i - y * bs;
+                    cp_async4(dc + 4 * i, sc + (size_t)y * a.cur_pitch + xx);
+                }
+                pb++;
+                pox += bs;
+                if (++pbx == a.bw) { pbx = 0; pox = 0; poy += bs; }
+            }
+            cp_async_commit();   // one group per block, empty past the end, so the wait count below stays constant
+        }
+    };
+    // this warp's candidates c = warp + nwarps * j: reference k, key p -> offsets from the predictor
+    constexpr int MAXJ = (FM_MAXC + FW_WARPS - 1) / FW_WARPS;   // candidates per warp (one reference: 6 candidates, 6 warps)
+    const int nwarps = blockDim.x >> 5;
+    int cwin[MAXJ], cdx[MAXJ], cdy[MAXJ], cpl[MAXJ];
+    bool corg[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; j++) {
+        const int c = warp + nwarps * j, k = c / 6, p = c - 6 * k;
+        cwin[j] = k * nphase * win_bytes;
+        corg[j] = p == 0;
+        cdx[j] = (p == 3) - (p == 5);
+        cdy[j] = (p == 4) - (p == 2);
+        cpl[j] = c < ncand ? s_plane[k] : 0;
+    }
+    const int lrow = lane >> 1, lcol = 8 * (lane & 1);
+    const bool frac = a.sc == 2;
+    const int wmax = a.W - bs, hmax = a.H - bs;
+    long long cmp_total = 0;
+    int mvpx = 0, mvpy = 0;   // mv_field = {(0,0): [0,0]}  (PFrame.py:34); every thread carries the same values
+    int par = 0;
+    for (int b = 0; b < NS - 1; b++) prefetch();
+    int ox = 0, oy = 0, bx = 0;
+    for (int b = 0; b < a.nblk; b++) {
+        if (warp == 0) cp_async_wait<NS - 2>();   // block b's current pixels (copied by this warp)
+        __syncthreads();                          // ... visible to everyone; everybody is done with block b-1's slot
+        prefetch();                               // block b + NS - 1, into that slot
+        mbar_wait(&bars[b % NS], (uint32_t)(b / NS) & 1u);   // block b's windows have landed
+        const int wx = ox - ((ox - FW_MARGIN) & ~15);   // window column of the block's own position
+        const uint8_t* win = s_win + (b % NS) * slot_bytes;
+        const uint8_t* cur = s_cur + (b % NS) * bs * bs;
+        uint2 cw = make_uint2(0u, 0u);
+        if (BS16) cw = *reinterpret_cast<const uint2*>(cur + 16 * lrow + lcol);
+        int cbase[MAXJ];   // window offset of this lane's 8 pixels for a zero displacement
+#pragma unroll
+        for (int j = 0; j < MAXJ; j++) cbase[j] = cwin[j] + (FW_MARGIN + lrow) * FW_PITCH + wx + lcol;
+        int best_sad = 0;
+        for (;;) {
+#pragma unroll
+            for (int j = 0; j < MAXJ; j++) {
+                const int c = warp + nwarps * j;
+                if (c >= ncand) break;
+                const int cx = corg[j] ? 0 : mvpx + cdx[j];
+                const int cy = corg[j] ? 0 : mvpy + cdy[j];
+                int ph = 0, phx = 0, phy = 0, dx = cx, dy = cy;
+                if (frac) { phx = cx & 1; phy = cy & 1; ph = phx | (phy << 1); dx = cx >> 1; dy = cy >> 1; }
+                // is_out_of_range (block_predictor.py:116-143), expressed on the phase plane
+                const bool ok = (ox + dx >= 0) && (oy + dy >= 0) && (ox + dx <= wmax - phx) && (oy + dy <= hmax - phy);
+                const bool inwin = (unsigned)(dx + FW_MARGIN) <= 2u * FW_MARGIN && (unsigned)(dy + FW_MARGIN) <= 2u * FW_MARGIN;
+                int s = -1;
+                if (BS16) {
+                    if (ok) {
+                        int t;
+                        if (inwin) {
+                            const int off = cbase[j] + ph * win_bytes + dy * FW_PITCH + dx;
+                            const uint32_t sh = (uint32_t)(off & 3) * 8u;
+                            const uint32_t* q = reinterpret_cast<const uint32_t*>(win + (off & ~3));
+                            // q[2] may be the next row / the pad: shifted out when sh == 0
+                            t = (int)sad4(__funnelshift_r(q[1], q[2], sh), cw.y, sad4(__funnelshift_r(q[0], q[1], sh), cw.x, 0u));
+                        } else {
+                            t = fw_sad16_global(ref_base, ref_plane_bytes, ref_pitch, cpl[j] + ph, oy + dy + lrow, ox + dx + lcol, cw.x, cw.y);
+                        }
+                        s = (int)__reduce_add_sync(0xffffffffu, (unsigned)t);
+                    }
+                } else if (ok) {
+                    const uint8_t* rp = inwin ? win + cwin[j] + ph * win_bytes + (dy + FW_MARGIN) * FW_PITCH + wx + dx
+                                              : ref_base + (size_t)(cpl[j] + ph) * ref_plane_bytes + (size_t)(oy + dy) * ref_pitch + (ox + dx);
+                    const int rpitch = inwin ? FW_PITCH : ref_pitch;
+                    int t = 0;
+                    for (int i = lane; i < bs * bs; i += 32) {
+                        const int y = i / bs, x = i - y * bs;
+                        t += abs((int)cur[i] - (int)rp[(size_t)y * rpitch + x]);
+                    }
+                    s = (int)__reduce_add_sync(0xffffffffu, (unsigned)t);
+                }
+                if (lane == 0) s_sad[par][c] = s;
+            }
+            __syncthreads();
+            // first strict minimum in (reference ascending, key order): lane c holds candidate c (and c + 32)
+            uint32_t key = 0xffffffffu;
+            bool v0 = false;
+            if (lane < ncand) {
+                const int s = s_sad[par][lane];
+                if (s >= 0) { key = ((uint32_t)s << 8) | (uint32_t)lane; v0 = lane < 6; }
+            }
+            if (lane + 32 < ncand) {
+                const int s = s_sad[par][lane + 32];
+                if (s >= 0) key = min(key, ((uint32_t)s << 8) | (uint32_t)(lane + 32));
+            }
+            key = __reduce_min_sync(0xffffffffu, key);
+            const int nvalid = __popc(__ballot_sync(0xffffffffu, v0));
+            par ^= 1;
+            cmp_total += (long long)(nvalid * tri);
+            const int best_p = (key == 0xffffffffu) ? 0 : (int)(key & 255u) % 6;
+            best_sad = (key == 0xffffffffu) ? 0x7fffffff : (int)(key >> 8);
+            const int mvx = best_p == 0 ? 0 : mvpx + (best_p == 3) - (best_p == 5);
+            const int mvy = best_p == 0 ? 0 : mvpy + (best_p == 4) - (best_p == 2);
+            const bool stop = (best_p <= 1) || abs(mvx) >= 16 || abs(mvy) >= 16;
+            mvpx = mvx;
+            mvpy = mvy;
+            if (stop) break;
+        }
+        if (tid == 0) a.out[(size_t)fl * a.nblk + b] = make_int4(mvpx, mvpy, 0, best_sad);
+        ox += bs;
+        if (++bx == a.bw) { bx = 0; ox = 0; oy += bs; }
+    }
+    if (tid == 0 && cmp_out) cmp_out[fl] = cmp_total;
+}
+
 }  // namespace
 
 cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
@@ -488,6 +672,43 @@ cudaError_t launch_fastme_table(const MeArgs& a, int lanes, const uint8_t* ref_b
     fastme_finish_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(a, lanes, ref_base, ref_plane_bytes, ref_pitch, mvp_in,
                                                                        reinterpret_cast<unsigned long long*>(cmp_out));
     return cudaGetLastError();
+}
+
+static size_t fw_smem(const MeArgs& a, int max_refs, int ns) {
+    const size_t slot = (size_t)max_refs * a.nphase * (a.bs + 2 * FW_MARGIN) * FW_PITCH;
+    return ns * (slot + (size_t)a.bs * a.bs) + 16;
+}
+size_t fastme_window_smem(const MeArgs& a, int max_refs) { return fw_smem(a, max_refs, 2); }
+void fastme_window_box(int bs, int* box_w, int* box_h) { *box_w = FW_PITCH; *box_h = bs + 2 * FW_MARGIN; }
+
+template <bool BS16, int NS>
+static cudaError_t launch_fw(const CUtensorMap& map, const MeArgs& a, int lanes, size_t smem, const uint8_t* ref_base, size_t ref_plane_bytes,
+                             int ref_pitch, long long* cmp_out, cudaStream_t st) {
+    static size_t configured_dev[BVC_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device_slot()];
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fastme_window_kernel<BS16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int warps = a.max_refs >= 2 ? FW_WARPS : 6;   // 6 x nRef candidates per level
+    fastme_window_kernel<BS16, NS><<<lanes, 32 * warps, smem, st>>>(map, a, ref_base, ref_plane_bytes, ref_pitch, cmp_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fastme_window(const CUtensorMap* win_map, const MeArgs& a, int lanes, int max_refs, const uint8_t* ref_base,
+                                 size_t ref_plane_bytes, int ref_pitch, long long* cmp_out, cudaStream_t st) {
+    const size_t limit = 200 * 1024;
+    if (!win_map || a.bs > 32 || a.bs % 4 || max_refs < 1 || max_refs > BVC_MAX_REFS || fw_smem(a, max_refs, 2) > limit)
+        return cudaErrorInvalidValue;
+    MeArgs aa = a;
+    aa.max_refs = max_refs;
+    const int ns = fw_smem(a, max_refs, 8) <= limit ? 8 : fw_smem(a, max_refs, 4) <= limit ? 4 : 2;
+    const size_t smem = fw_smem(a, max_refs, ns);
+#define BVC_FW(B, N) launch_fw<B, N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
+    if (a.bs == 16) return ns == 8 ? BVC_FW(true, 8) : ns == 4 ? BVC_FW(true, 4) : BVC_FW(true, 2);
+    return ns == 8 ? BVC_FW(false, 8) : ns == 4 ? BVC_FW(false, 4) : BVC_FW(false, 2);
+#undef BVC_FW
 }
 
 }  // namespace bvc

@@ -153,6 +153,8 @@ int bvc_set_lane_groups(bvc_ctx *ctx, int groups);
  * full-search kernel; the walk of every block (find_fast_me_block, encoder/block_predictor.py:11-58) is tabulated for all
  * predictors within +-15 in parallel, so the serial predictor chain (encoder/PFrame.py:34,44,105-110) is one look-up per
  * block.  1: every candidate is evaluated when the serial walk reaches it.  2: SAD map, serial walk reading it.
+ * 3: no SAD map; serial walk with the reference windows of the blocks ahead staged in shared memory by TMA (no scratch
+ * memory: the SAD map of modes 0 / 2 takes 2 * (2*16+1)^2 bytes per block and reference).
  * The output does not depend on the setting. */
 int bvc_set_fastme_direct(bvc_ctx *ctx, int on);
 

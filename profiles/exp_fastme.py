@@ -10,7 +10,7 @@ frames = synth.moving_clip(77, H, W, n, step=2, clamp=24)
 out = np.empty(n * W * H // 2 + (1 << 20), np.uint8)
 with bvc.Context(W, H, bs, 16, qp, nref, True, False, ip, device=0, max_lanes=lanes) as ctx:
     ctx.set_lane_groups(1)
-    for direct in (0, 2, 1):   # transfer tables, serial walk on the SAD map, direct evaluation
+    for direct in (0, 3, 2, 1):   # transfer tables, fixed point, serial walk on the SAD map, direct evaluation
         ctx.set_fastme_direct(direct)
         for _ in range(2):
             ctx.encode_clip_into(frames, out)

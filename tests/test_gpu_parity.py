@@ -387,13 +387,31 @@ def test_fastme_clip_with_lane_groups_and_modes(frac, nref):
     frames = synth.moving_clip(33, H, W, n, step=5, clamp=24, blur=5)
     cfg = ob.make_config(W, H, bs, 4, qp, nref=nref, fastme=True, frac=frac, i_period=ip)
     want, want_recon = ob.encode_clip(cfg, frames)
-    for lanes, groups, mode in ((6, 1, 0), (6, 2, 0), (5, 3, 0), (6, 2, 2), (3, 2, 1)):
+    for lanes, groups, mode in ((6, 1, 0), (6, 2, 0), (5, 3, 0), (6, 2, 2), (3, 2, 1), (6, 2, 3), (5, 3, 3)):
         with _ctx(W, H, bs, 4, qp, nref, True, frac, ip, lanes=lanes) as ctx:
             ctx.set_lane_groups(groups)
             ctx.set_fastme_direct(mode)
             data, recon = ctx.encode_clip(frames, want_recon=True)
         assert data == want, f"lanes={lanes} groups={groups} mode={mode}"
         assert np.array_equal(recon, want_recon)
+
+
+@pytest.mark.parametrize("H,W,bs", [(16, 16, 16), (48, 16, 16), (16, 64, 16), (8, 40, 8), (36, 36, 4)])
+def test_fastme_modes_on_degenerate_geometry(H, W, bs):
+    """A single block, a single block column / row, and block sizes below 16: every candidate but the origin leaves the
+    plane in at least one direction, the half-pel phases shrink the valid range by one more pixel; all four FastME
+    evaluation modes against the oracle."""
+    ob = _ob()
+    frames = synth.moving_clip(700 + H + W, H, W, 5, step=2, clamp=6, blur=3)
+    for frac in (False, True):
+        cfg = ob.make_config(W, H, bs, 4, 2, nref=2, fastme=True, frac=frac, i_period=5)
+        want, want_recon = ob.encode_clip(cfg, frames)
+        for mode in (0, 1, 2, 3):
+            with _ctx(W, H, bs, 4, 2, 2, True, frac, 5, lanes=1) as ctx:
+                ctx.set_fastme_direct(mode)
+                data, recon = ctx.encode_clip(frames, want_recon=True)
+            assert data == want, f"frac={frac} mode={mode}"
+            assert np.array_equal(recon, want_recon)
 
 
 def test_i420_input_stage_pads_and_skips_chroma(tmp_path):
@@ -440,7 +458,7 @@ def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
     planes = [ob.halfpel_plane(x) for x in refs] if frac else refs
     mv_o, sad_o, cmp_o = ob.me_frame(cfg, cur, planes)
     assert np.abs(mv_o[:, 0]).max() > 16, "the case must leave the SAD map (+-16 MV units)"
-    for direct in (0, 1, 2):     # transfer tables (default), direct evaluation, serial walk on the SAD map
+    for direct in (0, 1, 2, 3):  # transfer tables (default), direct evaluation, serial walk on the SAD map, fixed point
         with _ctx(W, H, bs, 4, 3, nref, True, frac) as ctx:
             ctx.set_fastme_direct(direct)
             mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
