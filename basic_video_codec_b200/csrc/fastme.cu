@@ -618,6 +618,148 @@ __global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __gr
     if (tid == 0 && cmp_out) cmp_out[fl] = cmp_total;
 }
 
+// The 16x16 specialisation of the window walk, written for a short per-warp instruction stream: the level is a dependent
+// chain (predictor -> addresses -> LDS -> 2 x VABSDIFF4 -> redux -> barrier -> LDS -> redux -> decode), and with few warps
+// per scheduler every instruction of a warp costs several cycles whether it is on that chain or not.  So: everything that
+// does not depend on the predictor is precomputed per warp or per block, the key-to-vector decode goes through two nibble
+// tables, arithmetic is 32-bit throughout, the global-memory path for candidates outside the window is out of line, and
+// the fetch is warp-specialised: the last warp only feeds the TMA unit (it joins the per-block barrier, which tells it that
+// a slot is free), the consumer warps request their own 8 current pixels of the next block one block ahead and meet at a
+// named barrier inside a level.
+template <bool FRAC, int NJ, int NS>
+__global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_constant__ CUtensorMap win_map, MeArgs a,
+                                                                const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
+                                                                long long* cmp_out) {
+    constexpr int BS = 16, ROWS = BS + 2 * FW_MARGIN, WIN = ROWS * FW_PITCH, NPH = FRAC ? 4 : 1;
+    extern __shared__ __align__(128) uint8_t s_win[];   // [NS][max_refs * NPH][ROWS][FW_PITCH] | 16
+    __shared__ uint64_t bars[NS];
+    __shared__ int s_sad[2][FM_MAXC];
+    __shared__ int s_plane[BVC_MAX_REFS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fl = blockIdx.x;
+    const int ncw = (blockDim.x >> 5) - 1;   // consumer warps; the last warp only feeds the TMA unit
+    const int nref = a.lanes[fl].nref, ncand = 6 * nref, tri = nref * (nref + 1) / 2, nkp = nref * NPH;
+    const int slot_bytes = a.max_refs * NPH * WIN;
+    if (tid < BVC_MAX_REFS) s_plane[tid] = a.lanes[fl].ref_plane[tid];
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == ncw) {
+        // ---- producer: block b's windows are requested NS-1 blocks ahead, into the slot block b-NS has left ----
+        int pox = 0, poy = 0, pbx = 0, pb = 0;
+        auto request = [&]() {
+            if (lane == 0 && pb < a.nblk) {
+                const int slot = pb & (NS - 1);
+                uint8_t* dst = s_win + slot * slot_bytes;
+                mbar_arrive_expect_tx(&bars[slot], (uint32_t)(nkp * WIN));
+                for (int kp = 0; kp < nkp; kp++)
+                    tma_load_3d(dst + kp * WIN, &win_map, &bars[slot], pox - FW_MARGIN, poy - FW_MARGIN, s_plane[FRAC ? kp >> 2 : kp] + (FRAC ? kp & 3 : 0));
+                pb++;
+                pox += BS;
+                if (++pbx == a.bw) { pbx = 0; pox = 0; poy += BS; }
+            }
+        };
+        for (int b = 0; b < NS - 1; b++) request();
+        for (int b = 0; b < a.nblk; b++) {
+            __syncthreads();   // the consumers are done with block b-1: its slot is free
+            request();
+        }
+        return;
+    }
+    // ---- consumers ----
+    // this warp's candidates c = warp + ncw * j: reference k, key p; everything that does not depend on the predictor
+    int c_[NJ], keep[NJ], sx[NJ], sy[NJ], lanebase[NJ], plane[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const int c = warp + ncw * j, k = c / 6, p = c - 6 * k;
+        c_[j] = c;
+        keep[j] = p == 0 ? 0 : -1;                 // origin ignores the predictor
+        sx[j] = (p == 3) - (p == 5);
+        sy[j] = (p == 4) - (p == 2);
+        // byte offset, inside a slot, of this lane's 8 pixels (row lane/2, half lane%2) for a zero displacement
+        lanebase[j] = k * NPH * WIN + (FW_MARGIN + (lane >> 1)) * FW_PITCH + FW_MARGIN + 8 * (lane & 1);
+        plane[j] = c < ncand ? s_plane[k] : 0;
+    }
+    const int wmax = a.W - BS, hmax = a.H - BS, ncthreads = 32 * ncw;
+    const uint32_t win0 = smem_u32(s_win);
+    // this lane's 8 current pixels of the next block, requested one block ahead
+    const uint8_t* curl = a.cur_base + (size_t)a.lanes[fl].cur_plane * a.cur_plane_bytes + (size_t)(lane >> 1) * a.cur_pitch + 8 * (lane & 1);
+    const size_t cur_row_step = (size_t)BS * a.cur_pitch;
+    uint2 cw_next = *reinterpret_cast<const uint2*>(curl);
+    long long cmp_total = 0;
+    int mvpx = 0, mvpy = 0;   // mv_field = {(0,0): [0,0]}  (PFrame.py:34); every thread carries the same values
+    int par = 0;
+    int ox = 0, oy = 0, bx = 0;
+    int4* out = a.out + (size_t)fl * a.nblk;
+    for (int b = 0; b < a.nblk; b++) {
+        const int slot = b & (NS - 1);
+        __syncthreads();                          // everybody is done with block b-1 (the producer refills its slot)
+        const uint32_t cw0 = cw_next.x, cw1 = cw_next.y;
+        if (b + 1 < a.nblk) cw_next = *reinterpret_cast<const uint2*>(bx + 1 == a.bw ? curl + cur_row_step : curl + ox + BS);
+        mbar_wait(&bars[slot], (uint32_t)(b / NS) & 1u);   // block b's windows have landed
+        const uint32_t wslot = win0 + slot * slot_bytes;
+        int best_sad = 0, cmp_blk = 0;
+        for (;;) {
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                if (c_[j] >= ncand) break;
+                const int cx = (mvpx & keep[j]) + sx[j], cy = (mvpy & keep[j]) + sy[j];
+                int phx = 0, phy = 0, dx = cx, dy = cy;
+                if (FRAC) { phx = cx & 1; phy = cy & 1; dx = cx >> 1; dy = cy >> 1; }
+                const int px = ox + dx, py = oy + dy;
+                // is_out_of_range (block_predictor.py:116-143), expressed on the phase plane
+                const bool ok = px >= 0 && py >= 0 && px <= wmax - phx && py <= hmax - phy;
+                const bool inwin = (unsigned)(dx + FW_MARGIN) <= 2u * FW_MARGIN && (unsigned)(dy + FW_MARGIN) <= 2u * FW_MARGIN;
+                int s = -1;
+                if (ok) {
+                    uint32_t t;
+                    if (inwin) {
+                        const uint32_t off = wslot + lanebase[j] + (FRAC ? (phx + 2 * phy) * WIN : 0) + dy * FW_PITCH + dx;
+                        const uint32_t sh = (off & 3u) * 8u;
+                        uint32_t w0, w1, w2;   // w2 may be the next row / the pad: shifted out when sh == 0
+                        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                                     : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(off & ~3u));
+                        t = sad4(__funnelshift_r(w1, w2, sh), cw1, sad4(__funnelshift_r(w0, w1, sh), cw0, 0u));
+                    } else {
+                        t = (uint32_t)fw_sad16_global(ref_base, ref_plane_bytes, ref_pitch, plane[j] + (FRAC ? phx + 2 * phy : 0), py + (lane >> 1),
+                                                      px + 8 * (lane & 1), cw0, cw1);
+                    }
+                    s = (int)__reduce_add_sync(0xffffffffu, t);
+                }
+                if (lane == 0) s_sad[par][c_[j]] = s;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(ncthreads) : "memory");   // consumers only
+            // first strict minimum in (reference ascending, key order): lane c holds candidate c (and c + 32)
+            uint32_t key = 0xffffffffu;
+            bool v0 = false;
+            if (lane < ncand) {
+                const int s = s_sad[par][lane];
+                if (s >= 0) { key = ((uint32_t)s << 8) | (uint32_t)lane; v0 = lane < 6; }
+            }
+            if (NJ > 2 && lane + 32 < ncand) {   // more than 32 candidates: more than 5 references
+                const int s = s_sad[par][lane + 32];
+                if (s >= 0) key = min(key, ((uint32_t)s << 8) | (uint32_t)(lane + 32));
+            }
+            key = __reduce_min_sync(0xffffffffu, key);
+            cmp_blk += __popc(__ballot_sync(0xffffffffu, v0)) * tri;
+            par ^= 1;
+            // key -> vector: p = candidate % 6; offsets from two nibble tables (origin, pmv, top, right, bottom, left)
+            const uint32_t c = key & 255u, p = key == 0xffffffffu ? 0u : c - 6u * ((c * 43u) >> 8);
+            best_sad = key == 0xffffffffu ? 0x7fffffff : (int)(key >> 8);
+            const int ddx = (int)((0x012111u >> (4u * p)) & 15u) - 1, ddy = (int)((0x121011u >> (4u * p)) & 15u) - 1;
+            mvpx = (p ? mvpx : 0) + ddx;
+            mvpy = (p ? mvpy : 0) + ddy;
+            if (p <= 1u || abs(mvpx) >= 16 || abs(mvpy) >= 16) break;
+        }
+        cmp_total += cmp_blk;
+        if (tid == 0) out[b] = make_int4(mvpx, mvpy, 0, best_sad);
+        ox += BS;
+        if (++bx == a.bw) { bx = 0; ox = 0; oy += BS; curl += cur_row_step; }
+    }
+    if (tid == 0 && cmp_out) cmp_out[fl] = cmp_total;
+}
+
 }  // namespace
 
 cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
@@ -696,6 +838,21 @@ static cudaError_t launch_fw(const CUtensorMap& map, const MeArgs& a, int lanes,
     return cudaGetLastError();
 }
 
+template <bool FRAC, int NJ, int NS>
+static cudaError_t launch_fw16(const CUtensorMap& map, const MeArgs& a, int lanes, size_t smem, const uint8_t* ref_base, size_t ref_plane_bytes,
+                               int ref_pitch, long long* cmp_out, cudaStream_t st) {
+    static size_t configured_dev[BVC_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device_slot()];
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fastme_window16_kernel<FRAC, NJ, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int warps = (6 * a.max_refs + NJ - 1) / NJ + 1;   // consumer warps + the producer warp
+    fastme_window16_kernel<FRAC, NJ, NS><<<lanes, 32 * warps, smem, st>>>(map, a, ref_base, ref_plane_bytes, ref_pitch, cmp_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fastme_window(const CUtensorMap* win_map, const MeArgs& a, int lanes, int max_refs, const uint8_t* ref_base,
                                  size_t ref_plane_bytes, int ref_pitch, long long* cmp_out, cudaStream_t st) {
     const size_t limit = 200 * 1024;
@@ -705,6 +862,15 @@ cudaError_t launch_fastme_window(const CUtensorMap* win_map, const MeArgs& a, in
     aa.max_refs = max_refs;
     const int ns = fw_smem(a, max_refs, 8) <= limit ? 8 : fw_smem(a, max_refs, 4) <= limit ? 4 : 2;
     const size_t smem = fw_smem(a, max_refs, ns);
+    if (a.bs == 16 && (a.nphase == 4) == (a.sc == 2)) {
+#define BVC_FW16(F, J, N) launch_fw16<F, J, N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
+#define BVC_FW16N(F, J) (ns == 8 ? BVC_FW16(F, J, 8) : ns == 4 ? BVC_FW16(F, J, 4) : BVC_FW16(F, J, 2))
+        // at most 12 consumer warps (24 warps x 1 candidate and 12 x 2 measure the same at 4 references)
+        if (a.sc == 2) return max_refs <= 2 ? BVC_FW16N(true, 1) : max_refs <= 4 ? BVC_FW16N(true, 2) : BVC_FW16N(true, 4);
+        return max_refs <= 2 ? BVC_FW16N(false, 1) : max_refs <= 4 ? BVC_FW16N(false, 2) : BVC_FW16N(false, 4);
+#undef BVC_FW16N
+#undef BVC_FW16
+    }
 #define BVC_FW(B, N) launch_fw<B, N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
     if (a.bs == 16) return ns == 8 ? BVC_FW(true, 8) : ns == 4 ? BVC_FW(true, 4) : BVC_FW(true, 2);
     return ns == 8 ? BVC_FW(false, 8) : ns == 4 ? BVC_FW(false, 4) : BVC_FW(false, 2);
