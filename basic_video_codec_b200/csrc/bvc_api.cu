@@ -90,7 +90,8 @@ struct bvc_ctx {
     struct DBuf { void* p = nullptr; size_t cap = 0; };
     DBuf sad_map;         // FastME look-up table (uint16 [lanes][nref][phase][blk][n1*n1])
     DBuf fastme_tab;      // FastME transfer tables + per-block predictors (fastme_table_bytes)
-    int fastme_direct = 0;  // bvc_set_fastme_direct: 0 SAD map + transfer tables, 1 direct evaluation, 2 SAD map + serial walk
+    int fastme_direct = 0;  // bvc_set_fastme_direct: 0 auto (window walk / transfer tables), 1 direct evaluation, 2 SAD map + serial walk,
+                            // 3 window walk, 4 SAD map + transfer tables
     DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
         dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress;
 
@@ -151,14 +152,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_map(bvc_ctx* c, CUtensorMap* out, int box_w, int box_h) {
+static int encode_map(bvc_ctx* c, CUtensorMap* out, int box_w, int box_h, int box_d = 1) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, BVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {(cuuint64_t)c->g.W, (cuuint64_t)c->g.H, (cuuint64_t)c->ref_planes};
     cuuint64_t strides[2] = {(cuuint64_t)c->g.pitch, (cuuint64_t)c->g.plane_bytes};
-    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = ((EncodeTiledFn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->ref_pool, dims, strides, box, estr,
                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -175,9 +176,9 @@ static int make_ref_map(bvc_ctx* c) {
     c->have_map = false;
     c->have_fw_map = false;
     if (c->p.fast_me && c->g.bs % 4 == 0 && c->g.bs <= 32) {
-        int bw = 0, bh = 0;
-        fastme_window_box(c->g.bs, &bw, &bh);
-        int rc = encode_map(c, &c->fw_map, bw, bh);
+        int bw = 0, bh = 0, bd = 1;
+        fastme_window_box(c->g.bs, c->p.frac_me ? 4 : 1, &bw, &bh, &bd);
+        int rc = encode_map(c, &c->fw_map, bw, bh, bd);
         if (rc != BVC_OK) return rc;
         c->have_fw_map = true;
     }
@@ -344,7 +345,7 @@ extern "C" int bvc_set_lane_groups(bvc_ctx* c, int groups) {
 
 extern "C" int bvc_set_fastme_direct(bvc_ctx* c, int on) {
     if (!c) return BVC_ERR_INVALID;
-    c->fastme_direct = (on == 2 || on == 3) ? on : (on ? 1 : 0);
+    c->fastme_direct = (on >= 2 && on <= 4) ? on : (on ? 1 : 0);
     return BVC_OK;
 }
 
@@ -436,7 +437,7 @@ struct StepPlan {
 };
 
 // FastME for lanes [L0, L0+nl): SAD map by the tiled search kernel + table walk, or the direct kernel.
-static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cudaStream_t st) {
+static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cudaStream_t st, int step_lanes) {
     const Geom& g = c->g;
     const int Rm = c->p.frac_me ? 8 : 16;   // 16 MV units around the block: where the walk can look before it stops
     auto scratch_for = [&](size_t total, size_t offset, char** out) -> int {
@@ -450,11 +451,16 @@ static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cud
         *out = static_cast<char*>(c->fastme_tab.p) + offset;
         return BVC_OK;
     };
-    if (c->fastme_direct == 3 && c->have_fw_map && fastme_window_smem(m, c->p.nref_frames) <= 200 * 1024) {
+    // Serial walk over TMA-staged windows against SAD map + transfer tables: the walk costs ~1 us per block whatever the number
+    // of frames in flight (one CTA each), the map 20-45 ns per block and frame, so the walk wins from about 26 lanes per step.
+    const bool can_window = c->have_fw_map && fastme_window_smem(m, c->p.nref_frames) <= 200 * 1024;
+    const bool can_tables = c->have_map && me_can_map(g.bs, Rm);
+    const bool window = c->fastme_direct == 3 || (c->fastme_direct == 0 && g.bs == 16 && (step_lanes >= 26 || !can_tables));
+    if (window && can_window) {
         CK(launch_fastme_window(&c->fw_map, m, nl, c->p.nref_frames, c->ref_pool, g.plane_bytes, g.pitch, c->d_cmp + L0, st));
         return BVC_OK;
     }
-    if (c->fastme_direct != 1 && c->have_map && me_can_map(g.bs, Rm)) {
+    if (c->fastme_direct != 1 && can_tables) {
         const size_t n1 = 2 * (size_t)Rm + 1;
         const size_t stride = (n1 * n1 + 7) / 8 * 8;   // 16-byte multiples: the walk stages a block's table with cp.async
         const size_t per_lane = (size_t)c->p.nref_frames * m.nphase * g.nblk * stride;
@@ -526,7 +532,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.Rh = c->p.search_range * m.sc;
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
-            int rcf = launch_fastme_any(c, m, nl, L0, st_me);
+            int rcf = launch_fastme_any(c, m, nl, L0, st_me, sp.nl);
             if (rcf != BVC_OK) return rcf;
         } else {
             CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, st_me));
@@ -634,7 +640,7 @@ static int launch_me_lane0(bvc_ctx* c) {
     m.lanes = c->d_me_lanes; m.out = c->d_mv;
     m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
     m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
-    if (c->p.fast_me) { int rcf = launch_fastme_any(c, m, 1, 0, c->st); if (rcf != BVC_OK) return rcf; }
+    if (c->p.fast_me) { int rcf = launch_fastme_any(c, m, 1, 0, c->st, 1); if (rcf != BVC_OK) return rcf; }
     else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
     c->launches += 1;
     return BVC_OK;

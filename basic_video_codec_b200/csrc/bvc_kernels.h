@@ -62,7 +62,7 @@ cudaError_t launch_fastme_table(const MeArgs& a, int lanes, const uint8_t* ref_b
 // blocks ahead staged in shared memory while the current block is walked (one CTA per frame, one warp per reference).
 // Returns cudaErrorInvalidValue when the windows do not fit shared memory (fastme_window_smem() > 200 KB).
 size_t fastme_window_smem(const MeArgs& a, int max_refs);
-void fastme_window_box(int bs, int* box_w, int* box_h);
+void fastme_window_box(int bs, int nphase, int* box_w, int* box_h, int* box_d);
 cudaError_t launch_fastme_window(const CUtensorMap* win_map, const MeArgs& a, int lanes, int max_refs, const uint8_t* ref_base,
                                  size_t ref_plane_bytes, int ref_pitch, long long* cmp_out, cudaStream_t st);
 // true when the tiled search kernel can produce the SAD map for (block size, map radius in plane units)

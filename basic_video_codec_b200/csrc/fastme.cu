@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) fastme_finish_kernel(MeArgs a, int lanes,
 // flow: one warp per reference (6 candidates each) measured 2.3 us per block, 24 warps with copies issued by every thread
 // 2.1 us (profiles/r1_experiments.md).  Candidates outside the window (predictor drifted past 16) read global memory.
 // One CTA per frame; lanes run in parallel.
-constexpr int FW_PITCH = 64, FW_MARGIN = 16, FW_WARPS = 12;
+constexpr int FW_PITCH = 64, FW16_PITCH = 48, FW_MARGIN = 16, FW_WARPS = 12;
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -463,7 +463,8 @@ __device__ __noinline__ int fw_sad16_global(const uint8_t* ref_base, size_t ref_
     return (int)sad4(__funnelshift_r(w1, w2, sh), c1, sad4(__funnelshift_r(w0, w1, sh), c0, 0u));
 }
 
-template <bool BS16, int NS>   // NS: blocks in flight (ring of window slots): the fetch latency is several block walks long
+// Generic block sizes (4, 8, 32); 16x16 has its own kernel below.
+template <int NS>   // NS: blocks in flight (ring of window slots): the fetch latency is several block walks long
 __global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __grid_constant__ CUtensorMap win_map, MeArgs a,
                                                                          const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
                                                                          long long* cmp_out) {
@@ -524,7 +525,6 @@ __global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __gr
         cdy[j] = (p == 4) - (p == 2);
         cpl[j] = c < ncand ? s_plane[k] : 0;
     }
-    const int lrow = lane >> 1, lcol = 8 * (lane & 1);
     const bool frac = a.sc == 2;
     const int wmax = a.W - bs, hmax = a.H - bs;
     long long cmp_total = 0;
@@ -540,11 +540,6 @@ __global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __gr
         const int wx = ox - ((ox - FW_MARGIN) & ~15);   // window column of the block's own position
         const uint8_t* win = s_win + (b % NS) * slot_bytes;
         const uint8_t* cur = s_cur + (b % NS) * bs * bs;
-        uint2 cw = make_uint2(0u, 0u);
-        if (BS16) cw = *reinterpret_cast<const uint2*>(cur + 16 * lrow + lcol);
-        int cbase[MAXJ];   // window offset of this lane's 8 pixels for a zero displacement
-#pragma unroll
-        for (int j = 0; j < MAXJ; j++) cbase[j] = cwin[j] + (FW_MARGIN + lrow) * FW_PITCH + wx + lcol;
         int best_sad = 0;
         for (;;) {
 #pragma unroll
@@ -559,21 +554,7 @@ __global__ void __launch_bounds__(32 * FW_WARPS) fastme_window_kernel(const __gr
                 const bool ok = (ox + dx >= 0) && (oy + dy >= 0) && (ox + dx <= wmax - phx) && (oy + dy <= hmax - phy);
                 const bool inwin = (unsigned)(dx + FW_MARGIN) <= 2u * FW_MARGIN && (unsigned)(dy + FW_MARGIN) <= 2u * FW_MARGIN;
                 int s = -1;
-                if (BS16) {
-                    if (ok) {
-                        int t;
-                        if (inwin) {
-                            const int off = cbase[j] + ph * win_bytes + dy * FW_PITCH + dx;
-                            const uint32_t sh = (uint32_t)(off & 3) * 8u;
-                            const uint32_t* q = reinterpret_cast<const uint32_t*>(win + (off & ~3));
-                            // q[2] may be the next row / the pad: shifted out when sh == 0
-                            t = (int)sad4(__funnelshift_r(q[1], q[2], sh), cw.y, sad4(__funnelshift_r(q[0], q[1], sh), cw.x, 0u));
-                        } else {
-                            t = fw_sad16_global(ref_base, ref_plane_bytes, ref_pitch, cpl[j] + ph, oy + dy + lrow, ox + dx + lcol, cw.x, cw.y);
-                        }
-                        s = (int)__reduce_add_sync(0xffffffffu, (unsigned)t);
-                    }
-                } else if (ok) {
+                if (ok) {
                     const uint8_t* rp = inwin ? win + cwin[j] + ph * win_bytes + (dy + FW_MARGIN) * FW_PITCH + wx + dx
                                               : ref_base + (size_t)(cpl[j] + ph) * ref_plane_bytes + (size_t)(oy + dy) * ref_pitch + (ox + dx);
                     const int rpitch = inwin ? FW_PITCH : ref_pitch;
@@ -630,14 +611,16 @@ template <bool FRAC, int NJ, int NS>
 __global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_constant__ CUtensorMap win_map, MeArgs a,
                                                                 const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,
                                                                 long long* cmp_out) {
-    constexpr int BS = 16, ROWS = BS + 2 * FW_MARGIN, WIN = ROWS * FW_PITCH, NPH = FRAC ? 4 : 1;
-    extern __shared__ __align__(128) uint8_t s_win[];   // [NS][max_refs * NPH][ROWS][FW_PITCH] | 16
+    // window rows of 48 bytes (12 banks: rows r and r + 8 share banks, a 2-way conflict; the generic kernel's 64-byte rows
+    // alias every second row, 8-way)
+    constexpr int BS = 16, ROWS = BS + 2 * FW_MARGIN, PITCH = FW16_PITCH, WIN = ROWS * PITCH, NPH = FRAC ? 4 : 1;
+    extern __shared__ __align__(128) uint8_t s_win[];   // [NS][max_refs * NPH][ROWS][PITCH] | 16
     __shared__ uint64_t bars[NS];
     __shared__ int s_sad[2][FM_MAXC];
     __shared__ int s_plane[BVC_MAX_REFS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fl = blockIdx.x;
     const int ncw = (blockDim.x >> 5) - 1;   // consumer warps; the last warp only feeds the TMA unit
-    const int nref = a.lanes[fl].nref, ncand = 6 * nref, tri = nref * (nref + 1) / 2, nkp = nref * NPH;
+    const int nref = a.lanes[fl].nref, ncand = 6 * nref, tri = nref * (nref + 1) / 2;
     const int slot_bytes = a.max_refs * NPH * WIN;
     if (tid < BVC_MAX_REFS) s_plane[tid] = a.lanes[fl].ref_plane[tid];
     if (tid == 0) {
@@ -652,9 +635,9 @@ __global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_c
             if (lane == 0 && pb < a.nblk) {
                 const int slot = pb & (NS - 1);
                 uint8_t* dst = s_win + slot * slot_bytes;
-                mbar_arrive_expect_tx(&bars[slot], (uint32_t)(nkp * WIN));
-                for (int kp = 0; kp < nkp; kp++)
-                    tma_load_3d(dst + kp * WIN, &win_map, &bars[slot], pox - FW_MARGIN, poy - FW_MARGIN, s_plane[FRAC ? kp >> 2 : kp] + (FRAC ? kp & 3 : 0));
+                mbar_arrive_expect_tx(&bars[slot], (uint32_t)(nref * NPH * WIN));
+                for (int r = 0; r < nref; r++)   // the box is NPH planes deep: a reference's phase planes are consecutive
+                    tma_load_3d(dst + r * NPH * WIN, &win_map, &bars[slot], pox - FW_MARGIN, poy - FW_MARGIN, s_plane[r]);
                 pb++;
                 pox += BS;
                 if (++pbx == a.bw) { pbx = 0; pox = 0; poy += BS; }
@@ -678,7 +661,7 @@ __global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_c
         sx[j] = (p == 3) - (p == 5);
         sy[j] = (p == 4) - (p == 2);
         // byte offset, inside a slot, of this lane's 8 pixels (row lane/2, half lane%2) for a zero displacement
-        lanebase[j] = k * NPH * WIN + (FW_MARGIN + (lane >> 1)) * FW_PITCH + FW_MARGIN + 8 * (lane & 1);
+        lanebase[j] = k * NPH * WIN + (FW_MARGIN + (lane >> 1)) * PITCH + FW_MARGIN + 8 * (lane & 1);
         plane[j] = c < ncand ? s_plane[k] : 0;
     }
     const int wmax = a.W - BS, hmax = a.H - BS, ncthreads = 32 * ncw;
@@ -701,34 +684,46 @@ __global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_c
         const uint32_t wslot = win0 + slot * slot_bytes;
         int best_sad = 0, cmp_blk = 0;
         for (;;) {
+            // the candidates of a warp in phases (all loads, then all sums, then all reductions) so that their latencies overlap
+            uint32_t w0[NJ], w1[NJ], w2[NJ], sh[NJ];
+            int kind[NJ];   // 0 = leaves the plane or no candidate, 1 = in the window, 2 = outside the window
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
-                if (c_[j] >= ncand) break;
                 const int cx = (mvpx & keep[j]) + sx[j], cy = (mvpy & keep[j]) + sy[j];
                 int phx = 0, phy = 0, dx = cx, dy = cy;
                 if (FRAC) { phx = cx & 1; phy = cy & 1; dx = cx >> 1; dy = cy >> 1; }
                 const int px = ox + dx, py = oy + dy;
                 // is_out_of_range (block_predictor.py:116-143), expressed on the phase plane
-                const bool ok = px >= 0 && py >= 0 && px <= wmax - phx && py <= hmax - phy;
+                const bool ok = c_[j] < ncand && px >= 0 && py >= 0 && px <= wmax - phx && py <= hmax - phy;
                 const bool inwin = (unsigned)(dx + FW_MARGIN) <= 2u * FW_MARGIN && (unsigned)(dy + FW_MARGIN) <= 2u * FW_MARGIN;
-                int s = -1;
-                if (ok) {
-                    uint32_t t;
-                    if (inwin) {
-                        const uint32_t off = wslot + lanebase[j] + (FRAC ? (phx + 2 * phy) * WIN : 0) + dy * FW_PITCH + dx;
-                        const uint32_t sh = (off & 3u) * 8u;
-                        uint32_t w0, w1, w2;   // w2 may be the next row / the pad: shifted out when sh == 0
-                        asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
-                                     : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(off & ~3u));
-                        t = sad4(__funnelshift_r(w1, w2, sh), cw1, sad4(__funnelshift_r(w0, w1, sh), cw0, 0u));
-                    } else {
-                        t = (uint32_t)fw_sad16_global(ref_base, ref_plane_bytes, ref_pitch, plane[j] + (FRAC ? phx + 2 * phy : 0), py + (lane >> 1),
+                kind[j] = ok ? (inwin ? 1 : 2) : 0;
+                w0[j] = w1[j] = w2[j] = sh[j] = 0u;
+                if (kind[j] == 1) {
+                    const uint32_t off = wslot + lanebase[j] + (FRAC ? (phx + 2 * phy) * WIN : 0) + dy * PITCH + dx;
+                    sh[j] = (off & 3u) * 8u;
+                    // w2 may be the next row / the pad: shifted out when sh == 0
+                    asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                                 : "=r"(w0[j]), "=r"(w1[j]), "=r"(w2[j]) : "r"(off & ~3u));
+                } else if (kind[j] == 2) {
+                    w0[j] = (uint32_t)fw_sad16_global(ref_base, ref_plane_bytes, ref_pitch, plane[j] + (FRAC ? phx + 2 * phy : 0), py + (lane >> 1),
                                                       px + 8 * (lane & 1), cw0, cw1);
-                    }
-                    s = (int)__reduce_add_sync(0xffffffffu, t);
                 }
-                if (lane == 0) s_sad[par][c_[j]] = s;
             }
+            uint32_t t[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; j++)
+                t[j] = kind[j] == 1 ? sad4(__funnelshift_r(w1[j], w2[j], sh[j]), cw1, sad4(__funnelshift_r(w0[j], w1[j], sh[j]), cw0, 0u)) : w0[j];
+            // a lane's partial sum is below 2^11 and a block's SAD below 2^16: two candidates share one redux.sync
+#pragma unroll
+            for (int j = 0; j + 1 < NJ; j += 2) {
+                const uint32_t both = __reduce_add_sync(0xffffffffu, t[j] | (t[j + 1] << 16));
+                t[j] = both & 0xffffu;
+                t[j + 1] = both >> 16;
+            }
+            if (NJ & 1) t[NJ - 1] = __reduce_add_sync(0xffffffffu, t[NJ - 1]);
+#pragma unroll
+            for (int j = 0; j < NJ; j++)
+                if (lane == 0 && c_[j] < ncand) s_sad[par][c_[j]] = kind[j] ? (int)t[j] : -1;
             asm volatile("bar.sync 1, %0;" ::"r"(ncthreads) : "memory");   // consumers only
             // first strict minimum in (reference ascending, key order): lane c holds candidate c (and c + 32)
             uint32_t key = 0xffffffffu;
@@ -737,12 +732,12 @@ __global__ void __launch_bounds__(32 * 25) fastme_window16_kernel(const __grid_c
                 const int s = s_sad[par][lane];
                 if (s >= 0) { key = ((uint32_t)s << 8) | (uint32_t)lane; v0 = lane < 6; }
             }
-            if (NJ > 2 && lane + 32 < ncand) {   // more than 32 candidates: more than 5 references
+            if (NJ > 1 && lane + 32 < ncand) {   // more than 32 candidates: more than 5 references
                 const int s = s_sad[par][lane + 32];
                 if (s >= 0) key = min(key, ((uint32_t)s << 8) | (uint32_t)(lane + 32));
             }
             key = __reduce_min_sync(0xffffffffu, key);
-            cmp_blk += __popc(__ballot_sync(0xffffffffu, v0)) * tri;
+            if (warp == 0) cmp_blk += __popc(__ballot_sync(0xffffffffu, v0)) * tri;   // a statistic: only thread 0 reports it
             par ^= 1;
             // key -> vector: p = candidate % 6; offsets from two nibble tables (origin, pmv, top, right, bottom, left)
             const uint32_t c = key & 255u, p = key == 0xffffffffu ? 0u : c - 6u * ((c * 43u) >> 8);
@@ -817,24 +812,29 @@ cudaError_t launch_fastme_table(const MeArgs& a, int lanes, const uint8_t* ref_b
 }
 
 static size_t fw_smem(const MeArgs& a, int max_refs, int ns) {
+    if (a.bs == 16) return (size_t)ns * max_refs * a.nphase * (16 + 2 * FW_MARGIN) * FW16_PITCH + 16;   // fastme_window16_kernel
     const size_t slot = (size_t)max_refs * a.nphase * (a.bs + 2 * FW_MARGIN) * FW_PITCH;
     return ns * (slot + (size_t)a.bs * a.bs) + 16;
 }
 size_t fastme_window_smem(const MeArgs& a, int max_refs) { return fw_smem(a, max_refs, 2); }
-void fastme_window_box(int bs, int* box_w, int* box_h) { *box_w = FW_PITCH; *box_h = bs + 2 * FW_MARGIN; }
+void fastme_window_box(int bs, int nphase, int* box_w, int* box_h, int* box_d) {
+    *box_w = bs == 16 ? FW16_PITCH : FW_PITCH;
+    *box_h = bs + 2 * FW_MARGIN;
+    *box_d = bs == 16 ? nphase : 1;   // the 16x16 kernel fetches the phase planes of a reference with one request
+}
 
-template <bool BS16, int NS>
+template <int NS>
 static cudaError_t launch_fw(const CUtensorMap& map, const MeArgs& a, int lanes, size_t smem, const uint8_t* ref_base, size_t ref_plane_bytes,
                              int ref_pitch, long long* cmp_out, cudaStream_t st) {
     static size_t configured_dev[BVC_MAX_DEVICES] = {};
     size_t& configured = configured_dev[current_device_slot()];
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fastme_window_kernel<BS16, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(fastme_window_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const int warps = a.max_refs >= 2 ? FW_WARPS : 6;   // 6 x nRef candidates per level
-    fastme_window_kernel<BS16, NS><<<lanes, 32 * warps, smem, st>>>(map, a, ref_base, ref_plane_bytes, ref_pitch, cmp_out);
+    fastme_window_kernel<NS><<<lanes, 32 * warps, smem, st>>>(map, a, ref_base, ref_plane_bytes, ref_pitch, cmp_out);
     return cudaGetLastError();
 }
 
@@ -862,18 +862,18 @@ cudaError_t launch_fastme_window(const CUtensorMap* win_map, const MeArgs& a, in
     aa.max_refs = max_refs;
     const int ns = fw_smem(a, max_refs, 8) <= limit ? 8 : fw_smem(a, max_refs, 4) <= limit ? 4 : 2;
     const size_t smem = fw_smem(a, max_refs, ns);
-    if (a.bs == 16 && (a.nphase == 4) == (a.sc == 2)) {
+    if (a.bs == 16) {
+        if ((a.nphase == 4) != (a.sc == 2)) return cudaErrorInvalidValue;
 #define BVC_FW16(F, J, N) launch_fw16<F, J, N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
 #define BVC_FW16N(F, J) (ns == 8 ? BVC_FW16(F, J, 8) : ns == 4 ? BVC_FW16(F, J, 4) : BVC_FW16(F, J, 2))
-        // at most 12 consumer warps (24 warps x 1 candidate and 12 x 2 measure the same at 4 references)
-        if (a.sc == 2) return max_refs <= 2 ? BVC_FW16N(true, 1) : max_refs <= 4 ? BVC_FW16N(true, 2) : BVC_FW16N(true, 4);
-        return max_refs <= 2 ? BVC_FW16N(false, 1) : max_refs <= 4 ? BVC_FW16N(false, 2) : BVC_FW16N(false, 4);
+        // one candidate per warp up to 4 references (24 consumer warps: 0.96 us per block against 1.16 with 12 warps x 2)
+        if (a.sc == 2) return max_refs <= 4 ? BVC_FW16N(true, 1) : BVC_FW16N(true, 2);
+        return max_refs <= 4 ? BVC_FW16N(false, 1) : BVC_FW16N(false, 2);
 #undef BVC_FW16N
 #undef BVC_FW16
     }
-#define BVC_FW(B, N) launch_fw<B, N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
-    if (a.bs == 16) return ns == 8 ? BVC_FW(true, 8) : ns == 4 ? BVC_FW(true, 4) : BVC_FW(true, 2);
-    return ns == 8 ? BVC_FW(false, 8) : ns == 4 ? BVC_FW(false, 4) : BVC_FW(false, 2);
+#define BVC_FW(N) launch_fw<N>(*win_map, aa, lanes, smem, ref_base, ref_plane_bytes, ref_pitch, cmp_out, st)
+    return ns == 8 ? BVC_FW(8) : ns == 4 ? BVC_FW(4) : BVC_FW(2);
 #undef BVC_FW
 }
 

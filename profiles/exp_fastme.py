@@ -1,5 +1,5 @@
-"""FastME (BASELINE config 2: CIF, i=16, 4 references): clip time with transfer tables (default), the serial SAD-map
-walk and direct candidate evaluation (bvc_set_fastme_direct 0 / 2 / 1)."""
+"""FastME (BASELINE config 2: CIF, i=16, 4 references): clip time of every evaluation mode (bvc_set_fastme_direct: 0 auto,
+3 window walk, 4 transfer tables, 2 serial SAD-map walk, 1 direct candidate evaluation)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,7 +10,7 @@ frames = synth.moving_clip(77, H, W, n, step=2, clamp=24)
 out = np.empty(n * W * H // 2 + (1 << 20), np.uint8)
 with bvc.Context(W, H, bs, 16, qp, nref, True, False, ip, device=0, max_lanes=lanes) as ctx:
     ctx.set_lane_groups(1)
-    for direct in (0, 3, 2, 1):   # transfer tables, fixed point, serial walk on the SAD map, direct evaluation
+    for direct in (0, 3, 4, 2, 1):   # auto, window walk, transfer tables, serial walk on the SAD map, direct evaluation
         ctx.set_fastme_direct(direct)
         for _ in range(2):
             ctx.encode_clip_into(frames, out)

@@ -31,7 +31,7 @@ WORKLOADS = {
     "x_1080p_fastme_nref4": (1920, 1088, 600, 16, 16, 4, 30, 4, True, False, 20, dict(step=6, clamp=96)),
     "x_cif_halfpel_fastme_nref2": (352, 288, 296, 16, 4, 3, 8, 2, True, True, 37, dict(step=2, clamp=16)),
 }
-FASTME_MODE = int(os.environ.get("BVC_FASTME_MODE", "0"))   # bvc_set_fastme_direct: 0 transfer tables, 1 direct, 2 serial walk
+FASTME_MODE = int(os.environ.get("BVC_FASTME_MODE", "0"))   # bvc_set_fastme_direct: 0 auto, 1 direct, 2 serial map walk, 3 window walk, 4 tables
 
 
 def run(name):

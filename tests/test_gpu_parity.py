@@ -380,14 +380,14 @@ def test_lane_groups_do_not_change_the_stream():
 @pytest.mark.parametrize("frac,nref", [(False, 3), (True, 2)])
 def test_fastme_clip_with_lane_groups_and_modes(frac, nref):
     """FastME through the clip call: 15 blocks per frame (an odd count: the per-group slices of the transfer-table scratch
-    must stay 16-byte aligned), 1..3 lane groups running on their own streams, all three evaluation modes: same bytes as
+    must stay 16-byte aligned), 1..3 lane groups running on their own streams, every evaluation mode: same bytes as
     the oracle."""
     ob = _ob()
     H, W, bs, qp, ip, n = 48, 80, 16, 3, 4, 23
     frames = synth.moving_clip(33, H, W, n, step=5, clamp=24, blur=5)
     cfg = ob.make_config(W, H, bs, 4, qp, nref=nref, fastme=True, frac=frac, i_period=ip)
     want, want_recon = ob.encode_clip(cfg, frames)
-    for lanes, groups, mode in ((6, 1, 0), (6, 2, 0), (5, 3, 0), (6, 2, 2), (3, 2, 1), (6, 2, 3), (5, 3, 3)):
+    for lanes, groups, mode in ((6, 1, 0), (6, 2, 4), (5, 3, 4), (6, 2, 2), (3, 2, 1), (6, 2, 3), (5, 3, 3)):
         with _ctx(W, H, bs, 4, qp, nref, True, frac, ip, lanes=lanes) as ctx:
             ctx.set_lane_groups(groups)
             ctx.set_fastme_direct(mode)
@@ -399,14 +399,14 @@ def test_fastme_clip_with_lane_groups_and_modes(frac, nref):
 @pytest.mark.parametrize("H,W,bs", [(16, 16, 16), (48, 16, 16), (16, 64, 16), (8, 40, 8), (36, 36, 4)])
 def test_fastme_modes_on_degenerate_geometry(H, W, bs):
     """A single block, a single block column / row, and block sizes below 16: every candidate but the origin leaves the
-    plane in at least one direction, the half-pel phases shrink the valid range by one more pixel; all four FastME
-    evaluation modes against the oracle."""
+    plane in at least one direction, the half-pel phases shrink the valid range by one more pixel; every FastME
+    evaluation mode against the oracle."""
     ob = _ob()
     frames = synth.moving_clip(700 + H + W, H, W, 5, step=2, clamp=6, blur=3)
     for frac in (False, True):
         cfg = ob.make_config(W, H, bs, 4, 2, nref=2, fastme=True, frac=frac, i_period=5)
         want, want_recon = ob.encode_clip(cfg, frames)
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             with _ctx(W, H, bs, 4, 2, 2, True, frac, 5, lanes=1) as ctx:
                 ctx.set_fastme_direct(mode)
                 data, recon = ctx.encode_clip(frames, want_recon=True)
@@ -458,7 +458,7 @@ def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
     planes = [ob.halfpel_plane(x) for x in refs] if frac else refs
     mv_o, sad_o, cmp_o = ob.me_frame(cfg, cur, planes)
     assert np.abs(mv_o[:, 0]).max() > 16, "the case must leave the SAD map (+-16 MV units)"
-    for direct in (0, 1, 2, 3):  # transfer tables (default), direct evaluation, serial walk on the SAD map, fixed point
+    for direct in (0, 1, 2, 3, 4):  # auto, direct evaluation, serial walk on the SAD map, window walk, transfer tables
         with _ctx(W, H, bs, 4, 3, nref, True, frac) as ctx:
             ctx.set_fastme_direct(direct)
             mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
