@@ -325,9 +325,9 @@ class Context:
         self.lane_groups = int(groups)
 
     def set_fastme_direct(self, on):
-        """FastME evaluation (bvc_set_fastme_direct): 0 / False (default) = SAD map + transfer tables, 1 / True = every
-        candidate evaluated directly, 2 = SAD map + serial walk, 3 = serial walk over TMA-staged windows (no SAD map).  The
-        output does not depend on it."""
+        """FastME evaluation (bvc_set_fastme_direct): 0 / False (default) = automatic (window walk with many frames in
+        flight, else transfer tables), 1 / True = every candidate evaluated directly, 2 = SAD map + serial walk,
+        3 = window walk (TMA-staged windows, no SAD map), 4 = SAD map + transfer tables.  The output does not depend on it."""
         self._check(self._L.bvc_set_fastme_direct(self._h, int(on)))
 
     def launch_count(self):

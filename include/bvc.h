@@ -149,13 +149,14 @@ int bvc_decode_frame(bvc_ctx *ctx, int intra, const uint8_t *pred, size_t pred_l
  * exclusive only then).  Default 2 (environment override: BVC_LANE_GROUPS).  The output does not depend on it. */
 int bvc_set_lane_groups(bvc_ctx *ctx, int groups);
 
-/* FastME evaluation.  0 (default): the SADs of all candidates within 16 MV units of every block are computed by the tiled
- * full-search kernel; the walk of every block (find_fast_me_block, encoder/block_predictor.py:11-58) is tabulated for all
- * predictors within +-15 in parallel, so the serial predictor chain (encoder/PFrame.py:34,44,105-110) is one look-up per
- * block.  1: every candidate is evaluated when the serial walk reaches it.  2: SAD map, serial walk reading it.
- * 3: no SAD map; serial walk with the reference windows of the blocks ahead staged in shared memory by TMA (no scratch
- * memory: the SAD map of modes 0 / 2 takes 2 * (2*16+1)^2 bytes per block and reference).
- * The output does not depend on the setting. */
+/* FastME evaluation (find_fast_me_block, encoder/block_predictor.py:11-58, and the serial predictor chain of
+ * encoder/PFrame.py:34,44,105-110).  The output does not depend on the setting.
+ *   0 (default) automatic: 3 when at least 26 frames are in flight per step (16x16 blocks), else 4.
+ *   1 every candidate is evaluated from global memory when the serial walk reaches it (first version).
+ *   2 SAD map (all candidates within 16 MV units of every block, computed by the tiled full-search kernel), serial walk.
+ *   3 window walk: serial walk, the reference windows of the blocks ahead staged in shared memory by TMA; no scratch memory.
+ *   4 SAD map + transfer tables: the walk of every block tabulated for all predictors within +-15 in parallel, the chain
+ *     is one look-up per block.  Scratch: 2 * 33^2 bytes per block and reference for the map, 2.2 KB per block for the tables. */
 int bvc_set_fastme_direct(bvc_ctx *ctx, int on);
 
 /* instrumentation --------------------------------------------------------------------------- */
