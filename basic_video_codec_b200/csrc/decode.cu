@@ -58,9 +58,14 @@ __device__ __forceinline__ int eg_step(const uint32_t* sm, int p, long long rem,
     return 1;
 }
 
+// The 32 walks of a chunk visit the same bit positions over and over (prefix codes resynchronise after a few symbols), and
+// what a walk does at a position does not depend on where it came from.  So every position is decoded once -- 16 per
+// lane -- into a table (length, EOB flag, or how the walk ends there), and the 32 walks just follow the table.
 __global__ void __launch_bounds__(128) eg_spec_kernel(const uint8_t* data, const EgStream* streams, const int* chunk_stream,
                                                       long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab) {
     __shared__ uint32_t sm[4][EG_STAGE_WORDS + 1];
+    // per position: bits 0-4 code length (1..31, always odd); bit 5 EOB marker; 0x40 = end of stream, 0x80 = malformed
+    __shared__ uint8_t tab[4][EG_CHUNK_BITS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long gc = (long long)blockIdx.x * 4 + warp;
     if (gc >= nchunks) return;
@@ -70,15 +75,21 @@ __global__ void __launch_bounds__(128) eg_spec_kernel(const uint8_t* data, const
     __syncwarp();
     const long long left = st.nbits - bit0;
     const int end = (int)min((long long)EG_CHUNK_BITS, left);
+    // lane l decodes positions l, l + 32, ...: neighbouring lanes read neighbouring windows (no bank conflicts on `sm`)
+    for (int p = lane; p < end; p += 32) {
+        int v, len;
+        const int k = eg_step(sm[warp], p, left - p, v, len);
+        tab[warp][p] = k > 0 ? (uint8_t)(len | (v == BVC_EOB_MARKER ? 0x20 : 0)) : (k < 0 ? 0x80 : 0x40);
+    }
+    __syncwarp();
     int pos = lane, nsym = 0, neob = 0;
     bool err = false;
     while (pos < end) {
-        int v, len;
-        const int k = eg_step(sm[warp], pos, left - pos, v, len);
-        if (k <= 0) { err = k < 0; pos = EG_CHUNK_BITS; break; }
+        const uint32_t t = tab[warp][pos];
+        if (t & 0xc0u) { err = (t & 0x80u) != 0; pos = EG_CHUNK_BITS; break; }
         nsym++;
-        neob += (v == BVC_EOB_MARKER);
-        pos += len;
+        neob += (int)(t >> 5);
+        pos += (int)(t & 31u);
     }
     exit_tab[gc * 32 + lane] = err ? 255 : (uint8_t)max(pos - EG_CHUNK_BITS, 0);
     nsym_tab[gc * 32 + lane] = (uint16_t)nsym;
