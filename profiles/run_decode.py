@@ -29,7 +29,9 @@ def main():
     dec = dec_t.numpy()
     with bvc.Context(W, H, BS, R, QP, 1, False, False, IP, device=0, max_lanes=LANES) as ctx:
         ln = ctx.encode_clip_into(frames, out, recon)
-        data = out[:ln].copy()
+        data_t = torch.empty(int(ln), dtype=torch.uint8, pin_memory=True)   # pinned host buffers in and out
+        data = data_t.numpy()
+        data[:] = out[:ln]
         l0 = ctx.launch_count()
         got = ctx.decode_clip(data, N, out=dec)       # warm-up (allocations)
         launches = ctx.launch_count() - l0
