@@ -437,17 +437,14 @@ __global__ void __launch_bounds__(256) fastme_finish_kernel(MeArgs a, int lanes,
 // ---- window walk (no SAD map) -------------------------------------------------------------------------------------------
 // The SAD map costs as much as a full search of +-16 although a walk touches a few dozen positions, and the first direct
 // kernel above pays an L2 round trip per candidate and a CTA-wide barrier pair per level.  Here the serial chain stays,
-// but everything a level needs is in shared memory when the walk reaches the block: NS-1 blocks ahead, one thread asks
-// the TMA unit for the block's reference windows (every reference and phase plane, 16 pixels around the block -- where
-// the candidates of a predictor within +-16 lie; rows and columns outside the plane are zero-filled and never read by a
-// valid candidate) and warp 0 copies its current pixels with cp.async, so the fetch costs a handful of instructions
-// instead of a CTA's worth of address arithmetic.  The 6 x nRef candidates of a level are dealt to up to 12 warps (16x16:
-// one lane per half row, two VABSDIFF4 on funnel-shifted shared-memory words, redux.sync for the sum); after one barrier
-// every warp reduces the keys with redux.sync.  What bounds a level is the dependent instruction chain of a warp
-// (~5 cycles per instruction with one warp per scheduler) against the issue slots all warps spend on the same control
-// flow: one warp per reference (6 candidates each) measured 2.3 us per block, 24 warps with copies issued by every thread
-// 2.1 us (profiles/r1_experiments.md).  Candidates outside the window (predictor drifted past 16) read global memory.
-// One CTA per frame; lanes run in parallel.
+// but everything a level needs is in shared memory when the walk reaches the block: NS-1 blocks ahead the TMA unit is asked
+// for the block's reference windows (every reference and phase plane, 16 pixels around the block -- where the candidates
+// of a predictor within +-16 lie; rows and columns outside the plane are zero-filled and never read by a valid
+// candidate), so the fetch costs a handful of instructions instead of a CTA's worth of address arithmetic.  The 6 x nRef
+// candidates of a level are dealt to warps (one warp per candidate SAD, redux.sync for the sum); after one barrier every
+// warp reduces the keys with redux.sync.  Candidates outside the window (predictor drifted past 16) read global memory.
+// One CTA per frame; lanes run in parallel.  Two kernels: fastme_window_kernel for block sizes 4 / 8 / 32 (simple, byte-wise
+// SADs) and fastme_window16_kernel, the tuned one (history in profiles/r1_experiments.md, section 7).
 constexpr int FW_PITCH = 64, FW16_PITCH = 48, FW_MARGIN = 16, FW_WARPS = 12;
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
