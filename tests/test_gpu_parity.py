@@ -442,7 +442,7 @@ def test_i420_input_stage_pads_and_skips_chroma(tmp_path):
             ctx.clip_upload_i420(np.zeros(10 ** 5, np.uint8), 64, 64, 2)      # not the context's size
 
 
-@pytest.mark.parametrize("frac,bs,nref", [(False, 16, 2), (True, 8, 3), (False, 8, 1), (False, 4, 6)])
+@pytest.mark.parametrize("frac,bs,nref", [(False, 16, 2), (True, 8, 3), (False, 8, 1), (False, 4, 6), (False, 16, 6), (True, 16, 5), (True, 16, 1)])
 def test_fastme_sad_map_and_direct_paths_agree_with_oracle(frac, bs, nref):
     """FastME from the SAD map (default) and with direct evaluation (bvc_set_fastme_direct) against the oracle, on
     content whose motion exceeds the +-16 MV-unit map: a smooth gradient shifted 21 pixels makes the predictor drift
