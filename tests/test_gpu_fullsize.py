@@ -45,3 +45,29 @@ def test_4k_r64_4refs_spot_checks_and_roundtrip():
         omv, osad = ob.full_search_block(frames[3], [recon[0], recon[1], recon[2]], bx * bs, by * bs, bs, r)
         b = by * bw + bx
         assert mv[b].tolist() == list(omv) and int(sad[b]) == osad, (bx, by)
+
+
+@pytest.mark.parametrize("W,H,bs,r,nref,fastme,frac", [
+    (7680, 4320, 16, 16, 1, False, False),    # 8K: 129 600 blocks per frame, 270 x 480 block grid
+    (7680, 4320, 16, 16, 2, True, False),     # 8K FastME: chains of 129 600 blocks (transfer tables: 2 lanes in flight)
+    (4096, 2176, 8, 8, 2, False, True),       # half-pel planes of a 4K-wide frame, 8x8 blocks
+    (1936, 1096, 8, 4, 1, False, False),      # width and height that are multiples of 8 but not of 16 (pitch padding)
+])
+def test_large_and_odd_geometries_roundtrip(W, H, bs, r, nref, fastme, frac):
+    """Sizes beyond BASELINE's: the oracle would take minutes, so the size-independent property is checked --
+    decode(encode(x)) equals the encoder's reconstruction -- plus oracle motion vectors of a few sampled blocks."""
+    import basic_video_codec_b200 as bvc
+    from oracle import bindings as ob
+    n, ip = 4, 2
+    base = synth.moving_clip(5, 544, 960, n, step=3, clamp=24)
+    frames = np.ascontiguousarray(np.tile(base, (1, (H + 543) // 544, (W + 959) // 960))[:, :H, :W])
+    with bvc.Context(W, H, bs, r, 4, nref, fastme, frac, ip, device=0, max_lanes=2) as ctx:
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+        assert np.array_equal(ctx.decode_clip(data, n), recon)
+        if not fastme and not frac:
+            mv, sad, _ = ctx.me_search(frames[1], [recon[0]])
+            bw, bh = W // bs, H // bs
+            for bx, by in [(0, 0), (bw - 1, bh - 1), (bw // 2, bh // 3), (bw - 1, 0)]:
+                omv, osad = ob.full_search_block(frames[1], [recon[0]], bx * bs, by * bs, bs, r)
+                b = by * bw + bx
+                assert mv[b].tolist() == list(omv) and int(sad[b]) == osad, (bx, by)
