@@ -190,7 +190,7 @@ class Context:
         if intra:
             self._check(self._L.bvc_encode_iframe(self._h, _p(cur), _p(qp), C.byref(fo)))
         else:
-            keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+            keep = [self._check_frame(x) for x in refs]
             arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
             self._check(self._L.bvc_encode_pframe(self._h, _p(cur), arr, len(keep), _p(qp), C.byref(fo)))
         return self._finish_out(r, fo, pred, coef)
@@ -202,7 +202,7 @@ class Context:
         if refs is None:
             self._check(self._L.bvc_frame_begin(self._h, _p(cur), None, 0, 1))
         else:
-            keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+            keep = [self._check_frame(x) for x in refs]
             arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
             self._check(self._L.bvc_frame_begin(self._h, _p(cur), arr, len(keep), 0))
 
@@ -225,8 +225,8 @@ class Context:
 
     # ---- hooks ---------------------------------------------------------------------------------
     def me_search(self, cur, refs):
-        cur = np.ascontiguousarray(cur, dtype=np.uint8)
-        keep = [np.ascontiguousarray(x, dtype=np.uint8) for x in refs]
+        cur = self._check_frame(cur)
+        keep = [self._check_frame(x) for x in refs]
         arr = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
         mv = np.zeros((self.nblk, 3), np.int32)
         sad = np.zeros(self.nblk, np.int32)
@@ -243,18 +243,43 @@ class Context:
     # ---- clip level ------------------------------------------------------------------------------
     def encode_clip(self, frames, want_recon=False, out_capacity=None):
         """Host-buffer clip encode (the public end-to-end call).  Returns (container bytes, recon | None)."""
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        frames = self._check_clip(frames)
         n = frames.shape[0]
         cap = int(out_capacity or (n * self.W * self.H // 2 + (1 << 20)))
-        out = np.empty(cap, np.uint8)
         recon = np.empty_like(frames) if want_recon else None
-        ln = self.encode_clip_into(frames, out, recon)
-        return out[:ln].tobytes(), recon
+        for _ in range(2):
+            out = np.empty(cap, np.uint8)
+            ln = C.c_size_t(0)
+            rc = self._L.bvc_encode_clip(self._h, _p(frames), n, _p(out), out.size, C.byref(ln), _p(recon))
+            # noisy content at a low QP can need more than the default 4 bits per pixel: the library reports the size
+            if rc == BVC_ERR_NOMEM and out_capacity is None and int(ln.value) > cap:
+                cap = int(ln.value)
+                continue
+            break
+        self._check(rc)
+        return out[:int(ln.value)].tobytes(), recon
+
+    def _check_clip(self, frames):
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        if frames.ndim != 3 or frames.shape[1:] != (self.H, self.W):
+            raise ValueError(f"clip shape {frames.shape} != (n, {self.H}, {self.W})")
+        return frames
+
+    @staticmethod
+    def _check_buffer(buf, nbytes, what):
+        if buf is None:
+            return
+        if not (isinstance(buf, np.ndarray) and buf.dtype == np.uint8 and buf.flags.c_contiguous and buf.flags.writeable):
+            raise ValueError(f"{what} must be a writable C-contiguous uint8 array")
+        if buf.size < nbytes:
+            raise ValueError(f"{what} holds {buf.size} bytes, {nbytes} needed")
 
     def encode_clip_into(self, frames, out, recon=None):
         """Same call without Python-side copies: `out` is a caller-owned uint8 buffer (pinned for best
         transfer speed); returns the number of container bytes written."""
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        frames = self._check_clip(frames)
+        self._check_buffer(out, 6, "out")
+        self._check_buffer(recon, frames.size, "recon")
         ln = C.c_size_t(0)
         self._check(self._L.bvc_encode_clip(self._h, _p(frames), frames.shape[0], _p(out), out.size, C.byref(ln), _p(recon)))
         return int(ln.value)
@@ -300,7 +325,7 @@ class Context:
         return recon, lev, pred, qps
 
     def clip_upload(self, frames):
-        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        frames = self._check_clip(frames)
         self._check(self._L.bvc_clip_upload(self._h, _p(frames), frames.shape[0]))
 
     def clip_upload_i420(self, yuv, src_w, src_h, nframes):
@@ -314,6 +339,7 @@ class Context:
     def encode_clip_resident(self, nframes, out=None):
         if out is None:
             out = np.empty(nframes * self.W * self.H // 2 + (1 << 20), np.uint8)
+        self._check_buffer(out, 6, "out")
         ln = C.c_size_t(0)
         self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
         return out, int(ln.value)

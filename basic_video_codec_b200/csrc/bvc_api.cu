@@ -49,6 +49,7 @@ struct bvc_ctx {
     // scheduler does not place a second kernel's CTAs next to a kernel that still has CTAs to dispatch
     // (profiles/microbench/cosched.cu), so this buys the tails (~1.5 %), not a transform-under-search overlap.
     int ngroups = 2;
+    int tail_split = 1;   // motion search: tiles of the last, partly filled wave as one-row CTAs (BVC_TAIL_SPLIT=0 turns it off)
     cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
     cudaEvent_t ev_me[BVC_MAX_GROUPS] = {}, ev_post[BVC_MAX_GROUPS] = {};
     std::string err;
@@ -79,6 +80,7 @@ struct bvc_ctx {
     uint8_t* d_container = nullptr;
     size_t container_cap = 0;
     int* d_progress = nullptr;
+    int* d_ticket = nullptr;      // [max_lanes]: start-order counters of the wavefront kernels, one per lane group in flight
     MeLane* d_me_lanes = nullptr;
     FrameLane* d_fr_lanes = nullptr;
     size_t lane_desc_cap = 0;
@@ -186,7 +188,7 @@ static int make_ref_map(bvc_ctx* c) {
     const int R = c->p.fast_me ? (c->p.frac_me ? 8 : 16) : c->p.search_range;
     if (c->p.fast_me && !me_can_map(c->g.bs, R)) return BVC_OK;
     MeTileCfg cfg = me_tile_config(c->g.bs, R);
-    if (!cfg.tiled) return BVC_OK;
+    if (!cfg.tiled && !cfg.narrow) return BVC_OK;
     int rc = encode_map(c, &c->ref_map, cfg.win_pitch, cfg.rows);
     if (rc != BVC_OK) return rc;
     c->have_map = true;
@@ -244,6 +246,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
             CK(cudaEventCreateWithFlags(&c->ev_post[gi], cudaEventDisableTiming));
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
+        if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;
         CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
@@ -263,6 +266,8 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_cmp, L));
         CK(dalloc(&c->d_rowbits, 1));
         CK(dalloc(&c->d_progress, L * g.bh));
+        CK(dalloc(&c->d_ticket, L));
+        CK(cudaMemset(c->d_ticket, 0, L * sizeof(int)));
         c->coef_cap_words = nb * c->blk_words + 8;
         c->pred_cap_words = nb * 3 + g.bh + 8;
         CK(dalloc(&c->d_overflow, 1));
@@ -297,7 +302,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
-    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container);
@@ -370,6 +375,7 @@ static int ensure_in_pool(bvc_ctx* c, size_t planes) {
     if (c->in_pool) CK(cudaFree(c->in_pool));
     c->in_pool = nullptr;
     c->in_planes = 0;
+    c->resident_frames = 0;   // whatever bvc_clip_upload left in the old pool is gone
     CK(cudaMalloc((void**)&c->in_pool, planes * c->g.plane_bytes + 4096));
     c->in_planes = planes;
     return BVC_OK;
@@ -512,7 +518,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
     t.blk_bits = c->d_blk_bits + L0 * nb * c->blk_words; t.blk_nbits = c->d_blk_nbits + L0 * nb; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
-    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh; t.ticket = c->d_ticket + L0;
     t.row_begin = 0; t.row_count = g.bh;
     if (sp.intra) {
         CK(cudaMemsetAsync(t.progress, 0, (size_t)nl * g.bh * sizeof(int), st_post));
@@ -530,6 +536,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.nphase = c->p.frac_me ? 4 : 1;
         m.R = c->p.search_range;
         m.Rh = c->p.search_range * m.sc;
+        m.tail_split = c->tail_split;
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
             int rcf = launch_fastme_any(c, m, nl, L0, st_me, sp.nl);
@@ -607,6 +614,7 @@ static int frame_prepare(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* r
     if ((rc = ensure_in_pool(c, 1)) != BVC_OK) return rc;
     if ((rc = ensure_lane_desc(c, 1)) != BVC_OK) return rc;
     if ((rc = ensure_streams(c, 1)) != BVC_OK) return rc;
+    c->resident_frames = 0;   // plane 0 of the input pool is overwritten: a clip uploaded earlier is no longer resident
     if ((rc = upload_plane(c, c->in_pool, cur)) != BVC_OK) return rc;
     MeLane ml{};
     FrameLane fl{};
@@ -639,7 +647,7 @@ static int launch_me_lane0(bvc_ctx* c) {
     m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
     m.lanes = c->d_me_lanes; m.out = c->d_mv;
     m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
-    m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc;
+    m.sc = c->p.frac_me ? 2 : 1; m.nphase = c->p.frac_me ? 4 : 1; m.R = c->p.search_range; m.Rh = m.R * m.sc; m.tail_split = c->tail_split;
     if (c->p.fast_me) { int rcf = launch_fastme_any(c, m, 1, 0, c->st, 1); if (rcf != BVC_OK) return rcf; }
     else CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, 1, c->ref_pool, g.plane_bytes, g.pitch, c->st));
     c->launches += 1;
@@ -757,7 +765,7 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     t.levels = c->d_levels; t.resid_mc = c->d_resid_mc; t.resid_nomc = c->d_resid_nomc;
     t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
-    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress; t.ticket = c->d_ticket;
     pk = PackArgs{};
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
     pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
@@ -1077,7 +1085,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     DecArgs a{};
     a.ref_base = c->ref_pool; a.ref_plane_bytes = g.plane_bytes; a.ref_pitch = g.pitch;
     a.mv_all = d_mv; a.modes_all = d_modes; a.qp_all = d_qp; a.syms = d_syms; a.coef_sym0 = d_sym0; a.blk_start = d_blk_start;
-    a.levels_out = d_levels; a.progress = d_progress; a.err_flag = c->d_overflow;
+    a.levels_out = d_levels; a.progress = d_progress; a.ticket = c->d_ticket; a.err_flag = c->d_overflow;
     a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
     if (pred_only) steps.clear();
     // Decoded planes go back on their own stream so that the download of step s overlaps the kernels of step s+1 (the
@@ -1224,6 +1232,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     const int nwaves = (ngop + G - 1) / G;
     int rc;
     if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+    if (host_frames) c->resident_frames = 0;   // the pool is about to be overwritten with this call's frames
     if ((rc = ensure_streams(c, (size_t)nframes)) != BVC_OK) return rc;
     if ((rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
 
@@ -1377,7 +1386,10 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     CK(cudaMemcpyAsync(&overflow, c->d_overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     if (overflow) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
-    if ((size_t)total > out_cap) return fail(c, BVC_ERR_NOMEM, "output buffer too small");
+    if ((size_t)total > out_cap) {
+        *out_len = (size_t)total;   // what the caller has to provide
+        return fail(c, BVC_ERR_NOMEM, "output buffer too small (*out_len = bytes needed)");
+    }
     CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st));

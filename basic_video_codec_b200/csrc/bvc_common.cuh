@@ -80,6 +80,17 @@ __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t acc) {
     return d;
 }
 
+// Wavefront kernels (one warp per CTA): the CTA's position in the wavefront is the order in which it started.  The last
+// CTA of the grid puts the counter back to zero for the next launch on the stream.
+__device__ __forceinline__ int wavefront_ticket(int* counter, int lane) {
+    int tk = 0;
+    if (lane == 0) {
+        tk = atomicAdd(counter, 1);
+        if (tk == (int)gridDim.x - 1) atomicExch(counter, 0);
+    }
+    return __shfl_sync(0xffffffffu, tk, 0);
+}
+
 // signed exp-Golomb (reference encoder/entropy_encoder.py:8-29): code value e = map(v)+1 written in
 // nb = bitlen(e) bits preceded by nb-1 zeros  => total 2*nb-1 bits, numerically just `e`.
 __device__ __forceinline__ uint32_t eg_code(int v) { return (v <= 0 ? (uint32_t)(-2 * v) : (uint32_t)(2 * v - 1)) + 1u; }

@@ -26,6 +26,9 @@ struct MeArgs {
     int nphase;                    // 1 or 4
     int Rh;                        // range in MV units (= R*sc)
     int win_pitch, win_copy_bytes, win_lm; // filled by the launcher
+    int Rv;                        // vertical range the tiled bodies walk (>= R, 2*Rv a multiple of bs); launcher
+    int tiles_x, tiles_y, n_full;  // linear tile grid: CTAs [0, n_full) own whole tiles, the rest one block row each (launcher)
+    int tail_split;                // 1: cut the tiles of the last, partly filled wave into one-row CTAs
     int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
     // SAD map (FastME): when non-null the tiled kernel stores the SAD of every in-range candidate instead of reducing
     // them: uint16 [lane][ref][phase][blk][map_stride >= (2R+1)^2] (row = vertical offset + R, column = horizontal offset + R),
@@ -35,14 +38,19 @@ struct MeArgs {
     int map_stride;                // uint16 elements per (lane, ref, phase, block): (2R+1)^2 rounded up to a multiple of 8
 };
 struct MeTileCfg {
-    bool tiled;
+    bool tiled;     // me_tiled_kernel (2R >= bs)
+    bool narrow;    // me_narrow_kernel (2R < bs)
     int nb;         // blocks per CTA, side by side
     int nby;        // block rows per CTA, stacked
     int win_pitch;  // TMA box width in bytes
     int rows;       // TMA box height
     int win_lm;     // left margin: window column of x0-R inside the 16-byte aligned box
+    int Rv;         // vertical range walked (tiled kernel: R rounded up so that 2*Rv % bs == 0)
 };
 MeTileCfg me_tile_config(int bs, int R);
+// narrow-range search (me_narrow.cu): 2R < bs, one thread per (block, candidate column), exact work
+MeTileCfg me_narrow_config(int bs, int R);
+cudaError_t launch_me_narrow(const CUtensorMap& ref_map, const MeArgs& args, int lanes, cudaStream_t st);
 cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
                                  size_t ref_plane_bytes, int ref_pitch, cudaStream_t st);
 
@@ -107,6 +115,8 @@ struct TqArgs {
     int frac;                      // MVs in half-pel units, pred from phase planes
     int multi_ref;                 // nRefFrames > 1: pred from refs[mv.ref] else refs[0]
     int* progress;                 // I frames: device [lanes][bh] wavefront progress counters (zeroed)
+    int* ticket;                   // I frames: one self-resetting counter per launch in flight: a CTA's block row follows the
+                                   // order in which CTAs actually start, so a row never waits for a CTA that is not resident
     int row_begin, row_count;      // block rows to encode in this launch (0, bh = whole frame); the row-by-row
                                    // rate-control loop (Frame.get_rc_qp, Frame.py:168-188) launches one row at a time
 };
@@ -167,6 +177,7 @@ struct DecArgs {
     const int* blk_start;          // [nframes][nblk+1] first symbol of every block, relative to coef_sym0
     int16_t* levels_out;           // [nframes][H][W] or null
     int* progress;                 // I frames: [lanes][bh] wavefront counters (zeroed)
+    int* ticket;                   // I frames: start-order ticket counter (see TqArgs::ticket)
     int* err_flag;
     int W, H, bs, bw, bh, nblk;
     int frac;

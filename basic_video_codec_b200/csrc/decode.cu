@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
     build_zigzag<BS>(sm.zz, lane, 32);
     __syncwarp();
     const int ngrp = (lanes + NBW - 1) / NBW;
-    const int by = blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
+    const int tk = wavefront_ticket(a.ticket, lane);   // start order, not blockIdx: see tq_iframe_kernel
+    const int by = tk / ngrp, grp = tk % ngrp;
     const int q = lane / BS, x = lane % BS;
     const int fl_raw = grp * NBW + q;
     const bool valid = fl_raw < lanes;

@@ -152,24 +152,42 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     __shared__ uint32_t utab[NBY][2 * 128 + 1 + 2 * BS];   // per-pass candidate tables, indexed by m + BS
 
     const int tid = threadIdx.x;
-    const int R = a.R;
-    const int rows = NBY * BS + 2 * R;
+    const int R = a.R;        // horizontal range = the search range (plane units)
+    const int Rv = a.Rv;      // vertical range walked by the bodies: R rounded up so that 2*Rv is a multiple of BS;
+                              // offsets beyond R are masked through utab (bit 31) like offsets outside the plane
     const int WW = a.win_pitch;               // bytes, multiple of 16
     const int copy_stride = a.win_copy_bytes + 32;  // +32 B: copy k starts 8 banks after copy k-1 (conflict-free LDS)
-    const int bx0 = blockIdx.x * NB;
-    const int by0 = blockIdx.y * NBY;
+    // Tile from the linear CTA index.  CTAs [0, n_full) own a whole tile of NB x NBY blocks; the tiles of the last,
+    // partly filled wave are cut into NBY CTAs of one block row each (a quarter of the work at NBY = 4), so the tail of
+    // the launch is a fraction of a tile time instead of a whole one.
+    int tile = blockIdx.x, yy0 = 0, yy1 = NBY;
+    if (tile >= a.n_full) {
+        const int u = tile - a.n_full;
+        tile = a.n_full + u / NBY;
+        yy0 = u % NBY;
+        yy1 = yy0 + 1;
+    }
+    const int per_z = a.tiles_x * a.tiles_y;
+    const int z = tile / per_z, t2 = tile - z * per_z;
+    const int ty = t2 / a.tiles_x, tx = t2 - ty * a.tiles_x;
+    const int bx0 = tx * NB;
+    const int by0 = ty * NBY;
+    const int rows = (yy1 - yy0) * BS + 2 * Rv;       // window rows this CTA reads (the TMA box always has NBY*BS + 2*Rv)
+    const int box_bytes = WW * (NBY * BS + 2 * Rv);
+    const int wy0 = (by0 + yy0) * BS - Rv;           // plane row of window row 0
     // SAD-map mode has no reduction across references, so every (lane, reference) pair gets its own CTAs
-    // (grid.z = lanes * max_refs): small frames (CIF: 30 tiles per lane) then fill the GPU
-    const int lane = SADMAP ? (int)blockIdx.z / a.max_refs : (int)blockIdx.z;
+    // (z = lanes * max_refs): small frames (CIF: 30 tiles per lane) then fill the GPU
+    const int lane = SADMAP ? z / a.max_refs : z;
     const MeLane& L = a.lanes[lane];
-    const int r_begin = SADMAP ? (int)blockIdx.z % a.max_refs : 0;
+    const int r_begin = SADMAP ? z % a.max_refs : 0;
     const int r_end = SADMAP ? min(r_begin + 1, L.nref) : L.nref;
     if (r_begin >= r_end) return;
+    if (by0 + yy0 >= a.bh) return;                   // sub-tile below the last block row
     uint8_t* scur = smem + 4 * (size_t)copy_stride;   // [NBY*BS][NB*BS] current pixels of the CTA's blocks
 
     const int nmain = NB * 2 * R;
     const int xbase = (nmain + 31) & ~31;     // first thread of the extra warps
-    const int nseg = (2 * R + 1 + BS) / (BS + 1);
+    const int nseg = (2 * Rv + 1 + BS) / (BS + 1);
     const bool is_extra = tid >= xbase;
     int b, dx, m0 = 0, yye = 0;
     bool active;
@@ -184,8 +202,8 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
         b = e2 / nseg;
         const int seg = e2 - b * nseg;
         dx = R;
-        m0 = min(seg * (BS + 1), 2 * R - BS);  // overlapping the previous segment is harmless for an argmin
-        active = yye < NBY;
+        m0 = min(seg * (BS + 1), 2 * Rv - BS);  // overlapping the previous segment is harmless for an argmin
+        active = yye >= yy0 && yye < yy1;
     }
     active = active && (bx0 + b < a.bw);
     const int ox = (bx0 + b) * BS;
@@ -195,8 +213,8 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
         fence_mbar_init();
         // the first window is requested before anything else, so the TMA latency hides behind the staging of the
         // current blocks and the candidate table
-        mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
-        tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r_begin]);
+        mbar_arrive_expect_tx(&bar, (uint32_t)box_bytes);
+        tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, wy0, L.ref_plane[r_begin]);
     }
     for (int i = tid; i < NB * NBY; i += blockDim.x) sbest[i / NB][i % NB] = ~0ull;
     {   // stage the current blocks (NB*BS x NBY*BS bytes) in shared memory, 16 B per thread-iteration
@@ -227,26 +245,26 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     kc.scale = 1u << (a.key_mbits + a.key_l1bits);
 
     uint32_t parity = 0;
-    const int nmid = (2 * R) / BS - 1;
+    const int nmid = (2 * Rv) / BS - 1;
 
     for (int r = r_begin; r < r_end; r++) {
         for (int ph = 0; ph < a.nphase; ph++) {
             const int px = ph & 1, py = ph >> 1;
             if (tid == 0 && (r != r_begin || ph != 0)) {
-                mbar_arrive_expect_tx(&bar, (uint32_t)(WW * rows));
+                mbar_arrive_expect_tx(&bar, (uint32_t)box_bytes);
                 // box origin: 16-byte aligned column (bx0*BS - R - win_lm), rows <= 256
-                tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, by0 * BS - R, L.ref_plane[r] + ph);
+                tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, wy0, L.ref_plane[r] + ph);
             }
             if (PACKED) {
-                // utab[yy][m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane
-                const int per = 2 * R + 1 + 2 * BS;
+                // utab[yy][m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane or the range
+                const int per = 2 * Rv + 1 + 2 * BS;
                 for (int i = tid; i < NBY * per; i += blockDim.x) {
                     const int yy = i / per, ii = i - yy * per;
                     const int oy = (by0 + yy) * BS;
-                    const int mlo = max(0, R - oy);
-                    const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                    const int mlo = max(Rv - R, Rv - oy);
+                    const int mhi = min(Rv + R - py, a.H - py - BS - oy + Rv);
                     const int m = ii - BS;
-                    const uint32_t amvy = (uint32_t)abs(py - a.sc * R + a.sc * m);
+                    const uint32_t amvy = (uint32_t)abs(py - a.sc * Rv + a.sc * m);
                     utab[yy][ii] = (m >= mlo && m <= mhi) ? ((amvy << kc.mbits) | (uint32_t)m) : 0x80000000u;
                 }
             }
@@ -276,14 +294,14 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             if (xvalid) {
                 const uint32_t absmx = (uint32_t)abs(mvx);
                 const uint32_t tthr = PACKED ? (absmx << kc.mbits) : absmx;
-                const int mvy0 = py - a.sc * R;  // mvy = mvy0 + sc*m
-                // main threads: every stacked block row; extra threads: their one (row, segment)
-                const int yy_lo = is_extra ? yye : 0, yy_hi = is_extra ? yye + 1 : NBY;
+                const int mvy0 = py - a.sc * Rv;  // mvy = mvy0 + sc*m
+                // main threads: every block row of the CTA; extra threads: their one (row, segment)
+                const int yy_lo = is_extra ? yye : yy0, yy_hi = is_extra ? yye + 1 : yy1;
                 for (int yy = yy_lo; yy < yy_hi; yy++) {
                     if (by0 + yy >= a.bh) break;
                     const int oy = (by0 + yy) * BS;
-                    const int mlo = max(0, R - oy);
-                    const int mhi = min(2 * R - py, a.H - py - BS - oy + R);
+                    const int mlo = max(Rv - R, Rv - oy);
+                    const int mhi = min(Rv + R - py, a.H - py - BS - oy + Rv);
                     CurBlock<BS> cur;
                     load_cur<BS>(cur, scur + (size_t)yy * BS * (NB * BS) + b * BS, NB * BS);
                     uint32_t acc[BS];
@@ -292,11 +310,11 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                     uint32_t best = 0xFFFFFFFFu, bestm = 0;
                     const int n1 = 2 * R + 1;
                     uint16_t* smap = nullptr;
-                    if (SADMAP) {
+                    if (SADMAP) {   // map row = vertical offset + R (Rv == R whenever a map is asked for, see me_can_map)
                         const size_t blk = (size_t)(by0 + yy) * a.bw + bx0 + b;
                         smap = a.sad_map + ((((size_t)lane * a.max_refs + r) * a.nphase + ph) * a.nblk + blk) * (size_t)a.map_stride + (dx + R);
                     }
-                    const uint32_t* rowp = colp + (yy * BS + m0) * wpitch;
+                    const uint32_t* rowp = colp + ((yy - yy0) * BS + m0) * wpitch;
                     int mbase = m0 - (BS - 1);
                     const uint32_t* ut = &utab[yy][0] + BS + mbase;
                     const int nm = is_extra ? 0 : nmid;
@@ -331,7 +349,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     }
     for (int i = tid; i < NB * NBY; i += blockDim.x) {
         const int yy = i / NB, bb = i - yy * NB;
-        if (bx0 + bb < a.bw && by0 + yy < a.bh) {
+        if (yy >= yy0 && yy < yy1 && bx0 + bb < a.bw && by0 + yy < a.bh) {
             const unsigned long long k = sbest[yy][bb];
             const uint32_t hi = (uint32_t)(k >> 32), lo = (uint32_t)k;
             int4 o;
@@ -405,13 +423,27 @@ __global__ void __launch_bounds__(256) me_generic_kernel(MeArgs a, const uint8_t
     }
 }
 
+// resident CTAs of the whole GPU for a kernel / block size / dynamic shared memory size (cached per device)
+template <typename K>
+static int resident_slots(K kernel, int threads, size_t smem, int* cache) {
+    int& v = cache[current_device_slot()];
+    if (v > 0) return v;
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    v = per_sm * sms;
+    return v;
+}
+
 template <int BS, int NB, int NBY, bool PACKED, bool SADMAP, int WPC>
 cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     const int R = a.R;
-    const int nmain = NB * 2 * R;
-    const int nseg = (2 * R + 1 + BS) / (BS + 1);
-    const int threads = ((nmain + 31) & ~31) + ((NB * NBY * nseg + 31) & ~31);
     const MeTileCfg cfg = me_tile_config(BS, R);
+    a.Rv = cfg.Rv;
+    const int nmain = NB * 2 * R;
+    const int nseg = (2 * a.Rv + 1 + BS) / (BS + 1);
+    const int threads = ((nmain + 31) & ~31) + ((NB * NBY * nseg + 31) & ~31);
     a.win_pitch = cfg.win_pitch;
     a.win_lm = cfg.win_lm;
     a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
@@ -426,8 +458,18 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    dim3 grid((a.bw + NB - 1) / NB, (a.bh + NBY - 1) / NBY, SADMAP ? lanes * a.max_refs : lanes);
-    me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC><<<grid, threads, smem, st>>>(map, a);
+    a.tiles_x = (a.bw + NB - 1) / NB;
+    a.tiles_y = (a.bh + NBY - 1) / NBY;
+    const long long total = (long long)a.tiles_x * a.tiles_y * (SADMAP ? lanes * a.max_refs : lanes);
+    // whole waves of full tiles, then the remaining tiles as NBY one-row CTAs each (see the kernel)
+    static int slots_dev[BVC_MAX_DEVICES] = {};
+    const int slots = resident_slots(me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC>, threads, smem, slots_dev);
+    long long rem = (NBY > 1 && a.tail_split) ? total % slots : 0;
+    if (rem == total && total * NBY <= slots) rem = 0;   // a launch that does not even fill the GPU once: splitting cannot help the makespan
+    a.n_full = (int)(total - rem);
+    const long long grid = a.n_full + rem * NBY;
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    me_tiled_kernel<BS, NB, NBY, PACKED, SADMAP, WPC><<<(unsigned)grid, threads, smem, st>>>(map, a);
     return cudaGetLastError();
 }
 template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
@@ -453,11 +495,12 @@ static int bitlen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n;
 
 template <int BS, int NB, int NBY>
 cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
-    // packed key: SAD | L1 | m in 31 bits (bit 31 marks offsets outside the plane)
+    // packed key: SAD | L1 | m in 31 bits (bit 31 marks offsets outside the plane / the range)
+    const int Rv = me_tile_config(BS, a.R).Rv;
     const int sadbits = bitlen(255u * BS * BS);
     a.key_l1bits = bitlen(2u * a.Rh);
-    a.key_mbits = bitlen(2u * a.R);
-    if (sadbits + a.key_l1bits + a.key_mbits <= 31 && a.R <= 128) return launch_tiled_p<BS, NB, NBY, true>(map, a, lanes, st);
+    a.key_mbits = bitlen(2u * Rv);
+    if (sadbits + a.key_l1bits + a.key_mbits <= 31 && Rv <= 128) return launch_tiled_p<BS, NB, NBY, true>(map, a, lanes, st);
     return launch_tiled_p<BS, NB, NBY, false>(map, a, lanes, st);
 }
 
@@ -465,11 +508,11 @@ cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream
 // the same for every CTA) and NBY stacked.  Constraints: <= 544 threads, TMA box <= 256 x 256, four window copies
 // <= 110 KB; shapes that let two CTAs share an SM are preferred.
 struct TileShape { int nb, nby; };
-TileShape pick_shape(int bs, int R) {
+TileShape pick_shape(int bs, int R, int Rv) {
     const int cand16[] = {4, 2, 1}, cand8[] = {8, 4, 2}, cand4[] = {8, 4, 4};
     const int* c = bs == 16 ? cand16 : bs == 8 ? cand8 : cand4;
     const int lm = (16 - R % 16) % 16;
-    const int nseg = (2 * R + 1 + bs) / (bs + 1);
+    const int nseg = (2 * Rv + 1 + bs) / (bs + 1);
     // pass 0: shapes that leave room for two CTAs per SM (<= 341 threads at 96 registers, <= 106 KB of shared memory each):
     // at r = 64 that is 2 x 2 blocks (0.85 of the VABSDIFF4 peak on the 4K workload) instead of 4 x 1 in one 544-thread
     // CTA (0.80); pass 1: anything that fits.
@@ -480,7 +523,7 @@ TileShape pick_shape(int bs, int R) {
             const int nbys[] = {4, 2, 1};
             for (int j = 0; j < 3; j++) {
                 const int nby = nbys[j];
-                const int rows = nby * bs + 2 * R;
+                const int rows = nby * bs + 2 * Rv;
                 const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
                 const int smem = 4 * pitch * rows + nb * nby * bs * bs;
                 if (pitch > 256 || rows > 256) continue;
@@ -493,18 +536,27 @@ TileShape pick_shape(int bs, int R) {
 
 }  // namespace
 
+// Which search kernel serves (block size, range in plane units):
+//   2R <  BS : the narrow kernel (me_narrow.cu), exact work, one thread per (block, candidate column)
+//   2R >= BS : the tiled kernel; when 2R is not a multiple of BS the bodies walk a vertical range Rv > R (2*Rv the next
+//              multiple of BS) and the extra offsets are masked, so the executed / algorithmic VABSDIFF4 ratio is
+//              (2*Rv+1)/(2R+1) (1.0 for every BASELINE configuration)
+//   else     : the generic kernel (R = 0, windows beyond the TMA box limits)
 MeTileCfg me_tile_config(int bs, int R) {
-    MeTileCfg c{false, 0, 0, 0, 0, 0};
+    MeTileCfg c{};
     if (!(bs == 4 || bs == 8 || bs == 16)) return c;
-    if (R < 1 || (2 * R) % bs != 0 || 2 * R < bs) return c;
-    const TileShape t = pick_shape(bs, R);
+    if (R < 1) return c;
+    if (2 * R < bs) return me_narrow_config(bs, R);
+    const int Rv = (2 * R + bs - 1) / bs * bs / 2;
+    const TileShape t = pick_shape(bs, R, Rv);
     if (t.nb == 0) return c;
     c.tiled = true;
+    c.Rv = Rv;
     c.nb = t.nb;
     c.nby = t.nby;
     c.win_lm = (16 - R % 16) % 16;
     c.win_pitch = ((c.win_lm + t.nb * bs + 2 * R + 15) / 16) * 16;
-    c.rows = t.nby * bs + 2 * R;
+    c.rows = t.nby * bs + 2 * Rv;
     return c;
 }
 
@@ -519,6 +571,7 @@ cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args,
                                  size_t ref_plane_bytes, int ref_pitch, cudaStream_t st) {
     MeArgs a = args;
     const MeTileCfg cfg = me_tile_config(a.bs, a.R);
+    if (cfg.narrow && ref_map && !a.sad_map) return launch_me_narrow(*ref_map, a, lanes, st);
     if (cfg.tiled && ref_map) {
         if (a.bs == 16) {
             if (cfg.nb == 4) return launch_by_nby<16, 4>(cfg, *ref_map, a, lanes, st);
@@ -540,7 +593,8 @@ cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args,
 }
 
 bool me_can_map(int bs, int R) {
-    if (!me_tile_config(bs, R).tiled || R > 128) return false;
+    const MeTileCfg c = me_tile_config(bs, R);
+    if (!c.tiled || c.Rv != R || R > 128) return false;
     // the packed key (SAD | L1 | m in 31 bits) must fit; R here is already in plane units, L1 in MV units <= 4R
     return bitlen(255u * bs * bs) + bitlen(4u * R) + bitlen(2u * R) <= 31;
 }

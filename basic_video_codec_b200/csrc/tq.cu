@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
 // (bx,by-1) (IFrame.py:184-213) => anti-diagonal wavefront.  One warp (= one CTA) walks one block row
 // of NBW *different frames* (lanes) left to right; rows are chained through per-row progress counters
 // in global memory (release/acquire), row r trailing row r-1 by one block.
-// grid = (bh * ceil(lanes/NBW)), ordered row-major so producers are dispatched before consumers.
+// grid = (bh * ceil(lanes/NBW)).  A CTA does not derive its row from blockIdx: it takes a ticket when it starts, and
+// tickets are handed out row-major.  The CTA of the row above therefore holds a smaller ticket, i.e. it is already
+// resident and running whenever this CTA waits for it -- forward progress does not depend on the order in which the
+// hardware dispatches CTAs, nor on the whole grid being co-resident (grids beyond resident capacity, MPS, sanitizers).
 template <int BS>
 __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     constexpr int NBW = 32 / BS;
@@ -61,7 +64,8 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     build_zigzag<BS>(sm.zz, lane, 32);
     __syncwarp();
     const int ngrp = (lanes + NBW - 1) / NBW;
-    const int by = a.row_begin + blockIdx.x / ngrp, grp = blockIdx.x % ngrp;
+    const int tk = wavefront_ticket(a.ticket, lane);
+    const int by = a.row_begin + tk / ngrp, grp = tk % ngrp;
     const int q = lane / BS, x = lane % BS;
     const int fl_raw = grp * NBW + q;
     const bool valid = fl_raw < lanes;

@@ -110,7 +110,8 @@ int bvc_dct_quant_recon(int device, const int16_t *residual, const int16_t *pred
  * (1-based) with (idx-1) % I_Period == 0 is an I frame and clears the reference window, so GOPs are
  * independent and are encoded max_lanes at a time.  `frames` = nframes planes (host memory, ideally
  * pinned).  The container bytes (encoded.bin layout, encoder.py:104-121) are written to out[0..*out_len).
- * recon (optional) receives the nframes reconstructed planes. */
+ * recon (optional) receives the nframes reconstructed planes.  When out_cap is too small the call returns BVC_ERR_NOMEM
+ * with *out_len = the bytes needed, so the caller can retry. */
 int bvc_encode_clip(bvc_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *out, size_t out_cap,
                     size_t *out_len, uint8_t *recon);
 /* Same, for a clip whose planes are already resident in HBM (bvc_clip_upload), so the timed region

@@ -1,0 +1,119 @@
+"""Round-2 GPU tests: hazards the round-1 review named (stale resident clip, wavefront grids beyond resident
+capacity), the generalised tiled search, the sharded job and rate control on the clip path."""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ob():
+    from oracle import bindings as ob
+    return ob
+
+
+def _ctx(W, H, bs, r, qp, nref=1, fastme=False, frac=False, ip=1, lanes=1):
+    import basic_video_codec_b200 as bvc
+    return bvc.Context(W, H, bs, r, qp, nref, fastme, frac, ip, device=0, max_lanes=lanes)
+
+
+def test_resident_clip_is_invalidated_by_frame_calls():
+    """bvc_clip_upload -> frame-level call (overwrites plane 0 of the input pool) -> bvc_encode_clip_resident must refuse
+    instead of silently encoding the wrong frames; the same after a host-buffer clip call."""
+    W, H, bs, r, qp = 96, 64, 16, 8, 3
+    clip = synth.moving_clip(31, H, W, 6, step=3, clamp=16)
+    other = synth.moving_clip(32, H, W, 6, step=3, clamp=16)
+    with _ctx(W, H, bs, r, qp, ip=3, lanes=2) as ctx:
+        ctx.clip_upload(clip)
+        out, n = ctx.encode_clip_resident(6)
+        want = bytes(out[:n])
+        assert ctx.encode_clip(clip)[0] == want
+        # host path overwrote the pool (with `clip` again, but the library cannot know that)
+        with pytest.raises(ValueError):
+            ctx.encode_clip_resident(6)
+        ctx.clip_upload(clip)
+        ctx.encode_pframe(other[1], [other[0]])
+        with pytest.raises(ValueError):
+            ctx.encode_clip_resident(6)
+        ctx.clip_upload(clip)
+        out, n = ctx.encode_clip_resident(6)
+        assert bytes(out[:n]) == want
+
+
+def test_iframe_wavefront_grid_beyond_resident_capacity():
+    """32 I frames of 64 x 6000 with 4x4 blocks: 1500 block rows x 4 lane groups of the wavefront = 6000 one-warp CTAs,
+    more than the 148 x 32 the GPU can hold at once.  Rows are claimed by start-order tickets, so a waiting row's
+    producer is always resident; the streams and reconstructions must equal the oracle's, and the decoder's wavefront
+    (same scheme) must give the reconstruction back."""
+    ob = _ob()
+    W, H, bs, qp, n = 64, 6000, 4, 2, 32
+    base = synth.moving_clip(77, 600, W, n, step=2, clamp=8)
+    frames = np.ascontiguousarray(np.tile(base, (1, 10, 1)))
+    cfg = ob.make_config(W, H, bs, 1, qp, nref=1, i_period=1)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    with _ctx(W, H, bs, 1, qp, ip=1, lanes=n) as ctx:
+        for groups in (1, 2):
+            ctx.set_lane_groups(groups)
+            data, recon = ctx.encode_clip(frames, want_recon=True)
+            assert data == want
+            assert np.array_equal(recon, want_recon)
+        assert np.array_equal(ctx.decode_clip(data, n), recon)
+
+
+# ---- generalised search kernels: every (i, r), integer and half-pel ------------------------------------------------------
+# narrow kernel (2r < i), tiled kernel with a padded vertical range (2r >= i, 2r % i != 0), tiled exact (2r % i == 0)
+GEN_ME_CASES = [(bs, r, frac) for bs in (4, 8, 16) for r in (1, 2, 3, 5, 7) for frac in (False, True)] + \
+               [(16, 4, False), (16, 4, True), (16, 6, False), (16, 12, False), (16, 12, True), (8, 9, False), (8, 6, True), (4, 9, False)]
+
+
+@pytest.mark.parametrize("bs,r,frac", GEN_ME_CASES)
+def test_generalised_search_matches_oracle(bs, r, frac):
+    """Frames of 176 x 144 (QCIF: 1.4 tiles of the narrow kernel side by side, 2.25 stacked at i=16), two references,
+    moving and tie-heavy content: motion vectors, reference indices and SADs of every block against the oracle."""
+    ob = _ob()
+    W, H, nref = 176, 144, 2
+    for content in ("moving", "poster"):
+        clip = (synth.moving_clip(300 + bs + r, H, W, nref + 1, step=min(r, 5), clamp=16) if content == "moving"
+                else synth.posterised_clip(400 + bs + r, H, W, nref + 1))
+        cur, refs = clip[-1], [clip[i] for i in range(nref)]
+        cfg = ob.make_config(W, H, bs, r, 3, nref=nref, frac=frac)
+        planes = [ob.halfpel_plane(x) for x in refs] if frac else refs
+        mv_o, sad_o, cmp_o = ob.me_frame(cfg, cur, planes)
+        with _ctx(W, H, bs, r, 3, nref, False, frac) as ctx:
+            mv_g, sad_g, cmp_g = ctx.me_search(cur, refs)
+        assert np.array_equal(sad_g, sad_o), content
+        assert np.array_equal(mv_g, mv_o), content
+        assert cmp_g == cmp_o
+
+
+def test_config3_geometry_cif_halfpel_r4_clip_matches_oracle():
+    """BASELINE configs[2] geometry (CIF, i=16, r=4, half-pel) through the clip call: 2 GOPs of 4 frames in lanes."""
+    ob = _ob()
+    W, H, bs, r, qp = 352, 288, 16, 4, 4
+    frames = synth.moving_clip(352, H, W, 8, step=3, clamp=16)
+    cfg = ob.make_config(W, H, bs, r, qp, nref=2, frac=True, i_period=4)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    with _ctx(W, H, bs, r, qp, 2, False, True, ip=4, lanes=2) as ctx:
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+    assert np.array_equal(recon, want_recon)
+    assert data == want
+
+
+def test_tail_split_many_lanes_matches_oracle(monkeypatch):
+    """110 GOP lanes of 128 x 192 frames (i=16, r=16): 660 search tiles per step, more than the GPU holds at once (592 at
+    four 160-thread CTAs per SM), so the tiles of the last wave run as one-row CTAs.  Stream equal to the oracle's and
+    to the unsplit launch."""
+    ob = _ob()
+    W, H, bs, r, qp, ip, ngop = 128, 192, 16, 16, 4, 2, 110
+    base = synth.moving_clip(61, H, W, 8, step=5, clamp=24)
+    frames = np.ascontiguousarray(np.concatenate([np.roll(base[(2 * g) % 6: (2 * g) % 6 + 2], g, axis=2) for g in range(ngop)]))
+    cfg = ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip)
+    want, _ = ob.encode_clip(cfg, frames, want_recon=False)
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=ngop) as ctx:
+        ctx.set_lane_groups(1)
+        assert ctx.encode_clip(frames)[0] == want
+    monkeypatch.setenv("BVC_TAIL_SPLIT", "0")
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=ngop) as ctx:
+        ctx.set_lane_groups(1)
+        assert ctx.encode_clip(frames)[0] == want
