@@ -15,6 +15,7 @@ EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
     "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420", "bvc_set_fastme_direct",
+    "bvc_encode_clip_device", "bvc_container_download", "bvc_host_register", "bvc_host_unregister", "bvc_measure_peaks",
 ]
 
 
@@ -82,6 +83,11 @@ def load_library():
     L.bvc_last_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.bvc_me_work_per_frame.argtypes = [C.c_void_p, C.c_int]
     L.bvc_me_work_per_frame.restype = C.c_int64
+    L.bvc_encode_clip_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.bvc_container_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.bvc_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.bvc_host_unregister.argtypes = [C.c_void_p]
+    L.bvc_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _LIB = L
     return L
 
@@ -344,6 +350,30 @@ class Context:
         self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
         return out, int(ln.value)
 
+    # ---- sharded jobs: container left on the device, fetched into a caller-chosen place ----------------
+    def encode_clip_device(self, frames, nframes=None, cap_hint=0):
+        """Encode `frames` (host array) or, with frames=None, the first `nframes` resident frames; the container stays in
+        device memory.  Returns its length; fetch it with container_download()."""
+        ln = C.c_size_t(0)
+        if frames is not None:
+            frames = self._check_clip(frames)
+            nframes = frames.shape[0]
+        for _ in range(2):
+            rc = self._L.bvc_encode_clip_device(self._h, _p(frames), int(nframes), int(cap_hint), C.byref(ln))
+            if rc == BVC_ERR_NOMEM and int(ln.value) > cap_hint:
+                cap_hint = int(ln.value)
+                continue
+            break
+        self._check(rc)
+        return int(ln.value)
+
+    def container_download(self, dst, dst_offset=0, offset=0, length=None):
+        """Copy bytes [offset, offset+length) of the last container into the uint8 array `dst` at dst_offset."""
+        if length is None:
+            length = dst.size - dst_offset
+        self._check_buffer(dst, dst_offset + length, "dst")
+        self._check(self._L.bvc_container_download(self._h, C.c_void_p(dst.ctypes.data + int(dst_offset)), int(offset), int(length)))
+
     # ---- instrumentation -----------------------------------------------------------------------
     def set_lane_groups(self, groups: int):
         """Lane groups of the clip path (bvc_set_lane_groups): 1 = serial, default 2."""
@@ -387,3 +417,28 @@ def dct_quant_recon(residual, pred, qp, device=0):
     if rc != BVC_OK:
         _raise(rc, L.bvc_last_error(None).decode())
     return level, recon, idct, coef
+
+
+def host_register(arr):
+    """Page-lock the memory of a numpy array the caller keeps alive (bvc_host_register)."""
+    L = load_library()
+    rc = L.bvc_host_register(C.c_void_p(arr.ctypes.data), arr.nbytes)
+    if rc != BVC_OK:
+        _raise(rc, L.bvc_last_error(None).decode())
+
+
+def host_unregister(arr):
+    L = load_library()
+    L.bvc_host_unregister(C.c_void_p(arr.ctypes.data))
+
+
+def measure_peaks(device=0):
+    """Issue-rate ceilings measured on `device` right now: {"vabsdiff4_thread_ops_per_s", "px_absdiff_per_s",
+    "dfma_thread_ops_per_s", "sm_count"} (bvc_measure_peaks)."""
+    L = load_library()
+    v, f, n = C.c_double(0), C.c_double(0), C.c_int(0)
+    rc = L.bvc_measure_peaks(int(device), C.byref(v), C.byref(f), C.byref(n))
+    if rc != BVC_OK:
+        _raise(rc, "bvc_measure_peaks failed (no usable CUDA device)")
+    return {"vabsdiff4_thread_ops_per_s": v.value, "px_absdiff_per_s": 4.0 * v.value, "dfma_thread_ops_per_s": f.value,
+            "sm_count": n.value}

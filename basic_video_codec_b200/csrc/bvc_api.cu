@@ -111,6 +111,7 @@ struct bvc_ctx {
     int64_t last_launches[BVC_NUM_KERNEL_CLASSES] = {0, 0, 0, 0, 0};
     double last_clip_ms = 0;
     int resident_frames = 0;
+    size_t container_len = 0;   // bytes of the container the last clip call left in d_container
     // row-by-row (rate control) state
     bool row_open = false, row_intra = false;
     int row_nref = 0, row_next = 0;
@@ -536,7 +537,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.nphase = c->p.frac_me ? 4 : 1;
         m.R = c->p.search_range;
         m.Rh = c->p.search_range * m.sc;
-        m.tail_split = c->tail_split;
+        m.tail_split = c->tail_split && st_post == st_me;   // with lane groups the other group's kernels fill the tail
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
             int rcf = launch_fastme_any(c, m, nl, L0, st_me, sp.nl);
@@ -1222,11 +1223,13 @@ extern "C" int bvc_clip_upload_i420(bvc_ctx* c, const uint8_t* yuv, int src_w, i
     return BVC_OK;
 }
 
+// out == nullptr: the container stays on the device (bvc_encode_clip_device), out_cap is then the device capacity
 static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
-                            uint8_t* recon) {
+                            uint8_t* recon, bool keep_on_device = false) {
     const Geom& g = c->g;
     CK(cudaSetDevice(c->device));
-    if (nframes < 1 || !out || !out_len) return fail(c, BVC_ERR_INVALID, "bad arguments");
+    c->container_len = 0;
+    if (nframes < 1 || (!out && !keep_on_device) || !out_len) return fail(c, BVC_ERR_INVALID, "bad arguments");
     const int IP = c->p.i_period, G = c->max_lanes;
     const int ngop = (nframes + IP - 1) / IP;
     const int nwaves = (ngop + G - 1) / G;
@@ -1390,10 +1393,11 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         *out_len = (size_t)total;   // what the caller has to provide
         return fail(c, BVC_ERR_NOMEM, "output buffer too small (*out_len = bytes needed)");
     }
-    CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
+    if (!keep_on_device) CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
     CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st));
     *out_len = (size_t)total;
+    c->container_len = (size_t)total;
 
     // ---- instrumentation ----
     for (int i = 0; i < BVC_NUM_KERNEL_CLASSES; i++) { c->last_ms[i] = 0; c->last_launches[i] = 0; }
@@ -1418,4 +1422,29 @@ extern "C" int bvc_encode_clip_resident(bvc_ctx* c, int nframes, uint8_t* out, s
     if (!c) return BVC_ERR_INVALID;
     if (nframes > c->resident_frames) return fail(c, BVC_ERR_INVALID, "clip not resident: call bvc_clip_upload first");
     return encode_clip_impl(c, nullptr, nframes, out, out_cap, out_len, recon);
+}
+
+extern "C" int bvc_encode_clip_device(bvc_ctx* c, const uint8_t* frames, int nframes, size_t cap_hint, size_t* out_len) {
+    if (!c) return BVC_ERR_INVALID;
+    if (!frames && nframes > c->resident_frames) return fail(c, BVC_ERR_INVALID, "clip not resident: call bvc_clip_upload first");
+    const size_t cap = cap_hint ? cap_hint : (size_t)nframes * c->g.W * c->g.H / 2 + ((size_t)1 << 20);
+    return encode_clip_impl(c, frames, nframes, nullptr, cap, out_len, nullptr, true);
+}
+extern "C" int bvc_container_download(bvc_ctx* c, uint8_t* dst, size_t offset, size_t len) {
+    if (!c || (!dst && len)) return BVC_ERR_INVALID;
+    if (offset > c->container_len || len > c->container_len - offset) return fail(c, BVC_ERR_INVALID, "range outside the container of the last clip call");
+    CK(cudaSetDevice(c->device));
+    if (len) CK(cudaMemcpyAsync(dst, c->d_container + offset, len, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return BVC_OK;
+}
+extern "C" int bvc_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return BVC_ERR_INVALID;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, BVC_ERR_CUDA, "cudaHostRegister failed"); }
+    return BVC_OK;
+}
+extern "C" int bvc_host_unregister(void* ptr) {
+    if (!ptr) return BVC_ERR_INVALID;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, BVC_ERR_CUDA, "cudaHostUnregister failed"); }
+    return BVC_OK;
 }

@@ -119,6 +119,19 @@ int bvc_encode_clip(bvc_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *o
 int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
 int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
                              uint8_t *recon);
+/* Sharded jobs (GOPs of one clip on several GPUs, encoder.py:174-186 makes them independent): the same
+ * encode, but the finished container stays in device memory and only its length comes back; bvc_container_download then
+ * copies bytes [offset, offset+len) of it to `dst` -- typically straight into this rank's slice of a host buffer shared by
+ * all ranks, once the ranks have exchanged their lengths, so the concatenated stream is written exactly once.
+ * frames == NULL encodes the resident clip (bvc_clip_upload).  cap_hint: device bytes to reserve for the container
+ * (0 = nframes * W * H / 2 + 1 MB); BVC_ERR_NOMEM with *out_len = the bytes needed when it does not fit. */
+int bvc_encode_clip_device(bvc_ctx *ctx, const uint8_t *frames, int nframes, size_t cap_hint, size_t *out_len);
+int bvc_container_download(bvc_ctx *ctx, uint8_t *dst, size_t offset, size_t len);
+/* Page-lock (cudaHostRegister) a host range the caller owns -- e.g. a POSIX shared-memory mapping -- so that uploads
+ * from it / downloads into it run at the link rate; bvc_host_unregister before unmapping. */
+int bvc_host_register(void *ptr, size_t bytes);
+int bvc_host_unregister(void *ptr);
+
 /* Input stage: like bvc_clip_upload, for an I420 (YUV 4:2:0 planar) file image of src_w x src_h frames.  Only the luma
  * planes are transferred (read_y_component, assign1/ex2.py:14-28) and they are padded bottom / right with 128 to the
  * context's width / height (pad_frame, common.py:22-32), which must be src_w / src_h rounded up to block_size. */
@@ -177,6 +190,10 @@ int64_t bvc_launch_count(const bvc_ctx *ctx);
 int bvc_last_kernel_times(const bvc_ctx *ctx, double *ms, int64_t *launches, double *clip_ms);
 /* algorithmic pixel-absdiffs (valid candidates * i*i * refs) of one P frame with `nref_avail` references */
 int64_t bvc_me_work_per_frame(const bvc_ctx *ctx, int nref_avail);
+/* Issue-rate ceilings of the device, measured now (dependent-free chains on every SM, best of five launches, CUDA
+ * events): VABSDIFF4.U8.ACC thread-ops/s (x4 = pixel-absdiffs/s, the search kernels' roofline) and DFMA thread-ops/s
+ * (the transform's).  Any pointer may be NULL. */
+int bvc_measure_peaks(int device, double *vabsdiff4_thread_ops_per_s, double *dfma_thread_ops_per_s, int *sm_count);
 
 #ifdef __cplusplus
 }

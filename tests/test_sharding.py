@@ -20,7 +20,9 @@ def _oracle_encode(frames, ec, device):
 def test_gop_maps():
     from basic_video_codec_b200 import sharding as sh
     assert sh.gop_ranges(10, 4) == [(0, 4), (4, 4), (8, 2)]
-    assert sh.assign_gops(5, 2) == [[0, 2, 4], [1, 3]]
+    assert sh.assign_gops(5, 2) == [[0, 1, 2], [3, 4]]      # contiguous runs: a rank's fragment is one slice of the stream
+    assert sh.assign_gops(20, 8) == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11], [12, 13], [14, 15], [16, 17], [18, 19]]
+    assert sh.assign_gops(2, 3) == [[0], [1], []]
     assert sh.scaling_ceiling(20, 8) == pytest.approx(20 / 3)   # 600 frames / I_Period 30 on 8 GPUs
     assert sh.scaling_ceiling(20, 4) == 4.0
 
@@ -49,7 +51,7 @@ def _worker(rank, world, port, q):
         touched.append(first)
         return frames[first:first + n]
 
-    out = sh.encode_clip_distributed(None, ec, rank=rank, world=world, encode_fn=_oracle_encode, load_gop=load, nframes=14)
+    out = sh.encode_clip_distributed(None, ec, rank=rank, world=world, encode_fn=_oracle_encode, load_gop=load, nframes=14, shape=(32, 48))
     q.put((rank, out, touched))
     dist.barrier()
     dist.destroy_process_group()
@@ -78,4 +80,4 @@ def test_two_ranks_gloo_concatenate_to_serial_stream():
     whole = _oracle_encode(frames, EncoderConfig(8, 2, 4, 3, nRefFrames=1), 0)
     assert res[0][0] == whole          # rank 0 holds the serial stream
     assert res[1][0] is None
-    assert res[0][1] == [0, 8] and res[1][1] == [4, 12]   # every rank only touched its own GOPs
+    assert res[0][1] == [0, 4] and res[1][1] == [8, 12]   # every rank only touched its own GOPs
