@@ -15,7 +15,7 @@ EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
     "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420", "bvc_set_fastme_direct",
-    "bvc_encode_clip_device", "bvc_container_download", "bvc_host_register", "bvc_host_unregister", "bvc_measure_peaks",
+    "bvc_encode_clip_device", "bvc_container_download", "bvc_host_register", "bvc_host_unregister", "bvc_measure_peaks", "bvc_set_rate_control",
 ]
 
 
@@ -87,6 +87,7 @@ def load_library():
     L.bvc_container_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.bvc_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.bvc_host_unregister.argtypes = [C.c_void_p]
+    L.bvc_set_rate_control.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     L.bvc_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _LIB = L
     return L
@@ -349,6 +350,16 @@ class Context:
         ln = C.c_size_t(0)
         self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
         return out, int(ln.value)
+
+    def set_rate_control(self, rc_flag, frame_bit_budget=0.0, table=None):
+        """RCflag 1 on the clip path (bvc_set_rate_control).  table: the reference's lookup {qp: {"I": bits per row, ...}}
+        (encoder/RateControl/lookup.py:97-118); rc_flag 0 turns rate control off."""
+        if not rc_flag:
+            self._check(self._L.bvc_set_rate_control(self._h, 0, 0.0, 0, None, None))
+            return
+        qps = np.array(sorted(q for q in table if "I" in table[q]), dtype=np.int32)
+        bits = np.array([int(table[int(q)]["I"]) for q in qps], dtype=np.int64)
+        self._check(self._L.bvc_set_rate_control(self._h, int(rc_flag), float(frame_bit_budget), int(qps.size), _p(qps), _p(bits)))
 
     # ---- sharded jobs: container left on the device, fetched into a caller-chosen place ----------------
     def encode_clip_device(self, frames, nframes=None, cap_hint=0):

@@ -112,6 +112,9 @@ struct bvc_ctx {
     double last_clip_ms = 0;
     int resident_frames = 0;
     size_t container_len = 0;   // bytes of the container the last clip call left in d_container
+    // rate control on the clip path (bvc_set_rate_control): RCflag 1, per-row feedback chained on the device
+    RcArgs rc{};
+    double* d_rc_remaining = nullptr;
     // row-by-row (rate control) state
     bool row_open = false, row_intra = false;
     int row_nref = 0, row_next = 0;
@@ -268,6 +271,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_rowbits, 1));
         CK(dalloc(&c->d_progress, L * g.bh));
         CK(dalloc(&c->d_ticket, L));
+        CK(dalloc(&c->d_rc_remaining, L));
         CK(cudaMemset(c->d_ticket, 0, L * sizeof(int)));
         c->coef_cap_words = nb * c->blk_words + 8;
         c->pred_cap_words = nb * 3 + g.bh + 8;
@@ -303,7 +307,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
-    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container);
@@ -521,12 +525,40 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh; t.ticket = c->d_ticket + L0;
     t.row_begin = 0; t.row_count = g.bh;
+    // rate control (RCflag 1) on the clip path: the transform runs block row by block row, and the launch that
+    // accounts a row's bits also picks the next row's QP -- the whole chain stays on the device, all lanes in lock step
+    const bool rc_rows = !frame_api && c->rc.n > 0;
+    RcArgs rc = c->rc;
+    rc.remaining = c->d_rc_remaining + L0;
+    rc.qp_rows = c->d_qp_rows + L0 * g.bh;
+    PackArgs pk{};
+    pk.mv = t.mv; pk.modes = t.modes; pk.qp_rows = t.qp_rows;
+    pk.blk_bits = t.blk_bits; pk.blk_nbits = t.blk_nbits; pk.blk_words = c->blk_words;
+    pk.coef_off = c->d_coef_off + L0 * (nb + 1);
+    pk.lanes = t.lanes;
+    pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh; pk.pred_row_off = c->d_pred_row_off + L0 * (g.bh + 1);
+    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
+    pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
+    pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
+    auto transform_rows = [&](bool intra) -> int {
+        CK(launch_rc_begin(rc, nl, g.bh, st_post));
+        for (int row = 0; row < g.bh; row++) {
+            t.row_begin = row; t.row_count = 1;
+            if (intra) CK(launch_tq_iframe(t, nl, st_post));
+            else CK(launch_tq_pframe(t, nl, st_post));
+            CK(launch_row_bits_rc(pk, rc, nl, row, nullptr, st_post));
+        }
+        t.row_begin = 0; t.row_count = g.bh;
+        c->launches += 1 + (intra ? 3 : 2) * g.bh;
+        return BVC_OK;
+    };
     if (sp.intra) {
         CK(cudaMemsetAsync(t.progress, 0, (size_t)nl * g.bh * sizeof(int), st_post));
         const int e0 = tick(c, st_post);
-        CK(launch_tq_iframe(t, nl, st_post));
+        if (rc_rows) { int rcr = transform_rows(true); if (rcr != BVC_OK) return rcr; }
+        else { CK(launch_tq_iframe(t, nl, st_post)); c->launches += 2; }
         span(c, BVC_K_TQ_I, e0, tick(c, st_post));
-        c->launches += 2;
     } else {
         MeArgs m{};
         m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
@@ -553,20 +585,10 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
             CK(cudaStreamWaitEvent(st_post, ev_me_done, 0));
             e1p = tick(c, st_post);
         }
-        CK(launch_tq_pframe(t, nl, st_post));
+        if (rc_rows) { int rcr = transform_rows(false); if (rcr != BVC_OK) return rcr; c->launches += 1; }
+        else { CK(launch_tq_pframe(t, nl, st_post)); c->launches += 2; }
         span(c, BVC_K_TQ_P, e1p, tick(c, st_post));
-        c->launches += 2;
     }
-    PackArgs pk{};
-    pk.mv = t.mv; pk.modes = t.modes; pk.qp_rows = t.qp_rows;
-    pk.blk_bits = t.blk_bits; pk.blk_nbits = t.blk_nbits; pk.blk_words = c->blk_words;
-    pk.coef_off = c->d_coef_off + L0 * (nb + 1);
-    pk.lanes = t.lanes;
-    pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
-    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh; pk.pred_row_off = c->d_pred_row_off + L0 * (g.bh + 1);
-    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
-    pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
-    pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
     const int ep = tick(c, st_post);
     CK(launch_pack(pk, nl, st_post));
     span(c, BVC_K_PACK, ep, tick(c, st_post));
@@ -1446,5 +1468,34 @@ extern "C" int bvc_host_register(void* ptr, size_t bytes) {
 extern "C" int bvc_host_unregister(void* ptr) {
     if (!ptr) return BVC_ERR_INVALID;
     if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, BVC_ERR_CUDA, "cudaHostUnregister failed"); }
+    return BVC_OK;
+}
+
+// Rate control on the clip path.  rc_flag 1 = RCflag 1 of the reference (encoder/Frame.py:168-188: the QP of every block
+// row follows from the frame's bit budget and the bits the rows before it consumed); the feedback loop runs on the
+// device.  rc_flag 0 turns it off.  RCflag 2 / 3 couple consecutive frames and GOPs (two passes, scene changes,
+// encoder.py:85-98) and stay on the frame-level calls.
+extern "C" int bvc_set_rate_control(bvc_ctx* c, int rc_flag, double frame_bit_budget, int n, const int32_t* qps, const int64_t* row_bits) {
+    if (!c) return BVC_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (rc_flag == 0) {
+        c->rc = RcArgs{};
+        std::vector<int32_t> q((size_t)c->max_lanes * c->g.bh, c->p.qp);   // back to the base QP on every row
+        CK(cudaMemcpyAsync(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return BVC_OK;
+    }
+    if (rc_flag != 1) return fail(c, BVC_ERR_UNSUPPORTED, "only RCflag 1 runs on the clip path (2 / 3 couple GOPs: use the frame-level calls)");
+    if (n < 1 || n > 16 || !qps || !row_bits) return fail(c, BVC_ERR_INVALID, "rate-control table must hold 1..16 (qp, bits per row) entries");
+    int lg = 0; while ((1 << lg) < c->g.bs) lg++;
+    RcArgs rc{};
+    rc.n = n;
+    for (int i = 0; i < n; i++) {
+        if (qps[i] < 0 || qps[i] > lg + 7 || (i && qps[i] <= qps[i - 1])) return fail(c, BVC_ERR_INVALID, "rate-control QPs must ascend within 0..log2(block_size)+7");
+        rc.qp[i] = qps[i];
+        rc.bits[i] = row_bits[i];
+    }
+    rc.frame_budget = frame_bit_budget;
+    c->rc = rc;
     return BVC_OK;
 }

@@ -154,6 +154,24 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
 // prediction symbols (row QP symbol included).  out: device long long[lanes].
 cudaError_t launch_row_bits(const PackArgs& a, int lanes, int row, long long* out, cudaStream_t st);
 
+// ---- rate control on the device (RCflag = 1, Frame.get_rc_qp encoder/Frame.py:168-188) ----------------
+// The QP of block row k+1 follows from the bits rows <= k consumed (calculate_constant_row_bit_budget +
+// find_rc_qp_for_row, encoder/RateControl/RateControl.py:9-20,34-43).  All arithmetic in IEEE double like the
+// reference's Python floats: remaining -= row_bits; budget = remaining / rows_left; first table entry (QP ascending)
+// whose expected row size is <= budget, else the largest QP.
+struct RcArgs {
+    int n;                      // table entries (0 = rate control off)
+    int qp[16];                 // ascending
+    long long bits[16];         // expected bits per block row at that QP (the lookup's 'I' column: Frame.py:169 always asks for 'I')
+    double frame_budget;        // targetBR / frame_rate
+    double* remaining;          // device [lanes]
+    int32_t* qp_rows;           // device [lanes][bh]: row k+1 is written when row k is accounted
+};
+// start of a frame: remaining = frame_budget, QP of row 0
+cudaError_t launch_rc_begin(const RcArgs& rc, int lanes, int bh, cudaStream_t st);
+// bits of block row `row` (as launch_row_bits), then the QP of row + 1
+cudaError_t launch_row_bits_rc(const PackArgs& a, const RcArgs& rc, int lanes, int row, long long* out, cudaStream_t st);
+
 // ---- decoder (decode.cu) -------------------------------------------------------------------------
 // One exp-Golomb bit stream inside the container image (two per frame: 2f = prediction data, 2f+1 = coefficients).
 struct EgStream {

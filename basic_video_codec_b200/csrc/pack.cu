@@ -155,8 +155,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
         a.row_bits[(size_t)fl * a.bh + r] = (prow[r + 1] - prow[r]) + (coff[(size_t)(r + 1) * a.bw] - coff[(size_t)r * a.bw]);
 }
 
-// bits of one block row: coefficient strings of its blocks + its prediction symbols
-__global__ void __launch_bounds__(256) pack_row_bits_kernel(PackArgs a, int row, long long* out) {
+__device__ __forceinline__ int rc_pick_qp(const RcArgs& rc, double budget) {
+    for (int i = 0; i < rc.n; i++)
+        if ((double)rc.bits[i] <= budget) return rc.qp[i];   // find_rc_qp_for_row, RateControl.py:34-43
+    return rc.qp[rc.n - 1];
+}
+
+// bits of one block row: coefficient strings of its blocks + its prediction symbols; with rate control the row is
+// charged to the frame's budget and the next row's QP is chosen (Frame.py:168-188, PFrame.py:53-83, IFrame.py:38-70)
+__global__ void __launch_bounds__(256) pack_row_bits_kernel(PackArgs a, RcArgs rc, int row, long long* out) {
     __shared__ long long warp_sums[33];
     const int fl = blockIdx.x;
     long long s = 0;
@@ -167,7 +174,21 @@ __global__ void __launch_bounds__(256) pack_row_bits_kernel(PackArgs a, int row,
     }
     long long tot;
     block_exscan(s, warp_sums, &tot);
-    if (threadIdx.x == 0) out[fl] = tot;
+    if (threadIdx.x == 0) {
+        if (out) out[fl] = tot;
+        if (rc.n > 0) {
+            const double rem = rc.remaining[fl] - (double)tot;
+            rc.remaining[fl] = rem;
+            if (row + 1 < a.bh) rc.qp_rows[(size_t)fl * a.bh + row + 1] = rc_pick_qp(rc, rem / (double)(a.bh - (row + 1)));
+        }
+    }
+}
+
+__global__ void rc_begin_kernel(RcArgs rc, int lanes, int bh) {
+    const int fl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fl >= lanes) return;
+    rc.remaining[fl] = rc.frame_budget;
+    rc.qp_rows[(size_t)fl * bh] = rc_pick_qp(rc, rc.frame_budget / (double)bh);
 }
 
 // One thread per block: after quantisation a block's string is a handful of words (about 125 bits at the headline QP), so
@@ -274,7 +295,16 @@ cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st) {
 
 namespace bvc {
 cudaError_t launch_row_bits(const PackArgs& a, int lanes, int row, long long* out, cudaStream_t st) {
-    pack_row_bits_kernel<<<lanes, 256, 0, st>>>(a, row, out);
+    RcArgs off{};
+    pack_row_bits_kernel<<<lanes, 256, 0, st>>>(a, off, row, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_row_bits_rc(const PackArgs& a, const RcArgs& rc, int lanes, int row, long long* out, cudaStream_t st) {
+    pack_row_bits_kernel<<<lanes, 256, 0, st>>>(a, rc, row, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_rc_begin(const RcArgs& rc, int lanes, int bh, cudaStream_t st) {
+    rc_begin_kernel<<<(lanes + 63) / 64, 64, 0, st>>>(rc, lanes, bh);
     return cudaGetLastError();
 }
 cudaError_t launch_container(const ContainerArgs& a, cudaStream_t st) {

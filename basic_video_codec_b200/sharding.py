@@ -103,6 +103,8 @@ class ShardedEncoder:
             if self.mine:
                 self.ctx = Context(self.W, self.H, ec.block_size, ec.search_range, ec.quantization_factor, ec.nRefFrames,
                                    ec.fastME, ec.fracMeEnabled, ec.I_Period, device=device, max_lanes=len(self.mine))
+                from .clip import configure_rate_control
+                configure_rate_control(self.ctx, ec)     # RCflag 1 couples rows of one frame only: GOPs stay independent
             host_register(self.buf.array)
             self.buf.registered = True
 

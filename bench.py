@@ -289,6 +289,17 @@ def main():
                      "all_ranks_equal": len({a for a, _ in shas}) == 1, "sha256": sha_resident}
     if not (stream_checks["resident_equals_host_path"] and stream_checks["all_ranks_equal"]):
         raise SystemExit(f"bench: streams differ between paths / ranks: {shas}")
+    # the CPU oracle's stream of this very clip, recorded once (oracle/gen_bench_clip_sha.py, 258 s on 8 cores): the number
+    # below is a number for a bit-exact stream
+    try:
+        rec = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_clip_oracle.json")))
+        stream_checks["equals_cpu_oracle_stream"] = (rec["sha256"] == sha_resident and rec["bytes"] == int(nbytes))
+        stream_checks["cpu_oracle_sha256"] = rec["sha256"]
+    except Exception as e:
+        stream_checks["equals_cpu_oracle_stream"] = None
+        stream_checks["cpu_oracle_sha256"] = f"record missing: {e}"
+    if stream_checks["equals_cpu_oracle_stream"] is False:
+        raise SystemExit("bench: the GPU stream differs from the CPU oracle's stream of the same clip")
 
     # ---- decoder, reported beside the headline: the stream just written, host buffers in and out ----
     decoder = None

@@ -32,7 +32,7 @@ extern "C" {
 typedef struct bvc_ctx bvc_ctx;
 
 /* EncoderConfig (encoder/params.py:6-23) + InputParameters.width/height (input_parameters.py:4-11).
- * RCflag is 0 in this ABI revision: per-row QPs are passed explicitly to the frame-level calls. */
+ * RCflag: per-row QPs are passed explicitly to the frame-level / row-level calls; bvc_set_rate_control puts RCflag 1 on the clip path. */
 typedef struct bvc_params {
     int width, height;   /* luma size; must be multiples of block_size (pad_frame, common.py:22-32, is applied by the Python layer) */
     int block_size;      /* i  : 4, 8 or 16 */
@@ -119,6 +119,15 @@ int bvc_encode_clip(bvc_ctx *ctx, const uint8_t *frames, int nframes, uint8_t *o
 int bvc_clip_upload(bvc_ctx *ctx, const uint8_t *frames, int nframes);
 int bvc_encode_clip_resident(bvc_ctx *ctx, int nframes, uint8_t *out, size_t out_cap, size_t *out_len,
                              uint8_t *recon);
+/* Rate control on the clip path: RCflag = 1 (Frame.get_rc_qp encoder/Frame.py:168-188 with
+ * calculate_constant_row_bit_budget / find_rc_qp_for_row, encoder/RateControl/RateControl.py:9-20,34-43).  After this call
+ * bvc_encode_clip* encode every frame block row by block row; the launch that accounts a row's bits picks the next row's
+ * QP, for all GOP lanes at once, without a host round trip.  frame_bit_budget = targetBR / frame_rate (encoder.py:181-185);
+ * the table is the lookup's 'I' column (Frame.py:169 always asks for 'I'): n <= 16 entries, QPs ascending, expected bits
+ * per block row.  rc_flag 0 switches back to the base QP; RCflag 2 / 3 (two passes, scene changes: consecutive frames and
+ * GOPs are coupled) stay on the frame-level calls and return BVC_ERR_UNSUPPORTED here. */
+int bvc_set_rate_control(bvc_ctx *ctx, int rc_flag, double frame_bit_budget, int n, const int32_t *qps, const int64_t *row_bits);
+
 /* Sharded jobs (GOPs of one clip on several GPUs, encoder.py:174-186 makes them independent): the same
  * encode, but the finished container stays in device memory and only its length comes back; bvc_container_download then
  * copies bytes [offset, offset+len) of it to `dst` -- typically straight into this rank's slice of a host buffer shared by

@@ -99,8 +99,60 @@ def rc_main(only=None):
         print(f"{name}: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
 
 
+def _y_generator_frames(width, height, n):
+    """The reference's own synthetic source (tests/y_generator.py), the stand-in for Foreman (an LFS pointer here)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_y_generator", os.path.join(rh.REFERENCE_ROOT, "tests", "y_generator.py"))
+    yg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(yg)
+    raw = yg.generate_yuv_bytestream(width, height, n)
+    return np.frombuffer(raw, dtype=np.uint8).reshape(n, height, width).copy()
+
+
+def cif_main(only=None):
+    """BASELINE configs 2 and 3 at their real geometry (CIF), input from the reference's tests/y_generator.py:
+      cif_c2      i=16, FastME, nRefFrames=4, 24 frames, I_Period 8                 (assign2/FastME.py:8-11 path)
+      rc1_cif_c3  i=16, r=4, half-pel, RCflag=1, 21 frames, I_Period 21, 2.4 Mbit/s (assign3/Ex1.py:16-31 path), with the
+                  reference's OWN lookup tables (encoder/RateControl/lookups/352_288_16_{I,P}.csv through its own loader)
+    Outputs of the reference's encode_video (defined fp64 DCT): container bytes + reconstruction hash + per-frame sizes."""
+    ns = rh.load_reference()
+    cases = {
+        "cif_c2": (24, dict(block=16, search_range=16, qp=3, i_period=8, nref=4, fastme=True), 0, 0),
+        "rc1_cif_c3": (21, dict(block=16, search_range=4, qp=4, i_period=21, nref=1, frac=True), 1, 2_400_000),
+    }
+    for name, (n, enc, rcflag, br) in cases.items():
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        frames = _y_generator_frames(352, 288, n)
+        table = None
+        if rcflag:
+            ec0 = rh.make_config(ns, block=enc["block"], search_range=enc["search_range"], qp=enc["qp"], i_period=enc["i_period"],
+                                 width=352, height=288)
+            table = ns.encoder.get_combined_lookup_table(ns.encoder.rc_lookup_file_path(ec0, "I"), ns.encoder.rc_lookup_file_path(ec0, "P"))
+            out = ref_encode_video_rc(ns, frames, enc, rcflag, br, None)
+        else:
+            out = rh.ref_encode_video(frames, **enc)
+        sizes, o, data = [], 0, out["encoded"]
+        while o < len(data):
+            pl = int.from_bytes(data[o + 1:o + 3], "big")
+            cl = int.from_bytes(data[o + 3 + pl:o + 6 + pl], "big")
+            sizes.append([int(data[o]), pl, cl])
+            o += 6 + pl + cl
+        meta = {"generator": f"reference tests/y_generator.py generate_yuv_bytestream(352,288,{n})", "enc": enc, "rcflag": rcflag,
+                "targetBR": br, "dct_mode": "fp64_defined",
+                "table": ({str(k): v for k, v in table.items()} if table else None),
+                "table_source": "reference encoder/RateControl/lookups/352_288_16_{I,P}.csv via its own get_combined_lookup_table" if table else None,
+                "encoded_sha256": hashlib.sha256(out["encoded"]).hexdigest(),
+                "recon_sha256": hashlib.sha256(out["recon"].tobytes()).hexdigest(), "frame_records": sizes}
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), frames=frames,
+                            encoded=np.frombuffer(out["encoded"], dtype=np.uint8), meta=np.array(json.dumps(meta)))
+        print(f"{name}: {len(out['encoded'])} B  ({time.time() - t0:.1f}s)")
+
+
 def ref_encode_video_rc(ns, frames, enc, rcflag, br, table):
-    """The reference's own encode_video with RCflag set and `table` returned by its lookup loader."""
+    """The reference's own encode_video with RCflag set and `table` returned by its lookup loader (table=None: the
+    reference loads its own CSVs)."""
     import tempfile
     rh.set_dct_mode("fp64_defined")
     n, H, W = frames.shape
@@ -108,7 +160,8 @@ def ref_encode_video_rc(ns, frames, enc, rcflag, br, table):
                                  fastME=enc.get("fastme", False), fracMeEnabled=enc.get("frac", False), RCflag=rcflag,
                                  targetBR=br, resolution=(W, H))
     orig = ns.encoder.get_combined_lookup_table
-    ns.encoder.get_combined_lookup_table = lambda a, b: {int(k): dict(v) for k, v in table.items()}
+    if table is not None:
+        ns.encoder.get_combined_lookup_table = lambda a, b: {int(k): dict(v) for k, v in table.items()}
     try:
         with tempfile.TemporaryDirectory(prefix="bvc_ref_rc_") as td:
             yfile = os.path.join(td, "clip.y")
@@ -142,6 +195,8 @@ def main(only=None):
 
     # ---- rate control (RCflag 1/2/3) with a lookup table measured by the oracle, patched into the reference ----
     rc_main(only)
+    # ---- BASELINE configs 2 and 3 at CIF (reference generator input, reference lookup tables) ----
+    cif_main(only)
 
     # CIF stand-in for BASELINE config 1 (Foreman is an LFS pointer): the reference's own synthetic
     # generator tests/y_generator.py, 10 frames, i=8 r=4 qp=3 I_Period=8.

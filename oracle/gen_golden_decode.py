@@ -52,19 +52,15 @@ def main(only=None):
             continue
         g = gu.load(name)
         meta = g["meta"]
-        if "recon" in g:
-            recon = g["recon"]
-        else:   # cif_c1 stores only the hash of the reconstruction; rebuild it with the oracle encoder (checked against the hash)
-            from oracle import bindings as ob
-            e = meta["enc"]
-            n, H, W = g["frames"].shape
-            cfg = ob.make_config(W, H, e["block"], e["search_range"], e["qp"], nref=e.get("nref", 1), i_period=e["i_period"])
-            _, recon = ob.encode_clip(cfg, g["frames"], nthreads=2)
-            assert hashlib.sha256(recon.tobytes()).hexdigest() == meta["recon_sha256"]
+        n, H, W = g["frames"].shape
+        # goldens that store only the hash of the reconstruction: the reference decoder reads mc_reconstructed.yuv for a
+        # PSNR log line only, so zeros do; the decoded planes are then compared with the stored hash
+        recon = g["recon"] if "recon" in g else np.zeros((n, H, W), np.uint8)
         t0 = time.time()
         dec = ref_decode_video(ns, g["encoded"], recon, meta["enc"], meta.get("rcflag", 0), meta.get("targetBR", 0))
         res[name] = {"frames": int(dec.shape[0]), "decoded_sha256": hashlib.sha256(dec.tobytes()).hexdigest(),
-                     "equals_encoder_recon": bool(np.array_equal(dec, recon))}
+                     "equals_encoder_recon": bool(np.array_equal(dec, recon)) if "recon" in g
+                     else hashlib.sha256(dec.tobytes()).hexdigest() == meta["recon_sha256"]}
         print(f"{name}: {res[name]}  ({time.time() - t0:.1f}s)", flush=True)
         json.dump(res, open(OUT, "w"), indent=1, sort_keys=True)
 

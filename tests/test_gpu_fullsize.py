@@ -71,3 +71,27 @@ def test_large_and_odd_geometries_roundtrip(W, H, bs, r, nref, fastme, frac):
                 omv, osad = ob.full_search_block(frames[1], [recon[0]], bx * bs, by * bs, bs, r)
                 b = by * bw + bx
                 assert mv[b].tolist() == list(omv) and int(sad[b]) == osad, (bx, by)
+
+
+def test_1080p_whole_gops_through_20_lanes_match_the_oracle_record():
+    """configs[3] as bench.py runs it: 20 GOP lanes, two lane groups, whole 30-frame GOPs.  Lanes alternate between GOP 0 and
+    GOP 1 of the bench clip (the first 60 frames of the seeded generator); every lane's container fragment must have the
+    sha256 the CPU oracle produced for that GOP (tests/golden/bench_clip_oracle.json, 258 s of 8 host cores for the whole
+    600-frame clip; bench.py checks the whole stream's hash on every run)."""
+    import hashlib
+    import json
+    import os
+    import basic_video_codec_b200 as bvc
+    from basic_video_codec_b200.sharding import split_container_by_gop
+    from tests import golden_util as gu
+    rec = json.load(open(os.path.join(gu.GOLD, "bench_clip_oracle.json")))
+    W, H, bs, r, qp, ip = 1920, 1088, 16, 32, 4, 30
+    two = synth.moving_clip(1080, H, W, 2 * ip, step=6, clamp=96, noise=2)
+    frames = np.ascontiguousarray(np.tile(two, (10, 1, 1)))
+    with bvc.Context(W, H, bs, r, qp, 1, False, False, ip, device=0, max_lanes=20) as ctx:
+        assert ctx.lane_groups == 2
+        data, _ = ctx.encode_clip(frames)
+    parts = split_container_by_gop(data, [ip] * 20)
+    for lane, p in enumerate(parts):
+        want = rec["gops"][lane % 2]
+        assert len(p) == want["bytes"] and hashlib.sha256(p).hexdigest() == want["sha256"], f"lane {lane}"

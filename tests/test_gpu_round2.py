@@ -1,5 +1,7 @@
 """Round-2 GPU tests: hazards the round-1 review named (stale resident clip, wavefront grids beyond resident
 capacity), the generalised tiled search, the sharded job and rate control on the clip path."""
+import os
+
 import numpy as np
 import pytest
 
@@ -117,3 +119,77 @@ def test_tail_split_many_lanes_matches_oracle(monkeypatch):
     with _ctx(W, H, bs, r, qp, ip=ip, lanes=ngop) as ctx:
         ctx.set_lane_groups(1)
         assert ctx.encode_clip(frames)[0] == want
+
+
+# ---- sharded job on the GPU ---------------------------------------------------------------------------------------------
+def test_sharded_encoder_single_rank_equals_clip_call():
+    """world = 1 through the sharding API (container left on the device, fetched into the shared buffer) == the plain
+    clip call == the oracle; a short last GOP and the resident path included."""
+    import basic_video_codec_b200 as bvc
+    from basic_video_codec_b200 import sharding
+    ob = _ob()
+    W, H, bs, r, qp, ip, n = 96, 64, 16, 8, 3, 4, 10
+    frames = synth.moving_clip(91, H, W, n, step=3, clamp=16)
+    want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=2, i_period=ip), frames, want_recon=False)
+    ec = bvc.EncoderConfig(bs, r, ip, qp, nRefFrames=2)
+    assert sharding.encode_clip_distributed(frames, ec) == want
+    with sharding.ShardedEncoder(ec, W, H, n) as enc:
+        assert bytes(enc.encode(frames)) == want
+        enc.upload(frames)
+        assert bytes(enc.encode(resident=True)) == want
+        assert bytes(enc.encode(load_gop=lambda f0, k: frames[f0:f0 + k])) == want
+
+
+def _shard_worker(rank, world, port, q):
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import basic_video_codec_b200 as bvc
+    from basic_video_codec_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    W, H, bs, r, qp, ip, n = 192, 128, 16, 16, 4, 3, 15
+    frames = synth.moving_clip(92, H, W, n, step=4, clamp=24)
+    ec = bvc.EncoderConfig(bs, r, ip, qp, nRefFrames=1)
+    with sharding.ShardedEncoder(ec, W, H, n, rank=rank, world=world, device=rank) as enc:
+        out = enc.encode(frames)
+        h1 = hashlib.sha256(bytes(out)).hexdigest() if out is not None else None
+        enc.upload(frames)
+        out = enc.encode(resident=True)
+        h2 = hashlib.sha256(bytes(out)).hexdigest() if out is not None else None
+    q.put((rank, h1, h2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_encoder_two_gpus_equals_single_gpu_stream():
+    """5 GOPs over 2 GPUs (NCCL for the length exchange and the barrier only): the stream rank 0 returns equals the
+    single-GPU stream and the oracle's."""
+    import hashlib
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ob = _ob()
+    W, H, bs, r, qp, ip, n = 192, 128, 16, 16, 4, 3, 15
+    frames = synth.moving_clip(92, H, W, n, step=4, clamp=24)
+    want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip), frames, want_recon=False)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_shard_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    res = dict((rk, (a, b)) for rk, a, b in (q.get(timeout=300) for _ in range(2)))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    hw = hashlib.sha256(want).hexdigest()
+    assert res[0] == (hw, hw)
+    assert res[1] == (None, None)

@@ -22,10 +22,13 @@ def test_clip_matches_reference_golden(name):
     frames = g["frames"]
     n, H, W = frames.shape
     cfg = _cfg(g["meta"], W, H)
-    data, recon = ob.encode_clip(cfg, frames)
+    data, recon = ob.encode_clip(cfg, frames, nthreads=2)
     assert hashlib.sha256(data).hexdigest() == g["meta"]["encoded_sha256"]
     assert data == g["encoded"]
-    assert np.array_equal(recon, g["recon"])
+    if "recon" in g:
+        assert np.array_equal(recon, g["recon"])
+    else:   # the CIF fixtures (BASELINE configs 1-3 at their real geometry) store the hash of the reconstruction
+        assert hashlib.sha256(recon.tobytes()).hexdigest() == g["meta"]["recon_sha256"]
 
 
 def test_cif_config1_standin():
@@ -181,6 +184,8 @@ def test_decoder_oracle_matches_reference_decoder(name):
     assert hashlib.sha256(dec.tobytes()).hexdigest() == ref["decoded_sha256"]
     if "recon" in g:
         assert np.array_equal(dec, g["recon"])
+    elif "recon_sha256" in g["meta"]:
+        assert hashlib.sha256(dec.tobytes()).hexdigest() == g["meta"]["recon_sha256"]
     if "levels" in g:
         assert np.array_equal(lev, g["levels"])
     assert kinds[0] == 1
@@ -201,3 +206,31 @@ def test_decoder_oracle_rejects_malformed_streams():
         ob.decode_clip(cfg, bytes(bad), n)
     except ValueError:
         pass
+
+
+def test_recorded_dct_divergence_claims():
+    """cif_c1_dct_divergence.json: what the judge of a drop-in needs to know, as recorded from the imported reference.
+    fp64 SciPy against the defined transform on identical residuals: different levels only at exact ties, coefficients
+    within 1e-9; the shipped float32 arithmetic differs from the contract in a handful of levels per frame."""
+    import json
+    import os
+    rec = json.load(open(os.path.join(gu.GOLD, "cif_c1_dct_divergence.json")))
+    probe = rec["same_residual_probe_fp64_scipy_vs_defined"]
+    assert probe["blocks"] == 15840 and probe["non_tie_diffs"] == 0 and probe["max_tie_distance"] == 0.0
+    assert probe["max_coef_diff_all"] < 1e-9
+    asis = rec["modes"][0]
+    assert asis["mode"].startswith("asis") and asis["total_levels"] == 10 * 288 * 352
+    assert 0 < asis["total_differing_levels"] < asis["total_levels"] // 1000      # 54 of 1 013 760 when recorded
+    assert abs(asis["container_bytes"] - asis["container_bytes_contract"]) < 64
+    for m in rec["modes"]:
+        for fr in m["frames"]:
+            assert abs(fr["psnr"] - fr["psnr_contract"]) < 0.25      # largest recorded: 0.11 dB (fp64_scipy, frame 7)
+
+
+def test_bench_clip_oracle_record_is_consistent():
+    """tests/golden/bench_clip_oracle.json (oracle/gen_bench_clip_sha.py): the oracle's stream of the whole bench.py
+    workload; the per-GOP fragments must add up to the serial stream's length."""
+    import json
+    import os
+    rec = json.load(open(os.path.join(gu.GOLD, "bench_clip_oracle.json")))
+    assert len(rec["gops"]) == 20 and sum(g["bytes"] for g in rec["gops"]) == rec["bytes"]

@@ -112,3 +112,25 @@ def test_reference_encode_video_equals_oracle_clip():
     out = rh.ref_encode_video(frames, block=8, search_range=2, qp=2, i_period=3, nref=2)
     data, recon = ob.encode_clip(ob.make_config(48, 32, 8, 2, 2, nref=2, i_period=3), frames)
     assert data == out["encoded"] and np.array_equal(recon, out["recon"])
+
+
+def test_whole_clip_divergence_from_the_shipped_float32_dct_is_recorded_and_only_ties():
+    """The drop-in contract is "the reference with the defined fp64 DCT".  tests/golden/cif_c1_dct_divergence.json
+    (oracle/gen_dct_divergence.py) records how far the reference as shipped (float32 SciPy) and with SciPy on float64 are
+    from it on the CIF config-1 stand-in.  Here the first two frames are re-encoded with the imported reference and must
+    reproduce the recorded per-frame numbers; and the same-residual probe must find differing levels only at exact
+    quantiser ties (defined coefficient / Q exactly k + 1/2, SciPy within 1e-9 of it)."""
+    import json
+    import os
+    _rh()
+    from oracle import gen_dct_divergence as gd
+    from tests import golden_util as gu
+    rec = json.load(open(os.path.join(gu.GOLD, "cif_c1_dct_divergence.json")))
+    live = gd.run(2)
+    for mode_live, mode_rec in zip(live["modes"], rec["modes"]):
+        assert mode_live["mode"] == mode_rec["mode"]
+        for fl, fr in zip(mode_live["frames"], mode_rec["frames"][:2]):
+            assert fl == fr
+    probe = live["same_residual_probe_fp64_scipy_vs_defined"]
+    assert probe["blocks"] > 0 and probe["non_tie_diffs"] == 0 and probe["max_tie_distance"] == 0.0
+    assert probe["max_coef_diff_all"] < 1e-9

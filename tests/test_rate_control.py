@@ -26,7 +26,10 @@ def test_oracle_control_loop_matches_reference(name):
                          frac=e.get("frac", False), i_period=e["i_period"])
     data, recon, qps, kinds = rc_oracle.encode_video_rc(frames, cfg, g["meta"]["rcflag"], g["meta"]["targetBR"], _table(g["meta"]))
     assert data == g["encoded"]
-    assert np.array_equal(recon, g["recon"])
+    if "recon" in g:
+        assert np.array_equal(recon, g["recon"])
+    else:
+        assert hashlib.sha256(recon.tobytes()).hexdigest() == g["meta"]["recon_sha256"]
     # the cases actually exercise rate control: QPs move, and the scene-change case re-codes a P frame as I
     assert len({q for row in qps for q in row}) > 1
     if name == "rc3_i8_scene":
@@ -85,7 +88,64 @@ def test_gpu_encode_video_with_rate_control(name, tmp_path):
     out = enc_mod.output_dir(params)
     data = open(os.path.join(out, "encoded.bin"), "rb").read()
     assert hashlib.sha256(data).hexdigest() == meta["encoded_sha256"]
-    assert open(os.path.join(out, "mc_reconstructed.yuv"), "rb").read() == g["recon"].tobytes()
+    rec = open(os.path.join(out, "mc_reconstructed.yuv"), "rb").read()
+    if "recon" in g:
+        assert rec == g["recon"].tobytes()
+    else:
+        assert hashlib.sha256(rec).hexdigest() == meta["recon_sha256"]
+
+
+def test_shipped_cif_lookup_tables_are_the_references():
+    """rc1_cif_c3 was produced by the reference reading its OWN encoder/RateControl/lookups/352_288_16_{I,P}.csv; the
+    tables this package ships for that geometry must give the same dictionary (they are data the drop-in has to match)."""
+    from basic_video_codec_b200 import EncoderConfig
+    from basic_video_codec_b200.encoder.RateControl import lookup
+    meta = gu.load("rc1_cif_c3")["meta"]
+    assert "lookups/352_288_16" in meta["table_source"]
+    ec = EncoderConfig(16, 4, 21, 4, resolution=(352, 288))
+    assert lookup.get_combined_lookup_table(lookup.rc_lookup_file_path(ec, "I"), lookup.rc_lookup_file_path(ec, "P")) == _table(meta)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in RC if n.startswith("rc1")])
+def test_gpu_clip_call_with_rate_control(name):
+    """RCflag 1 through the clip call: the per-row feedback loop runs on the device (bvc_set_rate_control), GOP lanes in
+    lock step.  Same stream as the reference's frame loop."""
+    import basic_video_codec_b200 as bvc
+    g = gu.load(name)
+    e, frames, meta = g["meta"]["enc"], g["frames"], g["meta"]
+    n, H, W = frames.shape
+    ec = bvc.EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], nRefFrames=e.get("nref", 1),
+                           fastME=e.get("fastme", False), fracMeEnabled=e.get("frac", False), RCflag=1,
+                           targetBR=meta["targetBR"], resolution=(W, H))
+    ec.rc_lookup_table = _table(meta)
+    for lanes in (1, 3):
+        data, recon = bvc.encode_clip(frames, ec, max_lanes=lanes, want_recon=True)
+        assert hashlib.sha256(data).hexdigest() == meta["encoded_sha256"], f"lanes={lanes}"
+        if "recon" in g:
+            assert np.array_equal(recon, g["recon"])
+        else:
+            assert hashlib.sha256(recon.tobytes()).hexdigest() == meta["recon_sha256"]
+
+
+@pytest.mark.gpu
+def test_gpu_rate_control_off_again_and_unsupported_modes():
+    """bvc_set_rate_control(0) restores the base QP on every row; RCflag 2 / 3 are refused on the clip path."""
+    import basic_video_codec_b200 as bvc
+    g = gu.load("rc1_i16")
+    e, frames, meta = g["meta"]["enc"], g["frames"], g["meta"]
+    n, H, W = frames.shape
+    with bvc.Context(W, H, e["block"], e["search_range"], e["qp"], 1, False, False, e["i_period"], max_lanes=2) as ctx:
+        plain = ctx.encode_clip(frames)[0]
+        ctx.set_rate_control(1, meta["targetBR"] / 30, _table(meta))
+        assert hashlib.sha256(ctx.encode_clip(frames)[0]).hexdigest() == meta["encoded_sha256"]
+        ctx.set_rate_control(0)
+        assert ctx.encode_clip(frames)[0] == plain
+        with pytest.raises(NotImplementedError):
+            ctx.set_rate_control(2, 1000.0, _table(meta))
+    ec = bvc.EncoderConfig(e["block"], e["search_range"], e["i_period"], e["qp"], RCflag=2, targetBR=1000, resolution=(W, H))
+    with pytest.raises(NotImplementedError):
+        bvc.encode_clip(frames, ec)
 
 
 @pytest.mark.gpu
