@@ -443,6 +443,7 @@ static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src, cudaStre
 
 struct StepPlan {
     int nl = 0;
+    int nref = 0;         // references every lane of the step sees (frame k of its GOP: min(k, nRefFrames))
     bool intra = false;
     size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
 };
@@ -569,6 +570,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.nphase = c->p.frac_me ? 4 : 1;
         m.R = c->p.search_range;
         m.Rh = c->p.search_range * m.sc;
+        m.uniform_nref = sp.nref;
         m.tail_split = c->tail_split && st_post == st_me;   // with lane groups the other group's kernels fill the tail
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
@@ -748,7 +750,7 @@ static int frame_common(bvc_ctx* c, const uint8_t* cur, const uint8_t* const* re
     c->row_open = false;
     if ((rc = frame_prepare(c, cur, refs, nref_avail, qp_rows, intra, &fl)) != BVC_OK) return rc;
     StepPlan sp;
-    sp.nl = 1; sp.intra = intra; sp.desc_off = 0;
+    sp.nl = 1; sp.intra = intra; sp.desc_off = 0; sp.nref = intra ? 0 : nref_avail;
     if (me_only) {
         if ((rc = launch_me_lane0(c)) != BVC_OK) return rc;
     } else {
@@ -1272,6 +1274,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         for (int k = 0; k < IP; k++) {
             StepPlan sp;
             sp.intra = (k == 0);
+            sp.nref = std::min(k, c->p.nref_frames);
             sp.desc_off = mel.size();
             std::vector<int> fr, op;
             for (int gi = g0; gi < g1; gi++) {

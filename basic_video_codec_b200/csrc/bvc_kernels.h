@@ -29,6 +29,8 @@ struct MeArgs {
     int Rv;                        // vertical range the tiled bodies walk (>= R, 2*Rv a multiple of bs); launcher
     int tiles_x, tiles_y, n_full;  // linear tile grid: CTAs [0, n_full) own whole tiles, the rest one block row each (launcher)
     int tail_split;                // 1: cut the tiles of the last, partly filled wave into one-row CTAs
+    int uniform_nref;              // > 0: every lane of the launch has this many references (no per-lane look-up in the kernels)
+    int n_tiles;                   // narrow kernel: tiles_x * tiles_y * lanes, walked by a persistent grid (launcher)
     int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
     // SAD map (FastME): when non-null the tiled kernel stores the SAD of every in-range candidate instead of reducing
     // them: uint16 [lane][ref][phase][blk][map_stride >= (2R+1)^2] (row = vertical offset + R, column = horizontal offset + R),

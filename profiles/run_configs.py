@@ -30,6 +30,12 @@ WORKLOADS = {
     # not BASELINE configurations: FastME at the headline geometry (a chain of 8160 blocks per frame) and with half-pel
     "x_1080p_fastme_nref4": (1920, 1088, 600, 16, 16, 4, 30, 4, True, False, 20, dict(step=6, clamp=96)),
     "x_cif_halfpel_fastme_nref2": (352, 288, 296, 16, 4, 3, 8, 2, True, True, 37, dict(step=2, clamp=16)),
+    # round 2: the narrow-range search kernel on a GPU-filling size (config 3's search at 1080p), the reference's own ranges
+    "x_1080p_halfpel_r4": (1920, 1088, 600, 16, 4, 4, 30, 1, False, True, 20, dict(step=3, clamp=48)),
+    "x_1080p_i16_r4": (1920, 1088, 600, 16, 4, 4, 30, 1, False, False, 20, dict(step=3, clamp=48)),
+    "x_1080p_i8_r2": (1920, 1088, 600, 8, 2, 3, 30, 1, False, False, 20, dict(step=2, clamp=48)),
+    "x_1080p_i8_r3": (1920, 1088, 600, 8, 3, 3, 30, 1, False, False, 20, dict(step=2, clamp=48)),
+    "x_cif_i16_r2_nref4": (352, 288, 296, 16, 2, 3, 8, 4, False, False, 37, dict(step=2, clamp=16)),
 }
 FASTME_MODE = int(os.environ.get("BVC_FASTME_MODE", "0"))   # bvc_set_fastme_direct: 0 auto, 1 direct, 2 serial map walk, 3 window walk, 4 tables
 
@@ -79,6 +85,9 @@ def run(name):
         line["fastme_mode"] = FASTME_MODE
     if not fastme and kt["me"][0] > 0:
         line["me_px_absdiff_per_frame_1ref"] = work
+        # frame k of a GOP sees min(k, nRef) references (deque cleared at the I frame)
+        tot = sum(work * min(k, nref) for f0, nf in gops for k in range(1, nf))
+        line["me_tpx_per_s"] = tot / (kt["me"][0] * 1e-3) / 1e12
     print(json.dumps(line), flush=True)
     assert all(checked), f"{name}: GPU stream differs from the oracle"
 
