@@ -51,7 +51,12 @@ struct bvc_ctx {
     int ngroups = 2;
     int tail_split = 1;   // motion search: tiles of the last, partly filled wave as one-row CTAs (BVC_TAIL_SPLIT=0 turns it off)
     cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
-    cudaEvent_t ev_me[BVC_MAX_GROUPS] = {}, ev_post[BVC_MAX_GROUPS] = {};
+    // st_pack: entropy coding of I levels + stream assembly.  Nothing of the next step's search needs them (it needs the
+    // reconstruction only), so they leave the per-group critical path ME(k) -> transform(k) -> ME(k+1) and run while the
+    // next search is on the GPU (high priority: they take the slots the search frees).  The motion-vector array is double
+    // buffered by step parity so that ME(k+1) does not overwrite what the assembly of step k still reads.
+    cudaStream_t st_pack[BVC_MAX_GROUPS] = {};
+    cudaEvent_t ev_me[BVC_MAX_GROUPS] = {}, ev_post[BVC_MAX_GROUPS] = {}, ev_tq[BVC_MAX_GROUPS] = {}, ev_pack[BVC_MAX_GROUPS] = {};
     std::string err;
     int64_t launches = 0;
 
@@ -246,8 +251,11 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
             CK(cudaStreamCreateWithPriority(&c->st_grp[gi], cudaStreamNonBlocking, prio_lo));
             CK(cudaStreamCreateWithPriority(&c->st_post[gi], cudaStreamNonBlocking, prio_hi));
+            CK(cudaStreamCreateWithPriority(&c->st_pack[gi], cudaStreamNonBlocking, prio_hi));
             CK(cudaEventCreateWithFlags(&c->ev_me[gi], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_post[gi], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_tq[gi], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_pack[gi], cudaEventDisableTiming));
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
@@ -255,7 +263,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         c->ref_planes = L * c->slots * c->pps;
         CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
         CK(cudaMemset(c->ref_pool, 0, c->ref_planes * g.plane_bytes + 4096));
-        CK(dalloc(&c->d_mv, L * nb));
+        CK(dalloc(&c->d_mv, 2 * L * nb));   // two sets, by step parity
         CK(dalloc(&c->d_modes, L * nb));
         CK(dalloc(&c->d_isad, L * nb));
         CK(dalloc(&c->d_qp_rows, L * g.bh));
@@ -301,8 +309,11 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     for (int gi = 0; gi < BVC_MAX_GROUPS; gi++) {
         if (c->st_grp[gi]) { cudaStreamSynchronize(c->st_grp[gi]); cudaStreamDestroy(c->st_grp[gi]); }
         if (c->st_post[gi]) { cudaStreamSynchronize(c->st_post[gi]); cudaStreamDestroy(c->st_post[gi]); }
+        if (c->st_pack[gi]) { cudaStreamSynchronize(c->st_pack[gi]); cudaStreamDestroy(c->st_pack[gi]); }
         if (c->ev_me[gi]) cudaEventDestroy(c->ev_me[gi]);
         if (c->ev_post[gi]) cudaEventDestroy(c->ev_post[gi]);
+        if (c->ev_tq[gi]) cudaEventDestroy(c->ev_tq[gi]);
+        if (c->ev_pack[gi]) cudaEventDestroy(c->ev_pack[gi]);
     }
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
@@ -443,6 +454,7 @@ static int download_plane(bvc_ctx* c, uint8_t* dst, const uint8_t* src, cudaStre
 
 struct StepPlan {
     int nl = 0;
+    int k = 0;            // position of the step's frames inside their GOPs (parity picks the motion-vector set)
     int nref = 0;         // references every lane of the step sees (frame k of its GOP: min(k, nRefFrames))
     bool intra = false;
     size_t desc_off = 0;  // offset (in lanes) into the device descriptor arrays
@@ -511,14 +523,19 @@ static int launch_fastme_any(bvc_ctx* c, const MeArgs& m, int nl, size_t L0, cud
 // `st_post` (the same stream for the frame-level calls).  Per-lane scratch arrays are indexed by the lane
 // inside a launch, so a lane group simply gets base pointers advanced by l0 lanes.
 static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStream_t st_me, cudaStream_t st_post, int l0, int nl,
-                        cudaEvent_t ev_me_done) {
+                        cudaEvent_t ev_me_done, cudaStream_t st_pack = nullptr, cudaEvent_t ev_tq_done = nullptr,
+                        cudaEvent_t ev_pack_done = nullptr) {
     const Geom& g = c->g;
     const size_t nb = (size_t)g.nblk, L0 = (size_t)l0;
+    const bool side_pack = st_pack && st_pack != st_post;
+    int4* const mv_set = c->d_mv + (size_t)(sp.k & 1) * c->max_lanes * nb;
+    // the transform of this step rewrites the per-block strings the previous step's assembly reads
+    if (side_pack) CK(cudaStreamWaitEvent(st_post, ev_pack_done, 0));
     TqArgs t{};
     t.cur_base = c->in_pool; t.cur_plane_bytes = g.plane_bytes; t.cur_pitch = g.pitch;
     t.ref_base = c->ref_pool; t.ref_plane_bytes = g.plane_bytes; t.ref_pitch = g.pitch;
     t.lanes = c->d_fr_lanes + sp.desc_off + L0;
-    t.mv = c->d_mv + L0 * nb; t.modes = c->d_modes + L0 * nb; t.isad = c->d_isad + L0 * nb; t.qp_rows = c->d_qp_rows + L0 * g.bh;
+    t.mv = mv_set + L0 * nb; t.modes = c->d_modes + L0 * nb; t.isad = c->d_isad + L0 * nb; t.qp_rows = c->d_qp_rows + L0 * g.bh;
     t.levels = (frame_api || sp.intra) ? c->d_levels + L0 * (size_t)g.W * g.H : nullptr;
     t.resid_mc = frame_api ? c->d_resid_mc : nullptr;
     t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
@@ -558,13 +575,14 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         CK(cudaMemsetAsync(t.progress, 0, (size_t)nl * g.bh * sizeof(int), st_post));
         const int e0 = tick(c, st_post);
         if (rc_rows) { int rcr = transform_rows(true); if (rcr != BVC_OK) return rcr; }
+        else if (side_pack) { CK(launch_tq_iframe(t, nl, st_post, false)); c->launches += 1; }   // entropy coding follows on st_pack
         else { CK(launch_tq_iframe(t, nl, st_post)); c->launches += 2; }
         span(c, BVC_K_TQ_I, e0, tick(c, st_post));
     } else {
         MeArgs m{};
         m.cur_base = c->in_pool; m.cur_plane_bytes = g.plane_bytes; m.cur_pitch = g.pitch;
         m.lanes = c->d_me_lanes + sp.desc_off + L0;
-        m.out = c->d_mv + L0 * nb;
+        m.out = mv_set + L0 * nb;
         m.W = g.W; m.H = g.H; m.bs = g.bs; m.bw = g.bw; m.bh = g.bh; m.nblk = g.nblk;
         m.sc = c->p.frac_me ? 2 : 1;
         m.nphase = c->p.frac_me ? 4 : 1;
@@ -590,6 +608,15 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         if (rc_rows) { int rcr = transform_rows(false); if (rcr != BVC_OK) return rcr; c->launches += 1; }
         else { CK(launch_tq_pframe(t, nl, st_post)); c->launches += 2; }
         span(c, BVC_K_TQ_P, e1p, tick(c, st_post));
+    }
+    if (side_pack) {
+        CK(cudaEventRecord(ev_tq_done, st_post));
+        CK(cudaStreamWaitEvent(st_pack, ev_tq_done, 0));
+        if (sp.intra && !rc_rows) { CK(launch_tq_ientropy(t, nl, st_pack)); c->launches += 1; }
+        CK(launch_pack(pk, nl, st_pack));
+        CK(cudaEventRecord(ev_pack_done, st_pack));
+        c->launches += 2;
+        return BVC_OK;
     }
     const int ep = tick(c, st_post);
     CK(launch_pack(pk, nl, st_post));
@@ -1275,6 +1302,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             StepPlan sp;
             sp.intra = (k == 0);
             sp.nref = std::min(k, c->p.nref_frames);
+            sp.k = k;
             sp.desc_off = mel.size();
             std::vector<int> fr, op;
             for (int gi = g0; gi < g1; gi++) {
@@ -1363,6 +1391,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     for (int gi = 0; gi < NG; gi++) {
         CK(cudaStreamWaitEvent(c->st_grp[gi], ev_clip0, 0));
         CK(cudaStreamWaitEvent(c->st_post[gi], ev_clip0, 0));
+        CK(cudaStreamWaitEvent(c->st_pack[gi], ev_clip0, 0));
+        CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));   // "no assembly pending" for the first step of this call
     }
     for (size_t s = 0; s < nsteps; s++) {
         if (host_frames)
@@ -1375,7 +1405,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
                 CK(cudaStreamWaitEvent(sm, ev_h2d[s], 0));
                 if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s], 0));
             }
-            if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi])) != BVC_OK) return rc;
+            if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi], NG == 1 ? nullptr : c->st_pack[gi], c->ev_tq[gi],
+                                   c->ev_pack[gi])) != BVC_OK) return rc;
             // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
             if ((rc = enqueue_halfpel(c, steps[s].desc_off + l0, nl, spst)) != BVC_OK) return rc;
             if (recon) {
@@ -1395,6 +1426,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
             CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
             CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
+            CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_pack[gi], 0));
         }
     }
     // ---- container (encoder.py:104-121) assembled on the device, one download ----

@@ -123,7 +123,9 @@ struct TqArgs {
                                    // rate-control loop (Frame.get_rc_qp, Frame.py:168-188) launches one row at a time
 };
 cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st);
-cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st);
+// with_entropy = false: the wavefront only (levels stay in a.levels); launch_tq_ientropy codes them later, on any stream
+cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st, bool with_entropy = true);
+cudaError_t launch_tq_ientropy(const TqArgs& a, int lanes, cudaStream_t st);
 
 // Block-level hook: residual (int16) + pred (int16) -> level/recon/idct/coef, nblocks blocks of bs x bs
 int tq_blk_words(int bs);

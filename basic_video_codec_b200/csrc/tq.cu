@@ -235,7 +235,15 @@ cudaError_t launch_p(const TqArgs& a, int lanes, cudaStream_t st) {
 }
 
 template <int BS>
-cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
+cudaError_t launch_ie(const TqArgs& a, int lanes, cudaStream_t st) {
+    if (!a.levels) return cudaErrorInvalidValue;
+    dim3 grid((a.row_count * a.bw + TQ_WARPS - 1) / TQ_WARPS, lanes);
+    entropy_levels_kernel<BS><<<grid, TQ_WARPS * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int BS>
+cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st, bool with_entropy) {
     constexpr int NBW = 32 / BS;
     const size_t smem = sizeof(WarpTile<BS>) + BS * BS + 2 * NBW * BS + 64;
     const int ngrp = (lanes + NBW - 1) / NBW;
@@ -249,10 +257,8 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st) {
     if (!a.levels) return cudaErrorInvalidValue;   // the level plane feeds the entropy kernel
     tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    dim3 grid((a.row_count * a.bw + TQ_WARPS - 1) / TQ_WARPS, lanes);
-    entropy_levels_kernel<BS><<<grid, TQ_WARPS * 32, 0, st>>>(a);
-    return cudaGetLastError();
+    if (e != cudaSuccess || !with_entropy) return e;
+    return launch_ie<BS>(a, lanes, st);
 }
 
 template <int BS>
@@ -284,11 +290,19 @@ cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st) {
     }
     return cudaErrorInvalidValue;
 }
-cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st) {
+cudaError_t launch_tq_iframe(const TqArgs& a, int lanes, cudaStream_t st, bool with_entropy) {
     switch (a.bs) {
-        case 16: return launch_i<16>(a, lanes, st);
-        case 8: return launch_i<8>(a, lanes, st);
-        case 4: return launch_i<4>(a, lanes, st);
+        case 16: return launch_i<16>(a, lanes, st, with_entropy);
+        case 8: return launch_i<8>(a, lanes, st, with_entropy);
+        case 4: return launch_i<4>(a, lanes, st, with_entropy);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_tq_ientropy(const TqArgs& a, int lanes, cudaStream_t st) {
+    switch (a.bs) {
+        case 16: return launch_ie<16>(a, lanes, st);
+        case 8: return launch_ie<8>(a, lanes, st);
+        case 4: return launch_ie<4>(a, lanes, st);
     }
     return cudaErrorInvalidValue;
 }
