@@ -15,7 +15,7 @@ EXPORTS = [
     "bvc_create", "bvc_destroy", "bvc_last_error", "bvc_set_qp", "bvc_encode_iframe", "bvc_encode_pframe",
     "bvc_frame_begin", "bvc_frame_encode_row", "bvc_frame_end", "bvc_me_search", "bvc_interp_halfpel", "bvc_dct_quant_recon", "bvc_encode_clip", "bvc_clip_upload",
     "bvc_encode_clip_resident", "bvc_launch_count", "bvc_last_kernel_times", "bvc_me_work_per_frame", "bvc_set_lane_groups", "bvc_decode_clip", "bvc_decode_frame", "bvc_clip_upload_i420", "bvc_set_fastme_direct",
-    "bvc_encode_clip_device", "bvc_container_download", "bvc_host_register", "bvc_host_unregister", "bvc_measure_peaks", "bvc_set_rate_control",
+    "bvc_encode_clip_device", "bvc_container_download", "bvc_host_register", "bvc_host_unregister", "bvc_measure_peaks", "bvc_set_rate_control", "bvc_set_stream_slot_bytes",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library():
     L.bvc_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.bvc_host_unregister.argtypes = [C.c_void_p]
     L.bvc_set_rate_control.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    L.bvc_set_stream_slot_bytes.argtypes = [C.c_void_p, C.c_size_t]
     L.bvc_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _LIB = L
     return L
@@ -254,13 +255,19 @@ class Context:
         n = frames.shape[0]
         cap = int(out_capacity or (n * self.W * self.H // 2 + (1 << 20)))
         recon = np.empty_like(frames) if want_recon else None
-        for _ in range(2):
+        for _ in range(6):
             out = np.empty(cap, np.uint8)
             ln = C.c_size_t(0)
             rc = self._L.bvc_encode_clip(self._h, _p(frames), n, _p(out), out.size, C.byref(ln), _p(recon))
-            # noisy content at a low QP can need more than the default 4 bits per pixel: the library reports the size
+            # noisy content at a low QP can need more than the defaults (4 bits per pixel of host buffer, 6 of device slot):
+            # the library says which one was too small
+            if rc == BVC_ERR_NOMEM and b"device slot" in self._L.bvc_last_error(self._h):
+                self._check(self._L.bvc_set_stream_slot_bytes(self._h, C.c_size_t(-1).value))
+                continue
+            if rc == BVC_ERR_NOMEM and b"staging" in self._L.bvc_last_error(self._h):
+                continue            # the library has enlarged it
             if rc == BVC_ERR_NOMEM and out_capacity is None and int(ln.value) > cap:
-                cap = int(ln.value)
+                cap = max(int(ln.value), 2 * cap)
                 continue
             break
         self._check(rc)
@@ -360,6 +367,10 @@ class Context:
         qps = np.array(sorted(q for q in table if "I" in table[q]), dtype=np.int32)
         bits = np.array([int(table[int(q)]["I"]) for q in qps], dtype=np.int64)
         self._check(self._L.bvc_set_rate_control(self._h, int(rc_flag), float(frame_bit_budget), int(qps.size), _p(qps), _p(bits)))
+
+    def set_stream_slot_bytes(self, nbytes):
+        """Device bytes reserved per frame for its coefficient stream (bvc_set_stream_slot_bytes; 0 = default)."""
+        self._check(self._L.bvc_set_stream_slot_bytes(self._h, int(nbytes)))
 
     # ---- sharded jobs: container left on the device, fetched into a caller-chosen place ----------------
     def encode_clip_device(self, frames, nframes=None, cap_hint=0):

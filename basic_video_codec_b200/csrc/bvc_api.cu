@@ -82,8 +82,14 @@ struct bvc_ctx {
     int* d_overflow = nullptr;
     size_t stream_slots = 0;
     size_t coef_cap_words = 0, pred_cap_words = 0;
-    uint8_t* d_container = nullptr;
+    uint8_t* d_container = nullptr;   // whole-clip container kept on the device (bvc_encode_clip_device)
     size_t container_cap = 0;
+    uint8_t* d_frag[2] = {nullptr, nullptr};   // staging of one wave's container fragment
+    size_t frag_cap = 0, frag_min = 0;
+    int nfrag = 0;
+    void* h_totals = nullptr;         // pinned: per-wave fragment sizes and overflow flags
+    size_t h_totals_cap = 0;
+    size_t slot_bytes = 0;            // bvc_set_stream_slot_bytes: 0 = default
     int* d_progress = nullptr;
     int* d_ticket = nullptr;      // [max_lanes]: start-order counters of the wavefront kernels, one per lane group in flight
     MeLane* d_me_lanes = nullptr;
@@ -126,6 +132,8 @@ struct bvc_ctx {
     FrameLane row_fl{};
     long long* d_rowbits = nullptr;
 };
+
+static size_t default_coef_cap_words(const bvc_ctx* c);
 
 // record an event on `st` (default: the compute stream) and return its index (-1 when timing is off)
 static int tick(bvc_ctx* c, cudaStream_t st = nullptr) {
@@ -281,9 +289,9 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_ticket, L));
         CK(dalloc(&c->d_rc_remaining, L));
         CK(cudaMemset(c->d_ticket, 0, L * sizeof(int)));
-        c->coef_cap_words = nb * c->blk_words + 8;
+        c->coef_cap_words = default_coef_cap_words(c);
         c->pred_cap_words = nb * 3 + g.bh + 8;
-        CK(dalloc(&c->d_overflow, 1));
+        CK(dalloc(&c->d_overflow, 2));   // [0] a payload does not fit its container length field, [1] a stream slot is too small
         std::vector<int32_t> q(L * g.bh, p->qp);
         CK(cudaMemcpy(c->d_qp_rows, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
         int rc = make_ref_map(c);
@@ -321,7 +329,8 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
-    cudaFree(c->d_overflow); cudaFree(c->d_container);
+    cudaFree(c->d_overflow); cudaFree(c->d_container); cudaFree(c->d_frag[0]); cudaFree(c->d_frag[1]);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
     for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
                              &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
                              &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->sad_map, &c->fastme_tab})
@@ -427,6 +436,24 @@ static int ensure_container(bvc_ctx* c, size_t bytes) {
     c->d_container = nullptr; c->container_cap = 0;
     CK(cudaMalloc((void**)&c->d_container, bytes + 64));
     c->container_cap = bytes;
+    return BVC_OK;
+}
+// Words reserved per frame for the coefficient stream.  The worst case (every coefficient at the largest magnitude) is 26
+// bits per pixel; the default reserves 6 bits per pixel (at least 1 MB, never more than the worst case) -- pack_scan
+// reports a frame that does not fit and the call fails with BVC_ERR_NOMEM instead of overrunning
+// (bvc_set_stream_slot_bytes raises the reservation).
+static size_t default_coef_cap_words(const bvc_ctx* c) {
+    const size_t worst = (size_t)c->g.nblk * c->blk_words + 8;
+    const size_t want = c->slot_bytes ? c->slot_bytes : std::max((size_t)c->g.W * c->g.H / 4 * 3, (size_t)1 << 20);
+    return std::min(worst, want / 4 + 8);
+}
+static int ensure_fragments(bvc_ctx* c, size_t bytes, int n) {
+    if (bytes <= c->frag_cap && n <= c->nfrag) return BVC_OK;
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_frag[i]); c->d_frag[i] = nullptr; }
+    c->frag_cap = 0; c->nfrag = 0;
+    const size_t cap = std::max(bytes, c->frag_cap);
+    for (int i = 0; i < n; i++) CK(cudaMalloc((void**)&c->d_frag[i], cap + 64));
+    c->frag_cap = cap; c->nfrag = n;
     return BVC_OK;
 }
 static int ensure_pinned(bvc_ctx* c, void** p, size_t* cap, size_t need) {
@@ -556,7 +583,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     pk.lanes = t.lanes;
     pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
     pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh; pk.pred_row_off = c->d_pred_row_off + L0 * (g.bh + 1);
-    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
+    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words; pk.slot_overflow = c->d_overflow + 1;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
     auto transform_rows = [&](bool intra) -> int {
@@ -824,7 +851,7 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     pk.coef_off = c->d_coef_off; pk.lanes = c->d_fr_lanes;
     pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
     pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
-    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words;
+    pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words; pk.slot_overflow = c->d_overflow + 1;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = intra; pk.with_ref = c->p.nref_frames > 1;
 }
@@ -1274,21 +1301,39 @@ extern "C" int bvc_clip_upload_i420(bvc_ctx* c, const uint8_t* yuv, int src_w, i
     return BVC_OK;
 }
 
-// out == nullptr: the container stays on the device (bvc_encode_clip_device), out_cap is then the device capacity
+// Clip encoder.  GOPs are encoded max_lanes at a time ("waves" of max_lanes x I_Period frames, frame k of every GOP of the
+// wave per step).  Nothing in here scales with the length of the clip except tiny per-frame descriptors:
+//   * input planes live in a ring of IN_RING_STEPS steps x max_lanes planes, refilled three steps ahead on the copy
+//     stream (a slot is reused once every lane group has finished the step that read it);
+//   * the per-frame bit streams live in one wave's worth of slots; at the end of a wave its container fragment is laid
+//     out on the device into one of two staging buffers and goes to the caller's buffer on the download stream while
+//     the next wave is already running -- the host only waits for a wave's size after it has enqueued the wave after it.
+// out == nullptr (keep_on_device): the fragments are appended to c->d_container instead (bvc_encode_clip_device).
+static constexpr int IN_RING_STEPS = 6;
+
 static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes, uint8_t* out, size_t out_cap, size_t* out_len,
                             uint8_t* recon, bool keep_on_device = false) {
     const Geom& g = c->g;
     CK(cudaSetDevice(c->device));
     c->container_len = 0;
     if (nframes < 1 || (!out && !keep_on_device) || !out_len) return fail(c, BVC_ERR_INVALID, "bad arguments");
-    const int IP = c->p.i_period, G = c->max_lanes;
+    const int IP = c->p.i_period, G = c->max_lanes, D = IN_RING_STEPS;
     const int ngop = (nframes + IP - 1) / IP;
     const int nwaves = (ngop + G - 1) / G;
+    const size_t wave_frames = (size_t)std::min((long long)nframes, (long long)G * IP);
     int rc;
-    if ((rc = ensure_in_pool(c, (size_t)nframes)) != BVC_OK) return rc;
+    if ((rc = ensure_in_pool(c, host_frames ? (size_t)D * G : (size_t)nframes)) != BVC_OK) return rc;
     if (host_frames) c->resident_frames = 0;   // the pool is about to be overwritten with this call's frames
-    if ((rc = ensure_streams(c, (size_t)nframes)) != BVC_OK) return rc;
-    if ((rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
+    if ((rc = ensure_streams(c, wave_frames)) != BVC_OK) return rc;
+    // staging for one wave's container fragment (x2: the download of wave w overlaps the assembly of wave w+1)
+    // sized for 1 bit per pixel (the headline workload codes 0.5) unless an earlier call found that too small
+    const size_t frag_worst = wave_frames * (6 + 4 * (c->coef_cap_words + c->pred_cap_words));
+    const size_t frag_cap = std::min(std::min(out_cap, frag_worst), std::max(c->frag_min, wave_frames * ((size_t)g.W * g.H / 8) + ((size_t)1 << 20)));
+    if ((rc = ensure_fragments(c, frag_cap, nwaves > 1 ? 2 : 1)) != BVC_OK) return rc;
+    if (keep_on_device && (rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
+    if ((rc = ensure_pinned(c, &c->h_totals, &c->h_totals_cap, ((size_t)nwaves + 1) * 16)) != BVC_OK) return rc;
+    long long* h_total = static_cast<long long*>(c->h_totals);          // [nwaves] fragment bytes
+    int* h_over = reinterpret_cast<int*>(h_total + nwaves);             // [nwaves] length-field overflow flags (2 ints per slot)
 
     // ---- plan: one step per (wave, k); lane l of a step = GOP (wave*G + l) ----
     std::vector<StepPlan> steps;
@@ -1296,14 +1341,19 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     std::vector<FrameLane> frl;
     std::vector<std::vector<int>> step_frames;   // clip frame index of every lane of a step
     std::vector<std::vector<int>> step_outplane;
+    std::vector<int> step_wave;
+    std::vector<int> wave_nframes(nwaves, 0);
     for (int w = 0; w < nwaves; w++) {
         const int g0 = w * G, g1 = std::min(ngop, g0 + G);
+        const int wave_first = g0 * IP;
+        wave_nframes[w] = std::min(nframes, g1 * IP) - wave_first;
         for (int k = 0; k < IP; k++) {
             StepPlan sp;
             sp.intra = (k == 0);
             sp.nref = std::min(k, c->p.nref_frames);
             sp.k = k;
             sp.desc_off = mel.size();
+            const int sidx = (int)steps.size();          // global step index: the input ring slot is sidx % D
             std::vector<int> fr, op;
             for (int gi = g0; gi < g1; gi++) {
                 const int f = gi * IP + k;
@@ -1311,8 +1361,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
                 const int lane = gi - g0;
                 MeLane ml{};
                 FrameLane fl{};
-                ml.cur_plane = fl.cur_plane = f;
-                fl.slot = f;
+                ml.cur_plane = fl.cur_plane = host_frames ? (sidx % D) * G + lane : f;
+                fl.slot = f - wave_first;
                 const int nav = std::min(k, c->p.nref_frames);  // deque(maxlen=nRef), cleared at the I frame
                 ml.nref = fl.nref = nav;
                 for (int j = 0; j < nav; j++) {
@@ -1330,6 +1380,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             steps.push_back(sp);
             step_frames.push_back(fr);
             step_outplane.push_back(op);
+            step_wave.push_back(w);
         }
     }
     const size_t nsteps = steps.size();
@@ -1344,7 +1395,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         for (size_t s = 0; s < nsteps; s++)
             if ((rc = upload_halfpel_desc(c, step_outplane[s], steps[s].desc_off)) != BVC_OK) return rc;
     }
-    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st));
+    CK(cudaMemsetAsync(c->d_overflow, 0, 2 * sizeof(int), c->st));
 
     c->ev_used = 0;
     c->spans.clear();
@@ -1353,19 +1404,28 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     CK(bag.make(&ev_clip0));
     CK(bag.make(&ev_clip1));
     CK(cudaEventRecord(ev_clip0, c->st));
+
+    const int NG = std::max(1, std::min(c->ngroups, G));
+    const int per = (G + NG - 1) / NG;
+    // "step s is finished by group gi" (its search and transform have read the input planes of ring slot s % D)
+    std::vector<cudaEvent_t> ev_step((size_t)D * NG, nullptr);
+    for (auto& e : ev_step) CK(bag.make(&e, cudaEventDisableTiming));
     // ---- input: uploaded step by step on its own stream so the copies overlap compute ----
     std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps : 0);
     auto enqueue_upload = [&](size_t s) -> int {
         if (!host_frames || s >= nsteps) return BVC_OK;
         const std::vector<int>& fr = step_frames[s];
-        if (g.pitch == g.W && fr.size() > 1) {
+        if (s >= (size_t)D)   // the slot's previous tenant: step s - D, every group
+            for (int gi = 0; gi < NG; gi++) CK(cudaStreamWaitEvent(c->st_h2d, ev_step[(s % D) * NG + gi], 0));
+        uint8_t* dst = c->in_pool + (size_t)(s % D) * G * g.plane_bytes;   // lanes of a step sit side by side in the ring
+        const size_t fbytes = (size_t)g.W * g.H, spitch = (size_t)IP * fbytes;
+        if (g.pitch == g.W && fr.size() > 1 && spitch <= 0x7fffffffull && g.plane_bytes <= 0x7fffffffull) {
             // the frames of a step are IP apart (frame k of consecutive GOPs): one strided copy, "row" = one plane
-            CK(cudaMemcpy2DAsync(c->in_pool + (size_t)fr[0] * g.plane_bytes, (size_t)IP * g.plane_bytes,
-                                 host_frames + (size_t)fr[0] * g.W * g.H, (size_t)IP * g.W * g.H, (size_t)g.W * g.H, fr.size(),
+            CK(cudaMemcpy2DAsync(dst, g.plane_bytes, host_frames + (size_t)fr[0] * fbytes, spitch, fbytes, fr.size(),
                                  cudaMemcpyHostToDevice, c->st_h2d));
         } else {
-            for (int f : fr)
-                CK(cudaMemcpy2DAsync(c->in_pool + (size_t)f * g.plane_bytes, g.pitch, host_frames + (size_t)f * g.W * g.H, g.W, g.W, g.H,
+            for (size_t l = 0; l < fr.size(); l++)
+                CK(cudaMemcpy2DAsync(dst + l * g.plane_bytes, g.pitch, host_frames + (size_t)fr[l] * fbytes, g.W, g.W, g.H,
                                      cudaMemcpyHostToDevice, c->st_h2d));
         }
         CK(bag.make(&ev_h2d[s], cudaEventDisableTiming));
@@ -1378,12 +1438,9 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             if ((rc = enqueue_upload(s)) != BVC_OK) return rc;
     }
 
-    // ---- the whole clip is enqueued without a single host wait ----
-    // Lane groups: group gi owns lanes [gi*per, (gi+1)*per) of every step and two streams.  Inside a group
-    // the order is ME(k) -> [TQ, pack, half-pel, recon download](k) -> ME(k+1); across groups there is no
-    // dependency, so the post-ME kernels of one group run while the other groups search.
-    const int NG = std::max(1, std::min(c->ngroups, G));
-    const int per = (G + NG - 1) / NG;
+    // Lane groups: group gi owns lanes [gi*per, (gi+1)*per) of every step and three streams.  Inside a group
+    // the order is ME(k) -> [TQ, half-pel, recon download](k) -> ME(k+1), stream assembly on the side; across groups
+    // there is no dependency, so the post-ME kernels of one group run while the other groups search.
     // per-kernel event pairs only make sense when the kernels of a step run back to back on one stream; with lane groups
     // they would just be ~500 extra event records per clip
     struct TimingGuard { bvc_ctx* c; bool saved; ~TimingGuard() { c->timing = saved; } } timing_guard{c, c->timing};
@@ -1394,68 +1451,117 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         CK(cudaStreamWaitEvent(c->st_pack[gi], ev_clip0, 0));
         CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));   // "no assembly pending" for the first step of this call
     }
+    CK(cudaStreamWaitEvent(c->st_d2h, ev_clip0, 0));
+
+    // ---- end of a wave: container fragment (encoder.py:104-121) on the device, size to the host ----
+    std::vector<cudaEvent_t> ev_total(nwaves, nullptr), ev_frag_free(nwaves, nullptr), ev_slots_free(nwaves, nullptr);
+    size_t out_off = 0;
+    int flushed = 0;       // waves whose fragment has been sent on its way
+    auto finish_wave = [&](int w) -> int {
+        if (NG > 1) {
+            for (int gi = 0; gi < NG; gi++) {
+                CK(cudaEventRecord(c->ev_post[gi], c->st_post[gi]));
+                CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
+                CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
+                CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
+                CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));
+                CK(cudaStreamWaitEvent(c->st, c->ev_pack[gi], 0));
+            }
+        }
+        if (w >= 2) CK(cudaStreamWaitEvent(c->st, ev_frag_free[w - 2], 0));   // staging buffer w & 1 has been copied out
+        ContainerArgs ca{};
+        ca.frame_bits = c->d_frame_bits; ca.coef_stream = c->d_coef_stream; ca.pred_stream = c->d_pred_stream;
+        ca.coef_cap_words = c->coef_cap_words; ca.pred_cap_words = c->pred_cap_words;
+        ca.frame_off = c->d_frame_off; ca.overflow = c->d_overflow;
+        ca.out = c->d_frag[w & 1]; ca.out_cap = (long long)c->frag_cap;
+        ca.nframes = wave_nframes[w]; ca.i_period = IP;
+        const int ec0 = tick(c);
+        CK(launch_container(ca, c->st));
+        span(c, BVC_K_PACK, ec0, tick(c));
+        c->launches += 2;
+        CK(cudaMemcpyAsync(&h_total[w], c->d_frame_off + wave_nframes[w], sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(&h_over[2 * w], c->d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(bag.make(&ev_total[w], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_total[w], c->st));
+        // the next wave's assembly may overwrite the stream slots and frame sizes only after this
+        CK(bag.make(&ev_slots_free[w], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_slots_free[w], c->st));
+        return BVC_OK;
+    };
+    // host side of a finished wave: wait for its size, then send the fragment to its place
+    auto flush_wave = [&](int w) -> int {
+        CK(cudaEventSynchronize(ev_total[w]));
+        if (h_over[2 * w]) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
+        if (h_over[2 * w + 1]) return fail(c, BVC_ERR_NOMEM, "a frame's bit stream does not fit its device slot: raise it with bvc_set_stream_slot_bytes");
+        const size_t total = (size_t)h_total[w];
+        if (out_off + total > out_cap) {
+            // report what the whole clip needs, as far as it is known: at least this much
+            *out_len = std::max(out_off + total, out_cap + 1);
+            return fail(c, BVC_ERR_NOMEM, "output buffer too small (*out_len = a lower bound of the bytes needed)");
+        }
+        if (total > c->frag_cap) {   // the wave's fragment did not fit its staging buffer: remember, the caller repeats the call
+            c->frag_min = total + total / 4;
+            *out_len = 0;
+            return fail(c, BVC_ERR_NOMEM, "container staging buffer too small for this content: it has been enlarged, repeat the call");
+        }
+        CK(cudaStreamWaitEvent(c->st_d2h, ev_total[w], 0));
+        if (keep_on_device) CK(cudaMemcpyAsync(c->d_container + out_off, c->d_frag[w & 1], total, cudaMemcpyDeviceToDevice, c->st_d2h));
+        else CK(cudaMemcpyAsync(out + out_off, c->d_frag[w & 1], total, cudaMemcpyDeviceToHost, c->st_d2h));
+        CK(bag.make(&ev_frag_free[w], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_frag_free[w], c->st_d2h));
+        out_off += total;
+        return BVC_OK;
+    };
+
+    // ---- the clip is enqueued wave after wave; the host is always at least one whole wave ahead of the GPU ----
     for (size_t s = 0; s < nsteps; s++) {
+        const int w = step_wave[s];
+        const bool wave_start = s == 0 || step_wave[s - 1] != w;
+        if (wave_start && w >= 1) {
+            // slots and frame sizes of the previous wave are free once its fragment is laid out
+            for (int gi = 0; gi < NG; gi++) CK(cudaStreamWaitEvent(NG == 1 ? c->st : c->st_pack[gi], ev_slots_free[w - 1], 0));
+            if (w >= 2) {   // wave w-2 has long finished: send its fragment off (this is the only host wait, a wave behind)
+                if ((rc = flush_wave(w - 2)) != BVC_OK) return rc;
+                flushed = w - 1;
+            }
+        }
         if (host_frames)
             if ((rc = enqueue_upload(s + 3)) != BVC_OK) return rc;
         for (int gi = 0; gi < NG; gi++) {
             const int l0 = gi * per, nl = std::min(steps[s].nl, l0 + per) - l0;
-            if (nl <= 0) continue;
             cudaStream_t sm = NG == 1 ? c->st : c->st_grp[gi], spst = NG == 1 ? c->st : c->st_post[gi];
-            if (host_frames) {
-                CK(cudaStreamWaitEvent(sm, ev_h2d[s], 0));
-                if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s], 0));
+            if (nl > 0) {
+                if (host_frames) {
+                    CK(cudaStreamWaitEvent(sm, ev_h2d[s], 0));
+                    if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s], 0));
+                }
+                if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi], NG == 1 ? nullptr : c->st_pack[gi], c->ev_tq[gi],
+                                       c->ev_pack[gi])) != BVC_OK) return rc;
+                // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
+                if ((rc = enqueue_halfpel(c, steps[s].desc_off + l0, nl, spst)) != BVC_OK) return rc;
+                if (recon) {
+                    for (int l = l0; l < l0 + nl; l++)
+                        if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]), spst)) != BVC_OK)
+                            return rc;
+                }
+                if (spst != sm) {   // the next motion search of this group needs this step's reconstructions
+                    CK(cudaEventRecord(c->ev_post[gi], spst));
+                    CK(cudaStreamWaitEvent(sm, c->ev_post[gi], 0));
+                }
             }
-            if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi], NG == 1 ? nullptr : c->st_pack[gi], c->ev_tq[gi],
-                                   c->ev_pack[gi])) != BVC_OK) return rc;
-            // phase planes of the new reconstructions (build_pre_interpolated_buffer, encoder.py:155)
-            if ((rc = enqueue_halfpel(c, steps[s].desc_off + l0, nl, spst)) != BVC_OK) return rc;
-            if (recon) {
-                for (int l = l0; l < l0 + nl; l++)
-                    if ((rc = download_plane(c, recon + (size_t)step_frames[s][l] * g.W * g.H, plane_ptr(c, step_outplane[s][l]), spst)) != BVC_OK)
-                        return rc;
-            }
-            if (spst != sm) {   // the next motion search of this group needs this step's reconstructions
-                CK(cudaEventRecord(c->ev_post[gi], spst));
-                CK(cudaStreamWaitEvent(sm, c->ev_post[gi], 0));
-            }
+            if (host_frames) CK(cudaEventRecord(ev_step[(s % D) * NG + gi], spst));   // this group is done with ring slot s % D
         }
+        if (s + 1 == nsteps || step_wave[s + 1] != w)
+            if ((rc = finish_wave(w)) != BVC_OK) return rc;
     }
-    if (NG > 1) {
-        for (int gi = 0; gi < NG; gi++) {
-            CK(cudaEventRecord(c->ev_post[gi], c->st_post[gi]));
-            CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
-            CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
-            CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
-            CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));
-            CK(cudaStreamWaitEvent(c->st, c->ev_pack[gi], 0));
-        }
-    }
-    // ---- container (encoder.py:104-121) assembled on the device, one download ----
-    ContainerArgs ca{};
-    ca.frame_bits = c->d_frame_bits; ca.coef_stream = c->d_coef_stream; ca.pred_stream = c->d_pred_stream;
-    ca.coef_cap_words = c->coef_cap_words; ca.pred_cap_words = c->pred_cap_words;
-    ca.frame_off = c->d_frame_off; ca.overflow = c->d_overflow;
-    ca.out = c->d_container; ca.out_cap = (long long)out_cap;
-    ca.nframes = nframes; ca.i_period = IP;
-    const int ec0 = tick(c);
-    CK(launch_container(ca, c->st));
-    span(c, BVC_K_PACK, ec0, tick(c));
-    c->launches += 2;
-    long long total = 0;
-    int overflow = 0;
-    CK(cudaMemcpyAsync(&total, c->d_frame_off + nframes, sizeof total, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(&overflow, c->d_overflow, sizeof overflow, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    if (overflow) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
-    if ((size_t)total > out_cap) {
-        *out_len = (size_t)total;   // what the caller has to provide
-        return fail(c, BVC_ERR_NOMEM, "output buffer too small (*out_len = bytes needed)");
-    }
-    if (!keep_on_device) CK(cudaMemcpyAsync(out, c->d_container, (size_t)total, cudaMemcpyDeviceToHost, c->st));
+    for (int w = flushed; w < nwaves; w++)
+        if ((rc = flush_wave(w)) != BVC_OK) return rc;
+    CK(cudaStreamWaitEvent(c->st, ev_frag_free[nwaves - 1], 0));
     CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st));
-    *out_len = (size_t)total;
-    c->container_len = (size_t)total;
+    CK(cudaStreamSynchronize(c->st_d2h));
+    *out_len = out_off;
+    c->container_len = out_off;
 
     // ---- instrumentation ----
     for (int i = 0; i < BVC_NUM_KERNEL_CLASSES; i++) { c->last_ms[i] = 0; c->last_launches[i] = 0; }
@@ -1533,5 +1639,19 @@ extern "C" int bvc_set_rate_control(bvc_ctx* c, int rc_flag, double frame_bit_bu
     }
     rc.frame_budget = frame_bit_budget;
     c->rc = rc;
+    return BVC_OK;
+}
+
+// Bytes reserved per frame for its coefficient bit stream on the device (0 = default: 6 bits per pixel, at least 1 MB;
+// values above the worst case are clamped to it).  Frees the slots; they are reallocated by the next clip call.
+extern "C" int bvc_set_stream_slot_bytes(bvc_ctx* c, size_t bytes) {
+    if (!c) return BVC_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));
+    c->slot_bytes = bytes;
+    c->coef_cap_words = default_coef_cap_words(c);
+    cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
+    c->d_coef_stream = c->d_pred_stream = nullptr; c->d_frame_bits = c->d_frame_off = nullptr;
+    c->stream_slots = 0;
     return BVC_OK;
 }

@@ -148,6 +148,7 @@ struct PackArgs {
     long long* row_bits;             // device [lanes][bh] (out) bits_per_row
     long long* pred_row_off;         // device [lanes][bh+1] scratch: prediction-stream offset of every row start
     size_t coef_cap_words, pred_cap_words;
+    int* slot_overflow;            // device flag: a frame's stream does not fit its slot (may be null)
     int bw, bh, nblk;
     int base_qp;
     int intra;                     // 1: modes, 0: motion vectors

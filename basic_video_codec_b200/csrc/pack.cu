@@ -129,7 +129,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
     for (int b = b0; b < b1; b++) { PredCode pc = pred_code(a, fl, b); psum += pc.len + pc.qlen; }
     long long ptot;
     long long ppre = block_exscan(psum, warp_sums, &ptot);
-    if (tid == 0) { a.frame_bits[2 * slot] = ptot; a.frame_bits[2 * slot + 1] = ctot; }
+    if (tid == 0) {
+        a.frame_bits[2 * slot] = ptot; a.frame_bits[2 * slot + 1] = ctot;
+        // the slots are sized for 6 bits per pixel by default, not for the worst case: tell the host instead of overrunning
+        if (a.slot_overflow && (((ctot + 31) >> 5) + 2 > (long long)a.coef_cap_words || ((ptot + 31) >> 5) + 2 > (long long)a.pred_cap_words))
+            atomicExch(a.slot_overflow, 1);
+    }
 
     // ---- zero the used part of both streams (+2 words of slack for the 3-word OR window) ----
     const long long cw = min((long long)a.coef_cap_words, ((ctot + 31) >> 5) + 2);
@@ -144,9 +149,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) pack_scan_kernel(PackArgs a) {
     for (int b = b0; b < b1; b++) {
         PredCode pc = pred_code(a, fl, b);
         if (b % a.bw == 0) prow[b / a.bw] = off;
-        if (pc.qlen) { put_bits_global_be(pstream, off, pc.qcode, pc.qlen); off += pc.qlen; }
-        put_bits_global_be(pstream, off, pc.code, pc.len);
-        off += pc.len;
+        if (((off + pc.qlen + pc.len + 31) >> 5) + 2 <= (long long)a.pred_cap_words) {
+            if (pc.qlen) put_bits_global_be(pstream, off, pc.qcode, pc.qlen);
+            put_bits_global_be(pstream, off + pc.qlen, pc.code, pc.len);
+        }
+        off += pc.qlen + pc.len;
     }
     if (tid == 0) prow[a.bh] = ptot;
     __syncthreads();
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) pack_emit_kernel(PackArgs a) {
     for (int j = 0; j <= n; j++) {
         const uint32_t lo = (j < n) ? src[j] : 0u;
         const uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
-        if (v) atomicOr(&dst[w0 + j], __byte_perm(v, 0, 0x0123));
+        if (v && w0 + j < (long long)a.coef_cap_words) atomicOr(&dst[w0 + j], __byte_perm(v, 0, 0x0123));
         hi = lo;
     }
 }
@@ -243,10 +250,11 @@ __global__ void __launch_bounds__(1024) container_scan_kernel(ContainerArgs a) {
 }
 
 __global__ void __launch_bounds__(256) container_copy_kernel(ContainerArgs a) {
-    const int f = blockIdx.y;
+  for (int f = blockIdx.y; f < a.nframes; f += gridDim.y) {
     const long long pb = (a.frame_bits[2 * f] + 7) >> 3, cb = (a.frame_bits[2 * f + 1] + 7) >> 3;
     const long long off = a.frame_off[f];
-    if (off + 6 + pb + cb > a.out_cap) return;       // host reports BVC_ERR_NOMEM from frame_off[nframes]
+    if (off + 6 + pb + cb > a.out_cap) continue;     // host reports BVC_ERR_NOMEM from frame_off[nframes]
+    if (pb > 4 * (long long)a.pred_cap_words || cb > 4 * (long long)a.coef_cap_words) continue;   // slot overflow, reported by pack_scan
     uint8_t* o = a.out + off;
     const uint8_t* ps = reinterpret_cast<const uint8_t*>(a.pred_stream + (size_t)f * a.pred_cap_words);
     const uint8_t* cs = reinterpret_cast<const uint8_t*>(a.coef_stream + (size_t)f * a.coef_cap_words);
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(256) container_copy_kernel(ContainerArgs a) {
         *reinterpret_cast<uint4*>(oc + head + (v << 4)) = val;
     }
     for (long long i = head + (nvec << 4) + t; i < cb; i += stride) oc[i] = cs[i];
+  }
 }
 
 }  // namespace
@@ -311,7 +320,7 @@ cudaError_t launch_container(const ContainerArgs& a, cudaStream_t st) {
     container_scan_kernel<<<1, 1024, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    dim3 grid(32, a.nframes);
+    dim3 grid(32, a.nframes < 65535 ? a.nframes : 65535);
     container_copy_kernel<<<grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }

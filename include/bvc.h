@@ -141,6 +141,12 @@ int bvc_container_download(bvc_ctx *ctx, uint8_t *dst, size_t offset, size_t len
 int bvc_host_register(void *ptr, size_t bytes);
 int bvc_host_unregister(void *ptr);
 
+/* Device memory of the clip calls does not grow with the clip: inputs pass through a ring of 6 steps x max_lanes planes, bit
+ * streams through one wave's (max_lanes x I_Period frames) slots.  A slot reserves 6 bits per pixel for a frame's
+ * coefficient stream by default (at least 1 MB, at most the worst case of 26 bits per pixel); a frame that needs more
+ * makes the call fail with BVC_ERR_NOMEM -- raise the reservation here (0 = default, SIZE_MAX = worst case) and repeat. */
+int bvc_set_stream_slot_bytes(bvc_ctx *ctx, size_t bytes);
+
 /* Input stage: like bvc_clip_upload, for an I420 (YUV 4:2:0 planar) file image of src_w x src_h frames.  Only the luma
  * planes are transferred (read_y_component, assign1/ex2.py:14-28) and they are padded bottom / right with 128 to the
  * context's width / height (pad_frame, common.py:22-32), which must be src_w / src_h rounded up to block_size. */

@@ -193,3 +193,49 @@ def test_sharded_encoder_two_gpus_equals_single_gpu_stream():
     hw = hashlib.sha256(want).hexdigest()
     assert res[0] == (hw, hw)
     assert res[1] == (None, None)
+
+
+# ---- streaming clip path: input ring, per-wave container fragments, bounded stream slots ---------------------------------
+@pytest.mark.parametrize("frac,nref,lanes,groups", [(False, 1, 2, 2), (True, 2, 3, 2), (False, 2, 1, 1), (False, 1, 4, 1)])
+def test_many_waves_stream_through_the_rings(frac, nref, lanes, groups):
+    """41 frames, I_Period 3 -> 14 GOPs (a short last one) in waves of 1-4 lanes: 4-14 waves, 42 steps through the
+    6-step input ring, a container fragment per wave.  Stream, reconstruction and the resident path against the oracle."""
+    ob = _ob()
+    W, H, bs, r, qp, ip, n = 96, 64, 16, 8, 3, 3, 41
+    frames = synth.moving_clip(123, H, W, n, step=3, clamp=16)
+    cfg = ob.make_config(W, H, bs, r, qp, nref=nref, frac=frac, i_period=ip)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    with _ctx(W, H, bs, r, qp, nref, False, frac, ip=ip, lanes=lanes) as ctx:
+        ctx.set_lane_groups(groups)
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+        assert data == want
+        assert np.array_equal(recon, want_recon)
+        assert ctx.encode_clip(frames)[0] == want            # a second pass over the same rings
+        ctx.clip_upload(frames)
+        out, ln = ctx.encode_clip_resident(n)
+        assert bytes(out[:ln]) == want
+        assert ctx.encode_clip_device(frames) == len(want)    # fragments appended on the device
+        got = np.empty(len(want), np.uint8)
+        ctx.container_download(got)
+        assert bytes(got) == want
+
+
+def test_small_output_buffer_and_small_stream_slots_are_reported_not_overrun():
+    """Noise at QP 0: far more than the default reservations.  A too small host buffer and a too small device slot both
+    come back as BVC_ERR_NOMEM (MemoryError); the binding's retry path ends with the oracle's stream."""
+    ob = _ob()
+    W, H, bs, r, qp, ip, n = 96, 64, 16, 4, 0, 2, 6
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, size=(n, H, W), dtype=np.uint8)
+    want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip), frames, want_recon=False)
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=2) as ctx:
+        small = np.empty(len(want) // 2, np.uint8)
+        with pytest.raises(MemoryError):
+            ctx.encode_clip_into(frames, small)
+        ctx.set_stream_slot_bytes(2048)
+        big = np.empty(2 * len(want), np.uint8)
+        with pytest.raises(MemoryError, match="device slot"):
+            ctx.encode_clip_into(frames, big)
+        assert ctx.encode_clip(frames)[0] == want             # retries with the worst-case slot
+        ctx.set_stream_slot_bytes(0)
+        assert ctx.encode_clip(frames)[0] == want
