@@ -918,13 +918,12 @@ extern "C" int bvc_interp_halfpel(bvc_ctx* c, const uint8_t* ref, uint8_t* out2x
     std::vector<int> v{pl};
     if ((rc = upload_halfpel_desc(c, v, 0)) != BVC_OK) return rc;
     if ((rc = enqueue_halfpel(c, 0, 1)) != BVC_OK) return rc;
-    uint8_t* tmp = nullptr;
-    CK(cudaMalloc((void**)&tmp, (size_t)4 * g.W * g.H));
-    CK(launch_halfpel_interleave(plane_ptr(c, pl), g.W, g.H, g.pitch, g.plane_bytes, tmp, c->st));
+    struct DevTmp { void* p = nullptr; ~DevTmp() { cudaFree(p); } } tmp;   // freed on every exit path
+    CK(cudaMalloc(&tmp.p, (size_t)4 * g.W * g.H));
+    CK(launch_halfpel_interleave(plane_ptr(c, pl), g.W, g.H, g.pitch, g.plane_bytes, static_cast<uint8_t*>(tmp.p), c->st));
     c->launches += 1;
-    CK(cudaMemcpyAsync(out2x, tmp, (size_t)4 * g.W * g.H, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(out2x, tmp.p, (size_t)4 * g.W * g.H, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    cudaFree(tmp);
     return BVC_OK;
 }
 
@@ -940,6 +939,8 @@ extern "C" int bvc_dct_quant_recon(int device, const int16_t* residual, const in
         int16_t *dr = nullptr, *dp = nullptr, *dl = nullptr;
         uint8_t* dc = nullptr;
         double *di = nullptr, *dco = nullptr;
+        struct Free6 { void **a, **b, **c, **d, **e, **f; ~Free6() { cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*d); cudaFree(*e); cudaFree(*f); } }
+            guard{(void**)&dr, (void**)&dp, (void**)&dl, (void**)&dc, (void**)&di, (void**)&dco};   // freed on every exit path
         CK(dalloc(&dr, n)); CK(dalloc(&dp, n)); CK(dalloc(&dl, n)); CK(dalloc(&dc, n));
         if (idct) CK(dalloc(&di, n));
         if (coef) CK(dalloc(&dco, n));
@@ -951,7 +952,6 @@ extern "C" int bvc_dct_quant_recon(int device, const int16_t* residual, const in
         CK(cudaMemcpy(recon, dc, n, cudaMemcpyDeviceToHost));
         if (idct) CK(cudaMemcpy(idct, di, n * 8, cudaMemcpyDeviceToHost));
         if (coef) CK(cudaMemcpy(coef, dco, n * 8, cudaMemcpyDeviceToHost));
-        cudaFree(dr); cudaFree(dp); cudaFree(dl); cudaFree(dc); cudaFree(di); cudaFree(dco);
         return BVC_OK;
     };
     int rc = run();

@@ -1,8 +1,9 @@
 """GOP sharding across ranks: an I frame clears the reference window
 (reference encoder/encoder.py:174-178), so GOPs are independent units.  Every rank encodes a contiguous run of
-GOPs on its own GPU; there is no collective on the data path.  What the ranks exchange is one integer each (the
-length of their container fragment); every rank then copies its fragment from device memory straight to its
-offset in a host buffer shared by the ranks of the node (a /dev/shm mapping, page-locked), so the serial stream
+GOPs on its own GPU; there is no collective on the data path -- not even for the bookkeeping: what the ranks exchange
+is one integer each (the length of their container fragment), through mailboxes in a host buffer shared by the ranks
+of the node (a /dev/shm mapping, page-locked).  Every rank then copies its fragment from device memory straight to
+its offset in that buffer, so the serial stream
 -- byte-identical to a single-GPU encode, the reference's encoded.bin layout (encoder.py:104-121) -- is written
 exactly once and rank 0 returns a view of it.
 """
@@ -37,11 +38,15 @@ def scaling_ceiling(ngop: int, world: int) -> float:
     return ngop / float(-(-ngop // world))
 
 
+_HDR = 4096      # bytes in front of the stream: per-rank mailboxes (see ShardedEncoder._exchange)
+
+
 class _SharedBuffer:
-    """A host buffer all ranks of the node map: a file in /dev/shm created by rank 0 (name broadcast once)."""
+    """A host buffer all ranks of the node map: a file in /dev/shm created by rank 0 (name broadcast once).  The first _HDR
+    bytes are the ranks' mailboxes, the stream follows."""
 
     def __init__(self, nbytes: int, rank: int, world: int):
-        self.nbytes = int(nbytes)
+        self.nbytes = int(nbytes) + _HDR
         self.path = None
         self.owner = rank == 0
         if world == 1:
@@ -63,8 +68,15 @@ class _SharedBuffer:
             dist.barrier()           # everyone has it mapped: the name can go
             if rank == 0:
                 os.unlink(self.path)
-        self.array = np.frombuffer(self.mm, dtype=np.uint8)
+        whole = np.frombuffer(self.mm, dtype=np.uint8)
+        self.mail = whole[:_HDR].view(np.int64).reshape(-1, 4)   # [rank] = (sequence, fragment bytes, done sequence, -)
+        if rank == 0:
+            self.mail[:] = 0
+        self.array = whole[_HDR:]
         self.registered = False
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()           # mailboxes zeroed before anyone posts
 
     def close(self):
         if self.registered:
@@ -72,6 +84,7 @@ class _SharedBuffer:
             host_unregister(self.array)
             self.registered = False
         self.array = None
+        self.mail = None
         try:
             self.mm.close()
         except BufferError:      # a view handed out by encode() is still alive: the mapping goes with it
@@ -97,7 +110,7 @@ class ShardedEncoder:
         self.capacity = int(capacity or (self.nframes * self.W * self.H // 2 + (1 << 20)))
         self.buf = _SharedBuffer(self.capacity, rank, world)
         self.ctx = None
-        self._sizes = None
+        self._seq = 0
         if encode_fn is None:
             from ._lib import Context, host_register
             if self.mine:
@@ -108,18 +121,43 @@ class ShardedEncoder:
             host_register(self.buf.array)
             self.buf.registered = True
 
-    # ---- the one exchange: fragment lengths ----
-    def _all_lengths(self, n: int) -> List[int]:
+    # ---- the one exchange: fragment lengths, through the mailboxes in the shared buffer ----
+    # All ranks run on one node (they share the host buffer), so the exchange is two 8-byte stores per rank and a spin on
+    # the other ranks' sequence numbers: a few microseconds, no collective, no GPU work.  (x86 / aarch64 store order
+    # within one writer: the length is written before the sequence number that announces it.)
+    def _post_length(self, n: int) -> List[int]:
+        self._seq += 1
         if self.world == 1:
             return [n]
-        import torch
-        import torch.distributed as dist
-        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-        mine = torch.tensor([n], dtype=torch.int64, device=dev)
-        if self._sizes is None or self._sizes.device != dev:
-            self._sizes = torch.empty(self.world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(self._sizes, mine)
-        return [int(x) for x in self._sizes.tolist()]
+        mail = self.buf.mail
+        mail[self.rank, 1] = n
+        mail[self.rank, 0] = self._seq
+        deadline = None
+        while True:
+            if bool((mail[:self.world, 0] >= self._seq).all()):
+                return [int(x) for x in mail[:self.world, 1]]
+            deadline = self._spin(deadline)
+
+    def _post_done(self):
+        if self.world == 1:
+            return
+        mail = self.buf.mail
+        mail[self.rank, 2] = self._seq
+        if self.rank != 0:
+            return
+        deadline = None
+        while not bool((mail[:self.world, 2] >= self._seq).all()):   # rank 0 hands out the stream: every fragment is in place
+            deadline = self._spin(deadline)
+
+    @staticmethod
+    def _spin(deadline):
+        import time
+        now = time.monotonic()
+        if deadline is None:
+            return now + 600.0
+        if now > deadline:
+            raise TimeoutError("a rank of the sharded encode did not post its fragment within 10 minutes")
+        return deadline
 
     def my_frames(self, frames: Optional[np.ndarray], load_gop: Optional[Callable[[int, int], np.ndarray]] = None):
         """The frames of this rank's GOPs: a view of `frames`, or load_gop(first, n) per GOP (only its own GOPs touched)."""
@@ -132,8 +170,9 @@ class ShardedEncoder:
 
     def encode(self, frames: Optional[np.ndarray] = None, load_gop: Optional[Callable[[int, int], np.ndarray]] = None,
                resident: bool = False):
-        """Encode the clip.  Returns a uint8 view of the whole container on rank 0, None elsewhere.  resident=True encodes
-        what upload() put in HBM (throughput measurements without the input transfer)."""
+        """Encode the clip.  Returns a uint8 view of the whole container on rank 0, None elsewhere (the view is valid until
+        the next encode() of any rank).  resident=True encodes what upload() put in HBM (throughput measurements without the
+        input transfer)."""
         data = None
         if not self.mine:
             n = 0
@@ -144,7 +183,7 @@ class ShardedEncoder:
             n = self.ctx.encode_clip_device(None, self.count)
         else:
             n = self.ctx.encode_clip_device(self.my_frames(frames, load_gop))
-        sizes = self._all_lengths(n)
+        sizes = self._post_length(n)
         total, off = sum(sizes), sum(sizes[:self.rank])
         if total > self.capacity:
             raise MemoryError(f"container of {total} bytes exceeds the shared buffer ({self.capacity})")
@@ -153,9 +192,7 @@ class ShardedEncoder:
                 self.buf.array[off:off + n] = np.frombuffer(data, dtype=np.uint8)
             else:
                 self.ctx.container_download(self.buf.array, off, 0, n)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.barrier()           # every fragment is in place
+        self._post_done()
         return self.buf.array[:total] if self.rank == 0 else None
 
     def upload(self, frames: Optional[np.ndarray] = None, load_gop=None):
