@@ -91,6 +91,8 @@ struct bvc_ctx {
     size_t h_totals_cap = 0;
     size_t slot_bytes = 0;            // bvc_set_stream_slot_bytes: 0 = default
     int* d_progress = nullptr;
+    uint32_t* d_top_mail = nullptr;   // [max_lanes][bh][bw][bs]: bottom rows handed down the I-frame wavefront (tq_iframe_kernel)
+    uint32_t epoch = 0;               // tag of the last I frame's mailbox entries
     int* d_ticket = nullptr;      // [max_lanes]: start-order counters of the wavefront kernels, one per lane group in flight
     MeLane* d_me_lanes = nullptr;
     FrameLane* d_fr_lanes = nullptr;
@@ -287,6 +289,8 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_rowbits, 1));
         CK(dalloc(&c->d_progress, L * g.bh));
         CK(dalloc(&c->d_ticket, L));
+        CK(dalloc(&c->d_top_mail, L * nb * bs));
+        CK(cudaMemset(c->d_top_mail, 0, L * nb * bs * sizeof(uint32_t)));   // epoch 0 = never posted
         CK(dalloc(&c->d_rc_remaining, L));
         CK(cudaMemset(c->d_ticket, 0, L * sizeof(int)));
         c->coef_cap_words = default_coef_cap_words(c);
@@ -326,7 +330,7 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
-    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_top_mail); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container); cudaFree(c->d_frag[0]); cudaFree(c->d_frag[1]);
@@ -569,6 +573,8 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.blk_bits = c->d_blk_bits + L0 * nb * c->blk_words; t.blk_nbits = c->d_blk_nbits + L0 * nb; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh; t.ticket = c->d_ticket + L0;
+    t.top_mail = c->d_top_mail + L0 * nb * g.bs;
+    if (sp.intra) { c->epoch = (c->epoch % 0xFFFFFEu) + 1; t.epoch = c->epoch; }   // one epoch per I frame (all its rows, also row by row)
     t.row_begin = 0; t.row_count = g.bh;
     // rate control (RCflag 1) on the clip path: the transform runs block row by block row, and the launch that
     // accounts a row's bits also picks the next row's QP -- the whole chain stays on the device, all lanes in lock step
@@ -599,7 +605,6 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         return BVC_OK;
     };
     if (sp.intra) {
-        CK(cudaMemsetAsync(t.progress, 0, (size_t)nl * g.bh * sizeof(int), st_post));
         const int e0 = tick(c, st_post);
         if (rc_rows) { int rcr = transform_rows(true); if (rcr != BVC_OK) return rcr; }
         else if (side_pack) { CK(launch_tq_iframe(t, nl, st_post, false)); c->launches += 1; }   // entropy coding follows on st_pack
@@ -845,6 +850,7 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress; t.ticket = c->d_ticket;
+    t.top_mail = c->d_top_mail; t.epoch = c->epoch;
     pk = PackArgs{};
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
     pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
@@ -862,9 +868,9 @@ extern "C" int bvc_frame_begin(bvc_ctx* c, const uint8_t* cur, const uint8_t* co
     c->row_open = false;
     if ((rc = frame_prepare(c, cur, refs, nref_avail, nullptr, intra != 0, &c->row_fl)) != BVC_OK) return rc;
     if (!intra && (rc = launch_me_lane0(c)) != BVC_OK) return rc;
-    CK(cudaMemsetAsync(c->d_progress, 0, (size_t)c->g.bh * sizeof(int), c->st));
     c->row_open = true;
     c->row_intra = intra != 0;
+    if (intra) c->epoch = (c->epoch % 0xFFFFFEu) + 1;   // all rows of this frame share one mailbox epoch
     c->row_nref = nref_avail;
     c->row_next = 0;
     return BVC_OK;

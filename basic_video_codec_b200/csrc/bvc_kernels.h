@@ -117,6 +117,9 @@ struct TqArgs {
     int frac;                      // MVs in half-pel units, pred from phase planes
     int multi_ref;                 // nRefFrames > 1: pred from refs[mv.ref] else refs[0]
     int* progress;                 // I frames: device [lanes][bh] wavefront progress counters (zeroed)
+    uint32_t* top_mail;            // I frames: device [lanes][bh][bw][bs] mailboxes: bottom row of the block above, every pixel
+                                   // as pixel | epoch << 8 (see tq_iframe_kernel)
+    uint32_t epoch;                // I frames: tag of this frame's mailbox entries (1 .. 2^24-1, never the previous frame's)
     int* ticket;                   // I frames: one self-resetting counter per launch in flight: a CTA's block row follows the
                                    // order in which CTAs actually start, so a row never waits for a CTA that is not resident
     int row_begin, row_count;      // block rows to encode in this launch (0, bh = whole frame); the row-by-row

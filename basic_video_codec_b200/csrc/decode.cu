@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
         bool polled = false;
         if (by > 0 && valid && x == 0 && seen < bx + 1) {
             polled = true;
-            while ((seen = *prog_up) < bx + 1) { __nanosleep(20); }
+            while ((seen = *prog_up) < bx + 1) {}   // pure spin: __nanosleep(20) sleeps for about a microsecond, a fifth of a block
         }
         if (__any_sync(0xffffffffu, polled)) __threadfence();
         __syncwarp();

@@ -43,8 +43,11 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
 // ---------------------------------------------------------------------------------------------
 // I frames: block (bx,by) needs the reconstructed right column of (bx-1,by) and bottom row of
 // (bx,by-1) (IFrame.py:184-213) => anti-diagonal wavefront.  One warp (= one CTA) walks one block row
-// of NBW *different frames* (lanes) left to right; rows are chained through per-row progress counters
-// in global memory (release/acquire), row r trailing row r-1 by one block.
+// of NBW *different frames* (lanes) left to right, row r trailing row r-1 by one block.  The hand-over between rows is
+// the data itself: a block posts its bottom row into a mailbox of 32-bit words, pixel | epoch << 8, and the block below
+// polls those words until they carry this frame's epoch.  One L2 round trip per block on the consumer side and plain
+// stores on the producer side -- no progress counter, no __threadfence in either warp (the counter + two fences + a
+// separate top-row load cost about a quarter of the 5 us a block took, profiles/r2_experiments.md).
 // grid = (bh * ceil(lanes/NBW)).  A CTA does not derive its row from blockIdx: it takes a ticket when it starts, and
 // tickets are handed out row-major.  The CTA of the row above therefore holds a smaller ticket, i.e. it is already
 // resident and running whenever this CTA waits for it -- forward progress does not depend on the order in which the
@@ -76,9 +79,10 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     uint8_t* recon_plane = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes;
     const uint8_t* cur_plane = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
     const int qp = a.qp_rows[(size_t)fl * a.bh + by];
-    volatile int* prog_up = (by > 0) ? a.progress + (size_t)fl * a.bh + (by - 1) : nullptr;
-    int* prog_me = a.progress + (size_t)fl * a.bh + by;
-    int seen = 0;                 // progress of the row above as last read (lane x == 0 of each frame)
+    // mailbox row `by` = bottom rows of block row by - 1 (written by the warp above), row by + 1 = ours for the warp below
+    const volatile uint32_t* mail_up = a.top_mail + (((size_t)fl * a.bh + by) * a.bw) * BS + x;
+    uint32_t* mail_dn = (by + 1 < a.bh && valid) ? a.top_mail + (((size_t)fl * a.bh + by + 1) * a.bw) * BS : nullptr;
+    const uint32_t tag = a.epoch << 8;
     uint32_t cw_next[BS / 4];     // the next block's current pixels are requested one block ahead
     load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch, cw_next);
 
@@ -88,19 +92,16 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
 #pragma unroll
         for (int i = 0; i < BS / 4; i++) cw[i] = cw_next[i];
         if (bx + 1 < a.bw) load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch + ox + BS, cw_next);
-        // wait until the block above is reconstructed; the row above usually runs several blocks ahead, so the counter is
-        // only read again when the last value seen does not cover this block
-        bool polled = false;
-        if (by > 0 && valid && x == 0 && seen < bx + 1) {
-            polled = true;
-            while ((seen = *prog_up) < bx + 1) { __nanosleep(20); }
+        // top neighbour: poll this lane's mailbox word until the block above has posted it for this frame; the left column
+        // was left in shared memory by this warp's previous block
+        int tv = 128;
+        if (oy > 0 && valid) {
+            uint32_t v = mail_up[bx * BS];
+            while ((v & 0xffffff00u) != tag) v = mail_up[bx * BS];   // pure spin: __nanosleep(20) costs about a microsecond here (1.24 against 0.91 ms per I step)
+            tv = (int)(v & 255u);
         }
-        if (__any_sync(0xffffffffu, polled)) __threadfence();
         __syncwarp();
-        // top neighbours come from the plane (bypass L1: written by another SM); the left column was left in shared
-        // memory by this warp's previous block
         const int lv = (ox > 0) ? (int)sm.left[q][x] : 128;
-        const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
         if (ox == 0) sm.left[q][x] = 128;
         sm.top[q][x] = (uint8_t)tv;
         store_row_words<BS>(&t.cur[q][x][0], cw);
@@ -143,11 +144,7 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         o.resid_pitch = a.W;
         o.idct_out = nullptr;
         o.coef_out = nullptr;
-        tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, true, &sm.left[0][0]);
-        // publish: reconstruction of (bx,by) is visible before the counter moves
-        __threadfence();
-        __syncwarp();
-        if (valid && x == 0) atomicExch(prog_me, bx + 1);
+        tq_warp<BS>(t, lane, valid, qp, o, nullptr, nullptr, true, &sm.left[0][0], mail_dn ? mail_dn + bx * BS : nullptr, tag);
     }
 }
 

@@ -170,7 +170,7 @@ __device__ __forceinline__ void stage_row(WarpTile<BS>& t, int q, int r, const u
 template <int BS, bool DBG = true>
 __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, int qp, const TqOut& o,
                                         const int16_t* res_override, const int16_t* pred_override, bool intra_u8_resid,
-                                        uint8_t* last_col = nullptr) {
+                                        uint8_t* last_col = nullptr, uint32_t* mail_row = nullptr, uint32_t mail_tag = 0) {
     const int q = lane / BS, x = lane % BS;
     double a[BS], r[BS];
     // ---- forward pass 1: columns (apply_dct_2d transforms columns first, dct.py:12) ----
@@ -263,6 +263,19 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         // the intra wavefront predicts the next block of the row from this block's right column: hand it over in shared
         // memory instead of reading it back from the plane
         if (last_col) last_col[q * BS + y] = (uint8_t)(ow[BS / 4 - 1] >> 24);
+        // ... and the block below predicts from this block's bottom row: post it in the row's mailbox, every pixel tagged
+        // with the launch epoch, so that the consumer polls the data itself (no counter, no fence on either side)
+        if (mail_row && y == BS - 1) {
+#pragma unroll
+            for (int i = 0; i < BS; i += 4) {
+                uint4 v;
+                v.x = ((ow[i >> 2]) & 255u) | mail_tag;
+                v.y = ((ow[i >> 2] >> 8) & 255u) | mail_tag;
+                v.z = ((ow[i >> 2] >> 16) & 255u) | mail_tag;
+                v.w = (ow[i >> 2] >> 24) | mail_tag;
+                __stcg(reinterpret_cast<uint4*>(mail_row + i), v);
+            }
+        }
     }
     __syncwarp();
 }
