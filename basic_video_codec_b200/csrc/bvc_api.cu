@@ -49,6 +49,7 @@ struct bvc_ctx {
     // scheduler does not place a second kernel's CTAs next to a kernel that still has CTAs to dispatch
     // (profiles/microbench/cosched.cu), so this buys the tails (~1.5 %), not a transform-under-search overlap.
     int ngroups = 2;
+    int tq_cta_cap = 0;   // clip path with lane groups: CTAs of the P transform launch (0 = one per work unit), BVC_TQ_CTAS
     int tail_split = 1;   // motion search: tiles of the last, partly filled wave as one-row CTAs (BVC_TAIL_SPLIT=0 turns it off)
     cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
     // st_pack: entropy coding of I levels + stream assembly.  Nothing of the next step's search needs them (it needs the
@@ -269,6 +270,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
+        if (const char* e = getenv("BVC_TQ_CTAS")) c->tq_cta_cap = std::max(0, atoi(e));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;
         CK(cudaMalloc((void**)&c->ref_pool, c->ref_planes * g.plane_bytes + 4096));
@@ -576,6 +578,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.top_mail = c->d_top_mail + L0 * nb * g.bs;
     if (sp.intra) { c->epoch = (c->epoch % 0xFFFFFEu) + 1; t.epoch = c->epoch; }   // one epoch per I frame (all its rows, also row by row)
     t.row_begin = 0; t.row_count = g.bh;
+    t.cta_cap = (!frame_api && st_post != st_me) ? c->tq_cta_cap : 0;   // beside the other group's search: see tq_pframe_kernel
     // rate control (RCflag 1) on the clip path: the transform runs block row by block row, and the launch that
     // accounts a row's bits also picks the next row's QP -- the whole chain stays on the device, all lanes in lock step
     const bool rc_rows = !frame_api && c->rc.n > 0;

@@ -8,6 +8,7 @@
 // and the per-block part of entropy_encode_dct_coffs_row (encoder/Frame.py:61-75).
 #include "bvc_kernels.h"
 #include "tq_device.cuh"
+#include <algorithm>
 
 namespace bvc {
 namespace {
@@ -21,9 +22,14 @@ struct TqCtaSmem {
 };
 
 // ---------------------------------------------------------------------------------------------
-// P frames: every block independent.  grid = (ceil(nblk / (TQ_WARPS*NBW)), lanes)
+// P frames: every block independent.  A work unit = TQ_WARPS*NBW consecutive blocks of one lane; grid = min(units, a.cta_cap)
+// CTAs, each looping over units.  The cap matters on the clip path: this kernel runs on a high-priority stream while the
+// other lane group's search is on the GPU, and the block scheduler hands a high-priority kernel *every* slot the search
+// frees until it has no CTA left to place -- an uncapped grid evicts the search 1:1.  Capped at about one search CTA's
+// registers per SM (3 CTAs), the transform (fp64 pipe / issue bound) runs beside one search CTA per SM (ALU pipe bound,
+// which alone still reaches 86 % of the two-CTA rate), so most of its time disappears under the search.
 template <int BS, bool DBG>
-__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
+__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, int units_x, int units) {
     constexpr int NBW = 32 / BS;
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
@@ -31,13 +37,17 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a) {
     build_zigzag<BS>(sm.zz, threadIdx.x, blockDim.x);
     __syncthreads();
     WarpTile<BS>& t = sm.w[warp];
-    const int fl = blockIdx.y;
     const int q = lane / BS;
     const int blk_begin = a.row_begin * a.bw, blk_end = (a.row_begin + a.row_count) * a.bw;
-    const int b = blk_begin + (blockIdx.x * TQ_WARPS + warp) * NBW + q;
-    const bool valid = b < blk_end;
-    const int bb = valid ? b : blk_end - 1;
-    tq_pframe_warp<BS, DBG>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
+#pragma unroll 1
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int fl = u / units_x, ux = u - fl * units_x;
+        const int b = blk_begin + (ux * TQ_WARPS + warp) * NBW + q;
+        const bool valid = b < blk_end;
+        const int bb = valid ? b : blk_end - 1;
+        tq_pframe_warp<BS, DBG>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
+        __syncwarp();   // the tile is this warp's alone, but the next unit restages it
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,8 +230,9 @@ cudaError_t launch_pd(const TqArgs& a, int lanes, cudaStream_t st) {
         once = true;
     }
     const int nb = a.row_count * a.bw;
-    dim3 grid((nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), lanes);
-    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(a);
+    const int units_x = (nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), units = units_x * lanes;
+    const int grid = a.cta_cap > 0 ? std::min(units, a.cta_cap) : units;
+    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(a, units_x, units);
     return cudaGetLastError();
 }
 template <int BS>
