@@ -49,6 +49,7 @@ struct bvc_ctx {
     // scheduler does not place a second kernel's CTAs next to a kernel that still has CTAs to dispatch
     // (profiles/microbench/cosched.cu), so this buys the tails (~1.5 %), not a transform-under-search overlap.
     int ngroups = 2;
+    int iquad = 1;        // I-frame wavefront with four warps per block pair (BVC_IQUAD=0: the one-warp kernel)
     int tq_cta_cap = 0;   // clip path with lane groups: CTAs of the P transform launch (0 = one per work unit), BVC_TQ_CTAS
     int tail_split = 1;   // motion search: tiles of the last, partly filled wave as one-row CTAs (BVC_TAIL_SPLIT=0 turns it off)
     cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
@@ -270,6 +271,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
+        if (const char* e = getenv("BVC_IQUAD")) c->iquad = atoi(e) != 0;
         if (const char* e = getenv("BVC_TQ_CTAS")) c->tq_cta_cap = std::max(0, atoi(e));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;
@@ -578,6 +580,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.top_mail = c->d_top_mail + L0 * nb * g.bs;
     if (sp.intra) { c->epoch = (c->epoch % 0xFFFFFEu) + 1; t.epoch = c->epoch; }   // one epoch per I frame (all its rows, also row by row)
     t.row_begin = 0; t.row_count = g.bh;
+    t.quad = c->iquad;
     t.cta_cap = (!frame_api && st_post != st_me) ? c->tq_cta_cap : 0;   // beside the other group's search: see tq_pframe_kernel
     // rate control (RCflag 1) on the clip path: the transform runs block row by block row, and the launch that
     // accounts a row's bits also picks the next row's QP -- the whole chain stays on the device, all lanes in lock step
@@ -853,7 +856,7 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
     t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress; t.ticket = c->d_ticket;
-    t.top_mail = c->d_top_mail; t.epoch = c->epoch;
+    t.top_mail = c->d_top_mail; t.epoch = c->epoch; t.quad = c->iquad;
     pk = PackArgs{};
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
     pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;

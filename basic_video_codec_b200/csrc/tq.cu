@@ -158,6 +158,131 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
     }
 }
 
+// The same wavefront with a block pair spread over the four schedulers of an SM (BS = 8, 16): one CTA of four warps per
+// (block row, NBW lanes).  Warp 0 runs the serial part of a block -- poll the top row, decide the mode, form the
+// residual -- then each of the four passes of the transform is split four ways (tq_device.cuh, quad_*), with a CTA barrier
+// between passes; afterwards warp 0 posts the bottom row and the right column (what the next blocks wait for) while
+// warps 1 and 2 write the reconstruction and the levels to the planes.  Bit-identical to tq_iframe_kernel: every output is
+// the same fma chain.  Per 16x16 block pair ~3000 instead of ~9000 cycles (profiles/r2_experiments.md).
+template <int BS>
+__global__ void __launch_bounds__(128) tq_iframe_quad_kernel(TqArgs a, int lanes) {
+    constexpr int NBW = 32 / BS;
+    struct QSmem {
+        QuadTile<BS> t;
+        __align__(16) uint8_t left[NBW][BS];
+        int ticket;
+    };
+    extern __shared__ __align__(16) uint8_t smraw[];
+    QSmem& sm = *reinterpret_cast<QSmem*>(smraw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        const int tk = atomicAdd(a.ticket, 1);
+        if (tk == (int)gridDim.x - 1) atomicExch(a.ticket, 0);
+        sm.ticket = tk;
+    }
+    __syncthreads();
+    const int ngrp = (lanes + NBW - 1) / NBW;
+    const int tk = sm.ticket;
+    const int by = a.row_begin + tk / ngrp, grp = tk % ngrp;
+    const int q = lane / BS, x = lane % BS;
+    const int fl_raw = grp * NBW + q;
+    const bool valid = fl_raw < lanes;
+    const int fl = valid ? fl_raw : lanes - 1;
+    const FrameLane& L = a.lanes[fl];
+    const int oy = by * BS;
+    QuadTile<BS>& t = sm.t;
+    uint8_t* recon_plane = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes;
+    const uint8_t* cur_plane = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
+    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
+    const volatile uint32_t* mail_up = a.top_mail + (((size_t)fl * a.bh + by) * a.bw) * BS + x;
+    uint32_t* mail_dn = (by + 1 < a.bh && valid) ? a.top_mail + (((size_t)fl * a.bh + by + 1) * a.bw) * BS : nullptr;
+    const uint32_t tag = a.epoch << 8;
+    uint32_t cw_next[BS / 4];
+    if (warp == 0) load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch, cw_next);
+
+    for (int bx = 0; bx < a.bw; bx++) {
+        const int ox = bx * BS;
+        if (warp == 0) {
+            uint32_t cw[BS / 4];
+#pragma unroll
+            for (int i = 0; i < BS / 4; i++) cw[i] = cw_next[i];
+            if (bx + 1 < a.bw) load_row_aligned<BS>(cur_plane + (size_t)(oy + x) * a.cur_pitch + ox + BS, cw_next);
+            int tv = 128;
+            if (oy > 0 && valid) {
+                uint32_t v = mail_up[bx * BS];
+                while ((v & 0xffffff00u) != tag) v = mail_up[bx * BS];
+                tv = (int)(v & 255u);
+            }
+            const int lv = (ox > 0) ? (int)sm.left[q][x] : 128;   // written by this warp at the end of the previous block
+            __syncwarp();
+            if (ox == 0) sm.left[q][x] = 128;
+            store_row_words<BS>(&t.cur[q][x][0], cw);
+            __syncwarp();
+            // mode decision, IFrame.py:184-195 (see tq_iframe_kernel)
+            int sh = 0, sv = 0;
+#pragma unroll
+            for (int i = 0; i < BS; i++) {
+                const int ch = t.cur[q][i][x];
+                sh += (ox > 0) ? ((ch - lv) & 255) : abs(ch - 128);
+                const int cv = t.cur[q][x][i];
+                sv += (oy > 0) ? ((cv - tv) & 255) : abs(cv - 128);
+            }
+#pragma unroll
+            for (int d = 1; d < BS; d <<= 1) {
+                sh += __shfl_xor_sync(0xffffffffu, sh, d);
+                sv += __shfl_xor_sync(0xffffffffu, sv, d);
+            }
+            const int mode = (sh < sv) ? 0 : 1;
+            uint32_t pw[BS / 4];
+#pragma unroll
+            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i] : (uint32_t)tv * 0x01010101u;
+            stage_row<BS>(t, q, x, cw, pw);
+            if (valid && x == 0) {
+                a.modes[(size_t)fl * a.nblk + by * a.bw + bx] = mode;
+                a.isad[(size_t)fl * a.nblk + by * a.bw + bx] = mode == 0 ? sh : sv;
+            }
+            if (a.resid_mc) __syncwarp();   // warp-uniform
+            if (a.resid_mc && valid) {   // debug plane of the frame-level calls: the int16 residual as uint8 (IFrame.py:30,57-58)
+                int8_t* d = a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox;
+#pragma unroll
+                for (int y = 0; y < BS; y++) d[(size_t)y * a.W + x] = (int8_t)(uint8_t)t.res[q][y][x];
+            }
+        }
+        __syncthreads();
+        BVC_QUAD_DISPATCH(quad_f1, warp, t, q, x)
+        __syncthreads();
+        BVC_QUAD_DISPATCH(quad_f2, warp, t, q, x, qp)
+        __syncthreads();
+        BVC_QUAD_DISPATCH(quad_i1, warp, t, q, x)
+        __syncthreads();
+        BVC_QUAD_DISPATCH(quad_i2, warp, t, q, x)
+        __syncthreads();
+        if (warp == 0) {
+            // what the neighbours wait for: the bottom row for the block below (one tagged word per pixel, lane x -> pixel x),
+            // the right column for this warp's next block
+            if (mail_dn) __stcg(mail_dn + bx * BS + x, (uint32_t)t.rec[q][BS - 1][x] | tag);
+            sm.left[q][x] = t.rec[q][x][BS - 1];
+        } else if (warp == 1) {
+            if (valid) {
+                uint32_t ow[BS / 4];
+                load_row_aligned<BS>(&t.rec[q][x][0], ow);
+                store_row_words<BS>(recon_plane + (size_t)(oy + x) * a.ref_pitch + ox, ow);
+            }
+        } else if (warp == 2) {
+            if (valid && a.levels) {
+                const uint32_t* ls = reinterpret_cast<const uint32_t*>(&t.lev[q][x][0]);
+                uint32_t* lg = reinterpret_cast<uint32_t*>(a.levels + ((size_t)fl * a.H + oy + x) * a.W + ox);
+                if constexpr (BS == 16) {
+                    *reinterpret_cast<uint4*>(lg) = *reinterpret_cast<const uint4*>(ls);
+                    *reinterpret_cast<uint4*>(lg + 4) = *reinterpret_cast<const uint4*>(ls + 4);
+                } else {
+                    *reinterpret_cast<uint4*>(lg) = *reinterpret_cast<const uint4*>(ls);
+                }
+            }
+        }
+    }
+}
+
 // Entropy coding of I-frame blocks from the level plane the wavefront kernel wrote (frame layout, a.levels): one warp
 // per block, every block independent -- kept out of the wavefront so that the serial chain through a frame is only
 // predict -> transform -> reconstruct.  grid = (ceil(blocks / TQ_WARPS), lanes)
@@ -263,7 +388,23 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st, bool with_entr
         once = true;
     }
     if (!a.levels) return cudaErrorInvalidValue;   // the level plane feeds the entropy kernel
-    tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
+    if constexpr (BS >= 8) {
+        // Four warps per block pair shorten the dependent chain (one 16x16 block step 4.8 -> 2.9 us), but the rows of a frame
+        // run in lock step, so every CTA of an SM is in the same pass at the same time: beyond about two CTAs per SM the passes
+        // queue for the SM's fp64 pipe and shared memory and the gain is gone (20 lanes of 1080p: 0.94 against 0.91 ms per I
+        // step; 3 lanes: 0.54 against 1.11, profiles/r2_iframe_quad.jsonl).
+        static int sms_dev[BVC_MAX_DEVICES] = {};
+        int& sms = sms_dev[current_device_slot()];
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        }
+        if (a.quad && a.row_count * ngrp <= 2 * sms) tq_iframe_quad_kernel<BS><<<a.row_count * ngrp, 128, sizeof(QuadTile<BS>) + NBW * BS + 32, st>>>(a, lanes);
+        else tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
+    } else {
+        tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !with_entropy) return e;
     return launch_ie<BS>(a, lanes, st);

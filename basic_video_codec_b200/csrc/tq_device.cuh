@@ -137,8 +137,8 @@ __device__ __forceinline__ void store_row_words(void* dst, const uint32_t (&w)[B
 }
 
 // Stage row r of block q: cur and pred bytes (as words) -> t.cur / t.pred / t.res (int16 residual).
-template <int BS>
-__device__ __forceinline__ void stage_row(WarpTile<BS>& t, int q, int r, const uint32_t (&cw)[BS / 4], const uint32_t (&pw)[BS / 4]) {
+template <int BS, typename Tile>
+__device__ __forceinline__ void stage_row(Tile& t, int q, int r, const uint32_t (&cw)[BS / 4], const uint32_t (&pw)[BS / 4]) {
     store_row_words<BS>(&t.cur[q][r][0], cw);
     store_row_words<BS>(&t.pred[q][r][0], pw);
     uint32_t rw[BS / 2];
@@ -279,6 +279,134 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
     }
     __syncwarp();
 }
+
+// ---------------------------------------------------------------------------------------------
+// The same transform spread over four warps (I-frame wavefront, tq.cu): the wavefront is a chain of bw + bh dependent
+// blocks, each walked by a single warp -- ~9000 cycles per 16x16 block pair, two thirds of it the 512 DFMA + ~220 other
+// fp64 operations every lane issues on ONE scheduler while the SM's other three idle.  Here a block pair belongs to a CTA
+// of four warps (one per scheduler): lane -> (q, line) as before, but warp WQ computes only BS/4 of each line's outputs
+// (forward: u or v in [WQ*BS/4, (WQ+1)*BS/4); inverse: the BS/8 mirrored pairs y, BS-1-y with y in [WQ*BS/8, ...)).
+// Every output is the same fma chain as in fold_fwd / fold_inv (same operands, same order), so the results are
+// bit-identical to tq_warp.  Lines are exchanged through two fp64 tiles (A: F1 -> F2, I1 -> I2; B: F2 -> I1) with one
+// CTA barrier per pass, issued by the caller (all four warps meet at the same barrier instruction).
+template <int BS>
+struct QuadTile {
+    static constexpr int NBW = 32 / BS;
+    double A[NBW][BS][BS + 1];
+    double B[NBW][BS][BS + 1];
+    __align__(16) int16_t lev[NBW][BS][BS];
+    __align__(16) int16_t res[NBW][BS][BS];
+    __align__(16) uint8_t cur[NBW][BS][BS];
+    __align__(16) uint8_t pred[NBW][BS][BS];
+    __align__(16) uint8_t rec[NBW][BS][BS];
+};
+
+// F1: columns of the residual (dct.py:12), outputs u of warp WQ -> A[q][u][x]
+template <int BS, int WQ>
+__device__ __forceinline__ void quad_f1(QuadTile<BS>& t, int q, int x) {
+    constexpr int Hh = BS / 2, UW = BS / 4;
+    double s[Hh], d[Hh];
+#pragma unroll
+    for (int y = 0; y < Hh; y++) {
+        const double lo = int_to_double((int)t.res[q][y][x]), hi = int_to_double((int)t.res[q][BS - 1 - y][x]);
+        s[y] = __dadd_rn(lo, hi);
+        d[y] = __dsub_rn(lo, hi);
+    }
+#pragma unroll
+    for (int k = 0; k < UW; k++) {
+        const int u = WQ * UW + k;
+        double acc = 0.0;
+#pragma unroll
+        for (int x2 = 0; x2 < Hh; x2++) acc = __fma_rn(DctC<BS>::ct(u * BS + x2), (u & 1) ? d[x2] : s[x2], acc);
+        t.A[q][u][x] = acc;
+    }
+}
+// F2: rows (this lane owns row u = x), outputs v of warp WQ, quantise / rescale -> lev[q][u][v], B[q][u][v]
+template <int BS, int WQ>
+__device__ __forceinline__ void quad_f2(QuadTile<BS>& t, int q, int x, int qp) {
+    constexpr int Hh = BS / 2, UW = BS / 4;
+    const int u = x;
+    double s[Hh], d[Hh];
+#pragma unroll
+    for (int i = 0; i < Hh; i++) {
+        const double lo = t.A[q][u][i], hi = t.A[q][u][BS - 1 - i];
+        s[i] = __dadd_rn(lo, hi);
+        d[i] = __dsub_rn(lo, hi);
+    }
+    const bool su = (u == 0) || (2 * u == BS);
+    const double w_sp = su ? DctC<BS>::w(0) : DctC<BS>::w(1);
+    const double w_nm = su ? DctC<BS>::w(1) : DctC<BS>::w(2);
+    short lv[UW];
+#pragma unroll
+    for (int k = 0; k < UW; k++) {
+        const int v = WQ * UW + k;
+        double acc = 0.0;
+#pragma unroll
+        for (int x2 = 0; x2 < Hh; x2++) acc = __fma_rn(DctC<BS>::ct(v * BS + x2), (v & 1) ? d[x2] : s[x2], acc);
+        const bool sv = (v == 0) || (2 * v == BS);
+        const double w = sv ? w_sp : w_nm;
+        const double coef = __dmul_rn(acc, w);
+        const int sh = qp + min(max(u + v - (BS - 2), 0), 2);
+        int li;
+        const double lq = rint_magic(__dmul_rn(coef, pow2_neg(sh)), li);
+        lv[k] = (short)li;
+        const double wq = __hiloint2double(__double2hiint(w) + (sh << 20), __double2loint(w));
+        t.B[q][u][v] = __dmul_rn(lq, wq);
+    }
+    uint32_t* ls = reinterpret_cast<uint32_t*>(&t.lev[q][u][WQ * UW]);
+#pragma unroll
+    for (int k = 0; k < UW / 2; k++) ls[k] = (uint32_t)(uint16_t)lv[2 * k] | ((uint32_t)(uint16_t)lv[2 * k + 1] << 16);
+}
+// I1: over u for column v = x, mirrored output pairs of warp WQ -> A[q][y][x]
+template <int BS, int WQ>
+__device__ __forceinline__ void quad_i1(QuadTile<BS>& t, int q, int x) {
+    constexpr int PW = BS / 8;
+    double a[BS];
+#pragma unroll
+    for (int i = 0; i < BS; i++) a[i] = t.B[q][i][x];
+#pragma unroll
+    for (int p = 0; p < PW; p++) {
+        const int y = WQ * PW + p;
+        double e = 0.0, o = 0.0;
+#pragma unroll
+        for (int u = 0; u < BS; u += 2) e = __fma_rn(DctC<BS>::ct(u * BS + y), a[u], e);
+#pragma unroll
+        for (int u = 1; u < BS; u += 2) o = __fma_rn(DctC<BS>::ct(u * BS + y), a[u], o);
+        t.A[q][y][x] = __dadd_rn(e, o);
+        t.A[q][BS - 1 - y][x] = __dsub_rn(e, o);
+    }
+}
+// I2: over v for row y = x, mirrored pixel pairs of warp WQ; reconstruct_block Frame.py:197-202 -> rec[q][y][i]
+template <int BS, int WQ>
+__device__ __forceinline__ void quad_i2(QuadTile<BS>& t, int q, int x) {
+    constexpr int PW = BS / 8;
+    const int y = x;
+    double a[BS];
+#pragma unroll
+    for (int i = 0; i < BS; i++) a[i] = t.A[q][y][i];
+#pragma unroll
+    for (int p = 0; p < PW; p++) {
+        const int i0 = WQ * PW + p;
+        double e = 0.0, o = 0.0;
+#pragma unroll
+        for (int u = 0; u < BS; u += 2) e = __fma_rn(DctC<BS>::ct(u * BS + i0), a[u], e);
+#pragma unroll
+        for (int u = 1; u < BS; u += 2) o = __fma_rn(DctC<BS>::ct(u * BS + i0), a[u], o);
+        const double r0 = __dadd_rn(e, o), r1 = __dsub_rn(e, o);
+        int v0, v1;
+        rint_magic(__dadd_rn(r0, int_to_double((int)t.pred[q][y][i0])), v0);
+        rint_magic(__dadd_rn(r1, int_to_double((int)t.pred[q][y][BS - 1 - i0])), v1);
+        t.rec[q][y][i0] = (uint8_t)min(max((int)(short)v0, 0), 255);
+        t.rec[q][y][BS - 1 - i0] = (uint8_t)min(max((int)(short)v1, 0), 255);
+    }
+}
+#define BVC_QUAD_DISPATCH(fn, warp, ...)                     \
+    switch (warp) {                                          \
+        case 0: fn<BS, 0>(__VA_ARGS__); break;               \
+        case 1: fn<BS, 1>(__VA_ARGS__); break;               \
+        case 2: fn<BS, 2>(__VA_ARGS__); break;               \
+        default: fn<BS, 3>(__VA_ARGS__); break;              \
+    }
 
 // ---------------------------------------------------------------------------------------------
 // zig-zag position table: zz[p] = row*BS + col (entropy_encoder.py:115-135):

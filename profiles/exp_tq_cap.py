@@ -18,7 +18,7 @@ from tests import synth  # noqa: E402
 W, H, BS, R, QP, IP = 1920, 1088, 16, 32, 4, 30
 lanes_list = [int(x) for x in sys.argv[1:]] or [20, 3]
 caps = [int(x) for x in os.environ.get("CAPS", "0,148,296,444,592,888").split(",")]
-groups_list = [int(x) for x in os.environ.get("GROUPS", "2,3,4").split(",")]
+groups_list = [int(x) for x in os.environ.get("LANE_GROUPS", "2,3,4").split(",")]
 base = synth.moving_clip(1080, H, W, IP * max(lanes_list), step=6, clamp=96, noise=2)
 for lanes in lanes_list:
     n = lanes * IP

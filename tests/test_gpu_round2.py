@@ -121,6 +121,32 @@ def test_tail_split_many_lanes_matches_oracle(monkeypatch):
         assert ctx.encode_clip(frames)[0] == want
 
 
+@pytest.mark.parametrize("bs", [8, 16])
+def test_iframe_quad_and_single_warp_wavefronts_match_oracle(bs, monkeypatch):
+    """The I-frame wavefront with four warps per block pair (few CTAs in flight) and with one (BVC_IQUAD=0, and any launch of
+    more than two CTAs per SM) are the same arithmetic: streams, reconstructions and the frame-level outputs (modes, levels,
+    residual plane) equal the oracle's for both, with an odd number of lanes (a half-filled warp) and the transform's
+    P-frame path (looping over work units under a CTA cap) after them."""
+    ob = _ob()
+    W, H, r, qp, ip, n = 160, 96, 4, 3, 3, 9
+    frames = synth.moving_clip(91 + bs, H, W, n, step=2, clamp=8)
+    cfg = ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    fo = ob.encode_iframe(cfg, frames[0])
+    for quad, cap in (("1", "0"), ("0", "0"), ("1", "7")):
+        monkeypatch.setenv("BVC_IQUAD", quad)
+        monkeypatch.setenv("BVC_TQ_CTAS", cap)
+        with _ctx(W, H, bs, r, qp, ip=ip, lanes=3) as ctx:
+            for groups in (1, 2):
+                ctx.set_lane_groups(groups)
+                data, recon = ctx.encode_clip(frames, want_recon=True)
+                assert data == want, (quad, cap, groups)
+                assert np.array_equal(recon, want_recon)
+            fg = ctx.encode_iframe(frames[0])
+            for k in ("recon", "levels", "modes", "resid_mc", "coef_bytes", "pred_bytes"):
+                assert np.array_equal(np.asarray(getattr(fg, k)), np.asarray(getattr(fo, k))), (quad, k)
+
+
 # ---- sharded job on the GPU ---------------------------------------------------------------------------------------------
 def test_sharded_encoder_single_rank_equals_clip_call():
     """world = 1 through the sharding API (container left on the device, fetched into the shared buffer) == the plain
