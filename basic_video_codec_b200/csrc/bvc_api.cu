@@ -434,7 +434,7 @@ static int ensure_streams(bvc_ctx* c, size_t slots) {
     CK(dalloc(&c->d_coef_stream, slots * c->coef_cap_words));
     CK(dalloc(&c->d_pred_stream, slots * c->pred_cap_words));
     CK(dalloc(&c->d_frame_bits, slots * 2));
-    CK(dalloc(&c->d_frame_off, slots + 1));
+    CK(dalloc(&c->d_frame_off, slots + BVC_MAX_GROUPS + 1));   // one offset table (n + 1 entries) per container part
     c->stream_slots = slots;
     return BVC_OK;
 }
@@ -1340,12 +1340,21 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     // staging for one wave's container fragment (x2: the download of wave w overlaps the assembly of wave w+1)
     // sized for 1 bit per pixel (the headline workload codes 0.5) unless an earlier call found that too small
     const size_t frag_worst = wave_frames * (6 + 4 * (c->coef_cap_words + c->pred_cap_words));
-    const size_t frag_cap = std::min(std::min(out_cap, frag_worst), std::max(c->frag_min, wave_frames * ((size_t)g.W * g.H / 8) + ((size_t)1 << 20)));
-    if ((rc = ensure_fragments(c, frag_cap, nwaves > 1 ? 2 : 1)) != BVC_OK) return rc;
+    // the staging of a wave is cut into one region per container part (lane group, see below); no region needs to hold
+    // more than the caller's buffer does
+    const int NG = std::max(1, std::min(c->ngroups, G));
+    const size_t frag_total = std::min(frag_worst, std::max(c->frag_min, wave_frames * ((size_t)g.W * g.H / 8) + ((size_t)1 << 20)));
+    const size_t region = std::min((out_cap + 255) & ~(size_t)255, (frag_total / NG + 256) & ~(size_t)255);
+    if ((rc = ensure_fragments(c, region * NG, nwaves > 1 ? 2 : 1)) != BVC_OK) return rc;
     if (keep_on_device && (rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
-    if ((rc = ensure_pinned(c, &c->h_totals, &c->h_totals_cap, ((size_t)nwaves + 1) * 16)) != BVC_OK) return rc;
-    long long* h_total = static_cast<long long*>(c->h_totals);          // [nwaves] fragment bytes
-    int* h_over = reinterpret_cast<int*>(h_total + nwaves);             // [nwaves] length-field overflow flags (2 ints per slot)
+    const int per = (G + NG - 1) / NG;
+    // A wave's container is laid out in NG parts, one per lane group (lanes are GOPs, a group's GOPs are consecutive in the
+    // stream): a part is assembled on its group's assembly stream right behind the group's last frame and sent off as soon
+    // as its size is known, so the first group's part travels while the last group still searches.
+    const size_t nparts = (size_t)nwaves * NG;
+    if ((rc = ensure_pinned(c, &c->h_totals, &c->h_totals_cap, (nparts + 1) * 16)) != BVC_OK) return rc;
+    long long* h_total = static_cast<long long*>(c->h_totals);          // [nwaves][NG] part bytes
+    int* h_over = reinterpret_cast<int*>(h_total + nparts);             // [nwaves][NG] overflow flags (2 ints per part)
 
     // ---- plan: one step per (wave, k); lane l of a step = GOP (wave*G + l) ----
     std::vector<StepPlan> steps;
@@ -1417,31 +1426,33 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     CK(bag.make(&ev_clip1));
     CK(cudaEventRecord(ev_clip0, c->st));
 
-    const int NG = std::max(1, std::min(c->ngroups, G));
-    const int per = (G + NG - 1) / NG;
     // "step s is finished by group gi" (its search and transform have read the input planes of ring slot s % D)
     std::vector<cudaEvent_t> ev_step((size_t)D * NG, nullptr);
     for (auto& e : ev_step) CK(bag.make(&e, cudaEventDisableTiming));
     // ---- input: uploaded step by step on its own stream so the copies overlap compute ----
-    std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps : 0);
+    std::vector<cudaEvent_t> ev_h2d(host_frames ? nsteps * NG : 0, nullptr);
     auto enqueue_upload = [&](size_t s) -> int {
         if (!host_frames || s >= nsteps) return BVC_OK;
         const std::vector<int>& fr = step_frames[s];
-        if (s >= (size_t)D)   // the slot's previous tenant: step s - D, every group
-            for (int gi = 0; gi < NG; gi++) CK(cudaStreamWaitEvent(c->st_h2d, ev_step[(s % D) * NG + gi], 0));
-        uint8_t* dst = c->in_pool + (size_t)(s % D) * G * g.plane_bytes;   // lanes of a step sit side by side in the ring
         const size_t fbytes = (size_t)g.W * g.H, spitch = (size_t)IP * fbytes;
-        if (g.pitch == g.W && fr.size() > 1 && spitch <= 0x7fffffffull && g.plane_bytes <= 0x7fffffffull) {
-            // the frames of a step are IP apart (frame k of consecutive GOPs): one strided copy, "row" = one plane
-            CK(cudaMemcpy2DAsync(dst, g.plane_bytes, host_frames + (size_t)fr[0] * fbytes, spitch, fbytes, fr.size(),
-                                 cudaMemcpyHostToDevice, c->st_h2d));
-        } else {
-            for (size_t l = 0; l < fr.size(); l++)
-                CK(cudaMemcpy2DAsync(dst + l * g.plane_bytes, g.pitch, host_frames + (size_t)fr[l] * fbytes, g.W, g.W, g.H,
+        // one copy per lane group, in group order: a group starts on a step as soon as ITS planes are there
+        for (int gi = 0; gi < NG; gi++) {
+            const int l0 = gi * per, nl = std::min((int)fr.size(), l0 + per) - l0;
+            if (nl <= 0) continue;
+            if (s >= (size_t)D) CK(cudaStreamWaitEvent(c->st_h2d, ev_step[(s % D) * NG + gi], 0));   // the slot's previous tenant: step s - D
+            uint8_t* dst = c->in_pool + ((size_t)(s % D) * G + l0) * g.plane_bytes;   // lanes of a step sit side by side in the ring
+            if (g.pitch == g.W && nl > 1 && spitch <= 0x7fffffffull && g.plane_bytes <= 0x7fffffffull) {
+                // the frames of a step are IP apart (frame k of consecutive GOPs): one strided copy, "row" = one plane
+                CK(cudaMemcpy2DAsync(dst, g.plane_bytes, host_frames + (size_t)fr[l0] * fbytes, spitch, fbytes, nl,
                                      cudaMemcpyHostToDevice, c->st_h2d));
+            } else {
+                for (int l = 0; l < nl; l++)
+                    CK(cudaMemcpy2DAsync(dst + l * g.plane_bytes, g.pitch, host_frames + (size_t)fr[l0 + l] * fbytes, g.W, g.W, g.H,
+                                         cudaMemcpyHostToDevice, c->st_h2d));
+            }
+            CK(bag.make(&ev_h2d[s * NG + gi], cudaEventDisableTiming));
+            CK(cudaEventRecord(ev_h2d[s * NG + gi], c->st_h2d));
         }
-        CK(bag.make(&ev_h2d[s], cudaEventDisableTiming));
-        CK(cudaEventRecord(ev_h2d[s], c->st_h2d));
         return BVC_OK;
     };
     if (host_frames) {
@@ -1465,62 +1476,64 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     }
     CK(cudaStreamWaitEvent(c->st_d2h, ev_clip0, 0));
 
-    // ---- end of a wave: container fragment (encoder.py:104-121) on the device, size to the host ----
-    std::vector<cudaEvent_t> ev_total(nwaves, nullptr), ev_frag_free(nwaves, nullptr), ev_slots_free(nwaves, nullptr);
+    // ---- end of a wave: container parts (encoder.py:104-121) on the device, sizes to the host ----
+    std::vector<cudaEvent_t> ev_total(nparts, nullptr), ev_frag_free(nparts, nullptr);
+    auto part_stream = [&](int gi) -> cudaStream_t { return NG == 1 ? c->st : c->st_pack[gi]; };
+    auto part_frames = [&](int w, int gi) -> int {
+        const long long n = std::min((long long)wave_nframes[w] - (long long)gi * per * IP, (long long)per * IP);
+        return n > 0 ? (int)n : 0;
+    };
     size_t out_off = 0;
-    int flushed = 0;       // waves whose fragment has been sent on its way
-    auto finish_wave = [&](int w) -> int {
-        if (NG > 1) {
-            for (int gi = 0; gi < NG; gi++) {
-                CK(cudaEventRecord(c->ev_post[gi], c->st_post[gi]));
-                CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
-                CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
-                CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
-                CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));
-                CK(cudaStreamWaitEvent(c->st, c->ev_pack[gi], 0));
-            }
-        }
-        if (w >= 2) CK(cudaStreamWaitEvent(c->st, ev_frag_free[w - 2], 0));   // staging buffer w & 1 has been copied out
+    int flushed = 0;       // waves whose parts have been sent on their way
+    auto finish_part = [&](int w, int gi) -> int {
+        const int n = part_frames(w, gi);
+        const size_t pi = (size_t)w * NG + gi;
+        h_total[pi] = 0; h_over[2 * pi] = h_over[2 * pi + 1] = 0;
+        if (n == 0) return BVC_OK;
+        cudaStream_t ps = part_stream(gi);   // behind the group's last stream assembly; the next wave's assembly follows on the same stream
+        if (w >= 2) CK(cudaStreamWaitEvent(ps, ev_frag_free[pi - 2 * NG], 0));   // staging buffer w & 1 has been copied out
+        const size_t first = (size_t)gi * per * IP;   // first frame slot of the part (a multiple of I_Period)
         ContainerArgs ca{};
-        ca.frame_bits = c->d_frame_bits; ca.coef_stream = c->d_coef_stream; ca.pred_stream = c->d_pred_stream;
+        ca.frame_bits = c->d_frame_bits + 2 * first;
+        ca.coef_stream = c->d_coef_stream + first * c->coef_cap_words; ca.pred_stream = c->d_pred_stream + first * c->pred_cap_words;
         ca.coef_cap_words = c->coef_cap_words; ca.pred_cap_words = c->pred_cap_words;
-        ca.frame_off = c->d_frame_off; ca.overflow = c->d_overflow;
-        ca.out = c->d_frag[w & 1]; ca.out_cap = (long long)c->frag_cap;
-        ca.nframes = wave_nframes[w]; ca.i_period = IP;
-        const int ec0 = tick(c);
-        CK(launch_container(ca, c->st));
-        span(c, BVC_K_PACK, ec0, tick(c));
+        ca.frame_off = c->d_frame_off + first + gi; ca.overflow = c->d_overflow;
+        ca.out = c->d_frag[w & 1] + (size_t)gi * region; ca.out_cap = (long long)region;
+        ca.nframes = n; ca.i_period = IP;
+        const int ec0 = tick(c, ps);
+        CK(launch_container(ca, ps));
+        span(c, BVC_K_PACK, ec0, tick(c, ps));
         c->launches += 2;
-        CK(cudaMemcpyAsync(&h_total[w], c->d_frame_off + wave_nframes[w], sizeof(long long), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(&h_over[2 * w], c->d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-        CK(bag.make(&ev_total[w], cudaEventDisableTiming));
-        CK(cudaEventRecord(ev_total[w], c->st));
-        // the next wave's assembly may overwrite the stream slots and frame sizes only after this
-        CK(bag.make(&ev_slots_free[w], cudaEventDisableTiming));
-        CK(cudaEventRecord(ev_slots_free[w], c->st));
+        CK(cudaMemcpyAsync(&h_total[pi], ca.frame_off + n, sizeof(long long), cudaMemcpyDeviceToHost, ps));
+        CK(cudaMemcpyAsync(&h_over[2 * pi], c->d_overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, ps));
+        CK(bag.make(&ev_total[pi], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_total[pi], ps));
         return BVC_OK;
     };
-    // host side of a finished wave: wait for its size, then send the fragment to its place
-    auto flush_wave = [&](int w) -> int {
-        CK(cudaEventSynchronize(ev_total[w]));
-        if (h_over[2 * w]) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
-        if (h_over[2 * w + 1]) return fail(c, BVC_ERR_NOMEM, "a frame's bit stream does not fit its device slot: raise it with bvc_set_stream_slot_bytes");
-        const size_t total = (size_t)h_total[w];
+    // host side of a finished part: wait for its size, then send it to its place
+    auto flush_part = [&](int w, int gi) -> int {
+        const size_t pi = (size_t)w * NG + gi;
+        if (!ev_total[pi]) return BVC_OK;   // no frames in this part
+        CK(cudaEventSynchronize(ev_total[pi]));
+        if (h_over[2 * pi]) return fail(c, BVC_ERR_OVERFLOW, "payload length does not fit the container field");
+        if (h_over[2 * pi + 1]) return fail(c, BVC_ERR_NOMEM, "a frame's bit stream does not fit its device slot: raise it with bvc_set_stream_slot_bytes");
+        const size_t total = (size_t)h_total[pi];
         if (out_off + total > out_cap) {
             // report what the whole clip needs, as far as it is known: at least this much
             *out_len = std::max(out_off + total, out_cap + 1);
             return fail(c, BVC_ERR_NOMEM, "output buffer too small (*out_len = a lower bound of the bytes needed)");
         }
-        if (total > c->frag_cap) {   // the wave's fragment did not fit its staging buffer: remember, the caller repeats the call
-            c->frag_min = total + total / 4;
+        if (total > region) {   // the part did not fit its staging region: remember, the caller repeats the call
+            c->frag_min = std::max(c->frag_min, (size_t)NG * (total + total / 4));
             *out_len = 0;
             return fail(c, BVC_ERR_NOMEM, "container staging buffer too small for this content: it has been enlarged, repeat the call");
         }
-        CK(cudaStreamWaitEvent(c->st_d2h, ev_total[w], 0));
-        if (keep_on_device) CK(cudaMemcpyAsync(c->d_container + out_off, c->d_frag[w & 1], total, cudaMemcpyDeviceToDevice, c->st_d2h));
-        else CK(cudaMemcpyAsync(out + out_off, c->d_frag[w & 1], total, cudaMemcpyDeviceToHost, c->st_d2h));
-        CK(bag.make(&ev_frag_free[w], cudaEventDisableTiming));
-        CK(cudaEventRecord(ev_frag_free[w], c->st_d2h));
+        CK(cudaStreamWaitEvent(c->st_d2h, ev_total[pi], 0));
+        const uint8_t* src = c->d_frag[w & 1] + (size_t)gi * region;
+        if (keep_on_device) CK(cudaMemcpyAsync(c->d_container + out_off, src, total, cudaMemcpyDeviceToDevice, c->st_d2h));
+        else CK(cudaMemcpyAsync(out + out_off, src, total, cudaMemcpyDeviceToHost, c->st_d2h));
+        CK(bag.make(&ev_frag_free[pi], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_frag_free[pi], c->st_d2h));
         out_off += total;
         return BVC_OK;
     };
@@ -1529,13 +1542,10 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     for (size_t s = 0; s < nsteps; s++) {
         const int w = step_wave[s];
         const bool wave_start = s == 0 || step_wave[s - 1] != w;
-        if (wave_start && w >= 1) {
-            // slots and frame sizes of the previous wave are free once its fragment is laid out
-            for (int gi = 0; gi < NG; gi++) CK(cudaStreamWaitEvent(NG == 1 ? c->st : c->st_pack[gi], ev_slots_free[w - 1], 0));
-            if (w >= 2) {   // wave w-2 has long finished: send its fragment off (this is the only host wait, a wave behind)
-                if ((rc = flush_wave(w - 2)) != BVC_OK) return rc;
-                flushed = w - 1;
-            }
+        if (wave_start && w >= 2) {   // wave w-2 has long finished: send its parts off (this is the only host wait, a wave behind)
+            for (int gi = 0; gi < NG; gi++)
+                if ((rc = flush_part(w - 2, gi)) != BVC_OK) return rc;
+            flushed = w - 1;
         }
         if (host_frames)
             if ((rc = enqueue_upload(s + 3)) != BVC_OK) return rc;
@@ -1544,8 +1554,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             cudaStream_t sm = NG == 1 ? c->st : c->st_grp[gi], spst = NG == 1 ? c->st : c->st_post[gi];
             if (nl > 0) {
                 if (host_frames) {
-                    CK(cudaStreamWaitEvent(sm, ev_h2d[s], 0));
-                    if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s], 0));
+                    CK(cudaStreamWaitEvent(sm, ev_h2d[s * NG + gi], 0));
+                    if (spst != sm) CK(cudaStreamWaitEvent(spst, ev_h2d[s * NG + gi], 0));
                 }
                 if ((rc = enqueue_step(c, steps[s], false, sm, spst, l0, nl, c->ev_me[gi], NG == 1 ? nullptr : c->st_pack[gi], c->ev_tq[gi],
                                        c->ev_pack[gi])) != BVC_OK) return rc;
@@ -1564,11 +1574,24 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
             if (host_frames) CK(cudaEventRecord(ev_step[(s % D) * NG + gi], spst));   // this group is done with ring slot s % D
         }
         if (s + 1 == nsteps || step_wave[s + 1] != w)
-            if ((rc = finish_wave(w)) != BVC_OK) return rc;
+            for (int gi = 0; gi < NG; gi++)
+                if ((rc = finish_part(w, gi)) != BVC_OK) return rc;
     }
     for (int w = flushed; w < nwaves; w++)
-        if ((rc = flush_wave(w)) != BVC_OK) return rc;
-    CK(cudaStreamWaitEvent(c->st, ev_frag_free[nwaves - 1], 0));
+        for (int gi = 0; gi < NG; gi++)
+            if ((rc = flush_part(w, gi)) != BVC_OK) return rc;
+    if (NG > 1) {   // everything the groups still have in flight (phase planes, reconstruction downloads) before the clip counts as done
+        for (int gi = 0; gi < NG; gi++) {
+            CK(cudaEventRecord(c->ev_post[gi], c->st_post[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_post[gi], 0));
+            CK(cudaEventRecord(c->ev_me[gi], c->st_grp[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_me[gi], 0));
+            CK(cudaEventRecord(c->ev_pack[gi], c->st_pack[gi]));
+            CK(cudaStreamWaitEvent(c->st, c->ev_pack[gi], 0));
+        }
+    }
+    for (int gi = 0; gi < NG; gi++)
+        if (ev_frag_free[(size_t)(nwaves - 1) * NG + gi]) CK(cudaStreamWaitEvent(c->st, ev_frag_free[(size_t)(nwaves - 1) * NG + gi], 0));
     CK(cudaEventRecord(ev_clip1, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaStreamSynchronize(c->st_d2h));
