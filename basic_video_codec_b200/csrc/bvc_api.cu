@@ -110,7 +110,8 @@ struct bvc_ctx {
     int fastme_direct = 0;  // bvc_set_fastme_direct: 0 auto (window walk / transfer tables), 1 direct evaluation, 2 SAD map + serial walk,
                             // 3 window walk, 4 SAD map + transfer tables
     DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
-        dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress;
+        dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress, dec_frame_ok, dec_step_frames,
+        dec_step_streams;
 
     // host staging
     void* h_desc = nullptr;       // pinned descriptor staging
@@ -341,7 +342,8 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     if (c->h_totals) cudaFreeHost(c->h_totals);
     for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
                              &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
-                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->sad_map, &c->fastme_tab})
+                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->dec_frame_ok, &c->dec_step_frames,
+                             &c->dec_step_streams, &c->sad_map, &c->fastme_tab})
         cudaFree(b->p);
     if (c->h_desc) cudaFreeHost(c->h_desc);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1031,82 +1033,9 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     const size_t nb = (size_t)g.nblk;
     int rc;
 
-    // ---- streams and chunk map ----
-    const int CB = eg_chunk_bits();
-    std::vector<EgStream> streams(2 * (size_t)n);
-    std::vector<uint8_t> intra(n);
-    long long nchunks = 0;
-    for (int f = 0; f < n; f++) {
-        intra[f] = (uint8_t)recs[f].intra;
-        for (int k = 0; k < 2; k++) {
-            EgStream& s = streams[2 * f + k];
-            s.byte0 = (long long)(k ? recs[f].coef_off : recs[f].pred_off);
-            s.nbits = 8LL * (long long)(k ? recs[f].coef_len : recs[f].pred_len);
-            s.chunk0 = nchunks;
-            s.sym0 = 0; s.nsym = 0; s.neob = 0; s.frame = f; s.kind = k;
-            nchunks += (s.nbits + CB - 1) / CB;
-        }
-    }
-    std::vector<int> chunk_stream((size_t)nchunks);
-    for (size_t si = 0; si < streams.size(); si++) {
-        const long long nc = (streams[si].nbits + CB - 1) / CB;
-        std::fill(chunk_stream.begin() + streams[si].chunk0, chunk_stream.begin() + streams[si].chunk0 + nc, (int)si);
-    }
-    uint8_t *d_in, *d_exit, *d_neob, *d_entry, *d_intra;
-    uint16_t* d_nsym;
-    EgStream* d_streams;
-    int *d_chunk_stream, *d_symbase, *d_eobbase, *d_blk_start, *d_progress;
-    int4* d_mv;
-    int32_t *d_modes, *d_qp;
-    long long* d_sym0;
-    int16_t *d_syms, *d_levels = nullptr;
-    FrameLane* d_lanes;
-    if ((rc = dbuf(c, c->dec_in, len, &d_in)) || (rc = dbuf(c, c->dec_streams, streams.size(), &d_streams)) ||
-        (rc = dbuf(c, c->dec_chunk_stream, (size_t)nchunks, &d_chunk_stream)) || (rc = dbuf(c, c->dec_exit, (size_t)nchunks * 32, &d_exit)) ||
-        (rc = dbuf(c, c->dec_nsym, (size_t)nchunks * 32, &d_nsym)) || (rc = dbuf(c, c->dec_neob, (size_t)nchunks * 32, &d_neob)) ||
-        (rc = dbuf(c, c->dec_entry, (size_t)nchunks, &d_entry)) || (rc = dbuf(c, c->dec_symbase, (size_t)nchunks, &d_symbase)) ||
-        (rc = dbuf(c, c->dec_eobbase, (size_t)nchunks, &d_eobbase)) || (rc = dbuf(c, c->dec_intra, (size_t)n, &d_intra)) ||
-        (rc = dbuf(c, c->dec_mv, (size_t)n * nb, &d_mv)) || (rc = dbuf(c, c->dec_modes, (size_t)n * nb, &d_modes)) ||
-        (rc = dbuf(c, c->dec_qp, (size_t)n * g.bh, &d_qp)) || (rc = dbuf(c, c->dec_blk_start, (size_t)n * (nb + 1), &d_blk_start)) ||
-        (rc = dbuf(c, c->dec_sym0, (size_t)n, &d_sym0)) || (rc = dbuf(c, c->dec_progress, (size_t)c->max_lanes * g.bh, &d_progress)))
-        return rc;
-    if (levels_out && (rc = dbuf(c, c->dec_levels, (size_t)n * g.W * g.H, &d_levels))) return rc;
-    CK(cudaMemsetAsync(d_in + len, 0, 256, c->st));
-    CK(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(d_streams, streams.data(), streams.size() * sizeof(EgStream), cudaMemcpyHostToDevice, c->st));
-    if (nchunks) CK(cudaMemcpyAsync(d_chunk_stream, chunk_stream.data(), (size_t)nchunks * sizeof(int), cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(d_intra, intra.data(), (size_t)n, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st));   // reused as the decoder's error flag
-
-    // ---- D1/D2: tokenize (speculative walk + chain); symbol totals come back to size the symbol array ----
-    CK(launch_eg_tokenize_spec(d_in, d_streams, (int)streams.size(), d_chunk_stream, nchunks, d_exit, d_nsym, d_neob, d_entry, d_symbase,
-                               d_eobbase, c->d_overflow, c->st));
-    c->launches += 2;
-    int err = 0;
-    CK(cudaMemcpyAsync(streams.data(), d_streams, streams.size() * sizeof(EgStream), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(&err, c->d_overflow, sizeof err, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    if (err) return fail(c, BVC_ERR_INVALID, "malformed exp-Golomb stream (not enough bits / code too long)");
-    long long total_syms = 0;
-    std::vector<long long> sym0(n);
-    for (size_t si = 0; si < streams.size(); si++) {
-        streams[si].sym0 = total_syms;
-        total_syms += streams[si].nsym;
-        if (streams[si].kind == 1) {
-            sym0[streams[si].frame] = streams[si].sym0;
-            if (streams[si].neob != g.nblk && !pred_only)
-                return fail(c, BVC_ERR_INVALID, "coefficient stream does not hold one EOB-terminated run per block");
-        }
-    }
-    if ((rc = dbuf(c, c->dec_syms, (size_t)total_syms + 8, &d_syms))) return rc;
-    CK(cudaMemcpyAsync(d_streams, streams.data(), streams.size() * sizeof(EgStream), cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(d_sym0, sym0.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, c->st));
-    // ---- D3/D4: symbols, block starts, motion vectors / modes / row QPs of every frame ----
-    CK(launch_eg_tokenize_emit(d_in, d_streams, d_chunk_stream, nchunks, d_entry, d_symbase, d_eobbase, d_syms, d_blk_start, g.nblk, c->st));
-    CK(launch_pred_decode(d_streams, d_syms, d_intra, n, d_mv, d_modes, d_qp, g.bw, g.bh, c->p.qp, c->p.nref_frames > 1, c->d_overflow, c->st));
-    c->launches += 2;
-
     // ---- GOP lanes: a GOP starts at every I frame (the window is cleared, decoder.py:55-58) ----
+    std::vector<uint8_t> intra(n);
+    for (int f = 0; f < n; f++) intra[f] = (uint8_t)recs[f].intra;
     struct Gop { int first, count, virt0; };
     std::vector<Gop> gops;
     for (int f = 0; f < n; f++) {
@@ -1119,7 +1048,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     if (nin > c->p.nref_frames) return fail(c, BVC_ERR_INVALID, "more initial references than nref_frames");
     const int G = c->max_lanes;
     std::vector<FrameLane> frl;
-    struct DStep { size_t off_i, n_i, off_p, n_p; std::vector<int> frames, outplanes; };
+    struct DStep { size_t off_i, n_i, off_p, n_p; std::vector<int> frames, outplanes; long long chunk_begin, nchunks, bits; size_t list_off; };
     std::vector<DStep> steps;
     for (size_t g0 = 0; g0 < gops.size(); g0 += G) {
         const size_t g1 = std::min(gops.size(), g0 + G);
@@ -1151,8 +1080,84 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
             steps.push_back(std::move(st));
         }
     }
-    if ((rc = dbuf(c, c->dec_lanes, frl.size(), &d_lanes))) return rc;
-    CK(cudaMemcpyAsync(d_lanes, frl.data(), frl.size() * sizeof(FrameLane), cudaMemcpyHostToDevice, c->st));
+
+    // ---- streams and chunk map.  Stream 2f + k = frame f's prediction data (k = 0) / coefficients (k = 1); the chunk tables
+    // are laid out step by step, so the streams a decode step needs are one contiguous chunk range and can be tokenized
+    // on their own, ahead of the step (the tokenizer runs on its own stream, a few steps in front of the rebuild kernels).
+    const int CB = eg_chunk_bits();
+    std::vector<EgStream> streams(2 * (size_t)n);
+    std::vector<int> step_frames, step_streams;   // concatenated per-step lists (frames; stream ids)
+    long long nchunks = 0, slab_syms = 0;
+    for (auto& st : steps) {
+        st.chunk_begin = nchunks; st.bits = 0; st.list_off = step_frames.size();
+        for (int f : st.frames) {
+            step_frames.push_back(f);
+            for (int k = 0; k < 2; k++) {
+                EgStream& s = streams[2 * (size_t)f + k];
+                s.byte0 = (long long)(k ? recs[f].coef_off : recs[f].pred_off);
+                s.nbits = 8LL * (long long)(k ? recs[f].coef_len : recs[f].pred_len);
+                s.chunk0 = nchunks;
+                s.sym0 = 0; s.nsym = 0; s.neob = 0; s.frame = f; s.kind = k;
+                nchunks += (s.nbits + CB - 1) / CB;
+                st.bits += s.nbits;
+                step_streams.push_back(2 * f + k);
+            }
+        }
+        st.nchunks = nchunks - st.chunk_begin;
+        slab_syms = std::max(slab_syms, st.bits);   // a symbol is at least one bit
+    }
+    // symbols live in a ring of per-step slabs: a step's symbols are only read by that step's kernels
+    constexpr int SLABS = 4;
+    slab_syms = (slab_syms + 15) & ~15LL;
+    uint8_t *d_in, *d_exit, *d_neob, *d_entry, *d_intra, *d_frame_ok;
+    uint16_t* d_nsym;
+    EgStream* d_streams;
+    int *d_chunk_stream, *d_symbase, *d_eobbase, *d_blk_start, *d_progress, *d_step_frames, *d_step_streams;
+    int4* d_mv;
+    int32_t *d_modes, *d_qp;
+    long long* d_sym0;
+    int16_t *d_syms, *d_levels = nullptr;
+    FrameLane* d_lanes;
+    if ((rc = dbuf(c, c->dec_in, len, &d_in)) || (rc = dbuf(c, c->dec_streams, streams.size(), &d_streams)) ||
+        (rc = dbuf(c, c->dec_chunk_stream, (size_t)nchunks, &d_chunk_stream)) || (rc = dbuf(c, c->dec_exit, (size_t)nchunks * 32, &d_exit)) ||
+        (rc = dbuf(c, c->dec_nsym, (size_t)nchunks * 32, &d_nsym)) || (rc = dbuf(c, c->dec_neob, (size_t)nchunks * 32, &d_neob)) ||
+        (rc = dbuf(c, c->dec_entry, (size_t)nchunks, &d_entry)) || (rc = dbuf(c, c->dec_symbase, (size_t)nchunks, &d_symbase)) ||
+        (rc = dbuf(c, c->dec_eobbase, (size_t)nchunks, &d_eobbase)) || (rc = dbuf(c, c->dec_intra, (size_t)n, &d_intra)) ||
+        (rc = dbuf(c, c->dec_mv, (size_t)n * nb, &d_mv)) || (rc = dbuf(c, c->dec_modes, (size_t)n * nb, &d_modes)) ||
+        (rc = dbuf(c, c->dec_qp, (size_t)n * g.bh, &d_qp)) || (rc = dbuf(c, c->dec_blk_start, (size_t)n * (nb + 1), &d_blk_start)) ||
+        (rc = dbuf(c, c->dec_sym0, (size_t)n, &d_sym0)) || (rc = dbuf(c, c->dec_progress, (size_t)c->max_lanes * g.bh, &d_progress)) ||
+        (rc = dbuf(c, c->dec_frame_ok, (size_t)n, &d_frame_ok)) || (rc = dbuf(c, c->dec_step_frames, step_frames.size(), &d_step_frames)) ||
+        (rc = dbuf(c, c->dec_step_streams, step_streams.size(), &d_step_streams)) ||
+        (rc = dbuf(c, c->dec_syms, (size_t)slab_syms * SLABS + 8, &d_syms)) || (rc = dbuf(c, c->dec_lanes, frl.size(), &d_lanes)))
+        return rc;
+    if (levels_out && (rc = dbuf(c, c->dec_levels, (size_t)n * g.W * g.H, &d_levels))) return rc;
+    // the small tables go through one pinned staging block (truly asynchronous copies), in front of the container itself
+    {
+        const size_t b_streams = streams.size() * sizeof(EgStream), b_intra = ((size_t)n + 15) & ~(size_t)15,
+                     b_sf = step_frames.size() * sizeof(int), b_ss = step_streams.size() * sizeof(int), b_frl = frl.size() * sizeof(FrameLane);
+        if ((rc = ensure_pinned(c, &c->h_desc, &c->h_desc_cap, b_streams + b_intra + b_sf + b_ss + b_frl + 64)) != BVC_OK) return rc;
+        uint8_t* h = static_cast<uint8_t*>(c->h_desc);
+        memcpy(h, streams.data(), b_streams);
+        CK(cudaMemcpyAsync(d_streams, h, b_streams, cudaMemcpyHostToDevice, c->st));
+        h += b_streams;
+        memcpy(h, intra.data(), (size_t)n);
+        CK(cudaMemcpyAsync(d_intra, h, (size_t)n, cudaMemcpyHostToDevice, c->st));
+        h += b_intra;
+        memcpy(h, step_frames.data(), b_sf);
+        CK(cudaMemcpyAsync(d_step_frames, h, b_sf, cudaMemcpyHostToDevice, c->st));
+        h += b_sf;
+        memcpy(h, step_streams.data(), b_ss);
+        CK(cudaMemcpyAsync(d_step_streams, h, b_ss, cudaMemcpyHostToDevice, c->st));
+        h += b_ss;
+        memcpy(h, frl.data(), b_frl);
+        CK(cudaMemcpyAsync(d_lanes, h, b_frl, cudaMemcpyHostToDevice, c->st));
+    }
+    CK(launch_eg_chunk_map(d_streams, (int)streams.size(), d_chunk_stream, c->st));
+    CK(cudaMemsetAsync(d_frame_ok, 0, (size_t)n, c->st));
+    CK(cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->st));   // reused as the decoder's error flag
+    CK(cudaMemsetAsync(d_in + len, 0, 256, c->st));
+    CK(cudaMemcpyAsync(d_in, data, len, cudaMemcpyHostToDevice, c->st));
+    c->launches += 1;
     if (c->p.frac_me) {
         if ((rc = ensure_lane_desc(c, frl.size() + (size_t)nin)) != BVC_OK) return rc;
         for (auto& st : steps)
@@ -1172,52 +1177,121 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
             if ((rc = enqueue_halfpel(c, frl.size(), nin)) != BVC_OK) return rc;
         }
     }
+    EventBag bag;
+    cudaEvent_t ev_up;
+    CK(bag.make(&ev_up, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev_up, c->st));
+    // ---- D1-D4 per step on the tokenizer stream: speculative walk, chain, symbol offsets (on the device: no host round
+    // trip), symbols + block starts, prediction data ----
+    cudaStream_t st_tok = c->st_grp[0];
+    CK(cudaStreamWaitEvent(st_tok, ev_up, 0));
+    std::vector<cudaEvent_t> ev_tok(steps.size(), nullptr), ev_dec(steps.size(), nullptr);
+    // The speculative walk and the chain pass of a stream do not touch the symbol ring, and the chain is one serial walk
+    // per stream (0.1-0.3 ms whatever the number of streams), so they run for batches of steps -- 1, 2, 4, 8, ... steps: the
+    // first step's streams are ready after one short batch, the later batches stay far ahead of the rebuild kernels.
+    size_t chained = 0;   // steps [0, chained) have had their chain pass enqueued
+    auto enqueue_tokenize = [&](size_t si) -> int {
+        if (si >= steps.size()) return BVC_OK;
+        if (si >= chained) {
+            const size_t s0 = chained, s1 = std::min(steps.size(), s0 + std::max<size_t>(1, s0));   // batch sizes 1, 1, 2, 4, 8, ...
+            long long nch = 0;
+            size_t nfr = 0;
+            for (size_t k = s0; k < s1; k++) { nch += steps[k].nchunks; nfr += steps[k].frames.size(); }
+            CK(launch_eg_tokenize_spec(d_in, d_streams, d_step_streams + 2 * steps[s0].list_off, (int)(2 * nfr), d_chunk_stream, steps[s0].chunk_begin,
+                                       nch, d_exit, d_nsym, d_neob, d_entry, d_symbase, d_eobbase, c->d_overflow, st_tok));
+            c->launches += 2;
+            chained = s1;
+        }
+        const DStep& st = steps[si];
+        const int nf = (int)st.frames.size();
+        if (si >= (size_t)SLABS && ev_dec[si - SLABS]) CK(cudaStreamWaitEvent(st_tok, ev_dec[si - SLABS], 0));   // the slab's previous tenant has been rebuilt
+        CK(launch_eg_offsets(d_streams, d_step_streams + 2 * st.list_off, 2 * nf, (long long)(si % SLABS) * slab_syms, d_sym0, d_frame_ok, g.nblk,
+                             pred_only ? 1 : 0, c->d_overflow, st_tok));
+        CK(launch_eg_tokenize_emit(d_in, d_streams, d_chunk_stream, st.chunk_begin, st.nchunks, d_entry, d_symbase, d_eobbase, d_syms, d_blk_start,
+                                   g.nblk, st_tok));
+        CK(launch_pred_decode(d_streams, d_syms, d_intra, d_step_frames + st.list_off, nf, d_mv, d_modes, d_qp, g.bw, g.bh, c->p.qp,
+                              c->p.nref_frames > 1, c->d_overflow, st_tok));
+        c->launches += 3;
+        CK(bag.make(&ev_tok[si], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_tok[si], st_tok));
+        return BVC_OK;
+    };
+    for (size_t si = 0; si < (size_t)SLABS - 1; si++)
+        if ((rc = enqueue_tokenize(si)) != BVC_OK) return rc;
+    int err = 0;
     // ---- D5/D6 step by step ----
     DecArgs a{};
     a.ref_base = c->ref_pool; a.ref_plane_bytes = g.plane_bytes; a.ref_pitch = g.pitch;
     a.mv_all = d_mv; a.modes_all = d_modes; a.qp_all = d_qp; a.syms = d_syms; a.coef_sym0 = d_sym0; a.blk_start = d_blk_start;
     a.levels_out = d_levels; a.progress = d_progress; a.ticket = c->d_ticket; a.err_flag = c->d_overflow;
     a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
-    if (pred_only) steps.clear();
+    a.frame_ok = d_frame_ok; a.top_mail = c->d_top_mail;
     // Decoded planes go back on their own stream so that the download of step s overlaps the kernels of step s+1 (the
     // 1.25 GB of planes of the headline clip are the decoder's bound).  A plane of the reconstruction ring is rewritten
     // `slots` frames later: the kernels that rewrite it wait for its pending download.
-    EventBag bag;
-    std::vector<cudaEvent_t> ev_done(frames_out ? steps.size() : 0), ev_copied(frames_out ? steps.size() : 0);
+    // The rebuild kernels run on a high-priority stream: the tokenizer's batches (low priority, many CTAs) would otherwise
+    // hold the GPU while a step waits -- the block scheduler does not place a second kernel beside one that still has CTAs
+    // to dispatch, but it does hand freed slots to the higher priority first.
+    cudaStream_t sd = c->st_post[0];
+    CK(cudaStreamWaitEvent(sd, ev_up, 0));
+    std::vector<cudaEvent_t> ev_copied(frames_out ? steps.size() : 0);
     std::vector<int> pending_copy(c->ref_planes, -1);   // plane -> step whose download still reads it
     for (size_t si = 0; si < steps.size(); si++) {
         auto& st = steps[si];
+        if ((rc = enqueue_tokenize(si + SLABS - 1)) != BVC_OK) return rc;   // the tokenizer stays SLABS - 1 steps ahead
+        if (pred_only) continue;                                            // prediction data only: nothing to rebuild
+        CK(cudaStreamWaitEvent(sd, ev_tok[si], 0));
         if (frames_out) {
             int wait_for = -1;
             for (int pl : st.outplanes) wait_for = std::max(wait_for, pending_copy[pl]);
-            if (wait_for >= 0) CK(cudaStreamWaitEvent(c->st, ev_copied[wait_for], 0));
+            if (wait_for >= 0) CK(cudaStreamWaitEvent(sd, ev_copied[wait_for], 0));
         }
         if (st.n_i) {
-            CK(cudaMemsetAsync(d_progress, 0, st.n_i * g.bh * sizeof(int), c->st));
+            c->epoch = (c->epoch % 0xFFFFFEu) + 1;   // one mailbox epoch per I step
+            a.epoch = c->epoch;
             a.lanes = d_lanes + st.off_i;
-            CK(launch_dec_iframe(a, (int)st.n_i, c->st));
+            CK(launch_dec_iframe(a, (int)st.n_i, sd));
             c->launches += 1;
         }
         if (st.n_p) {
             a.lanes = d_lanes + st.off_p;
-            CK(launch_dec_pframe(a, (int)st.n_p, c->st));
+            CK(launch_dec_pframe(a, (int)st.n_p, sd));
             c->launches += 1;
         }
-        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p))) != BVC_OK) return rc;
+        if ((rc = enqueue_halfpel(c, st.off_i, (int)(st.n_i + st.n_p), sd)) != BVC_OK) return rc;
+        CK(bag.make(&ev_dec[si], cudaEventDisableTiming));
+        CK(cudaEventRecord(ev_dec[si], sd));
         if (frames_out) {
-            CK(bag.make(&ev_done[si], cudaEventDisableTiming));
             CK(bag.make(&ev_copied[si], cudaEventDisableTiming));
-            CK(cudaEventRecord(ev_done[si], c->st));
-            CK(cudaStreamWaitEvent(c->st_d2h, ev_done[si], 0));
-            for (size_t l = 0; l < st.frames.size(); l++) {
-                if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * g.W * g.H, plane_ptr(c, st.outplanes[l]), c->st_d2h)) != BVC_OK)
-                    return rc;
-                pending_copy[st.outplanes[l]] = (int)si;
+            CK(cudaStreamWaitEvent(c->st_d2h, ev_dec[si], 0));
+            // the planes of a step are equally spaced on both sides when the step's frames are (frame k of consecutive
+            // GOPs, lanes side by side in the reconstruction ring): one strided copy, "row" = one plane
+            const size_t nfr = st.frames.size(), fbytes = (size_t)g.W * g.H;
+            bool strided = g.pitch == g.W && nfr > 2;
+            long long hstride = 0, dstride = 0;
+            if (strided) {
+                hstride = (long long)st.frames[1] - st.frames[0];
+                dstride = (long long)st.outplanes[1] - st.outplanes[0];
+                for (size_t l = 2; l < nfr && strided; l++)
+                    strided = (long long)st.frames[l] - st.frames[l - 1] == hstride && (long long)st.outplanes[l] - st.outplanes[l - 1] == dstride;
+                strided = strided && hstride > 0 && dstride > 0 && (unsigned long long)hstride * fbytes <= 0x7fffffffull &&
+                          (unsigned long long)dstride * g.plane_bytes <= 0x7fffffffull;
             }
+            if (strided) {
+                CK(cudaMemcpy2DAsync(frames_out + (size_t)st.frames[0] * fbytes, (size_t)hstride * fbytes, plane_ptr(c, st.outplanes[0]),
+                                     (size_t)dstride * g.plane_bytes, fbytes, nfr, cudaMemcpyDeviceToHost, c->st_d2h));
+            } else {
+                for (size_t l = 0; l < nfr; l++)
+                    if ((rc = download_plane(c, frames_out + (size_t)st.frames[l] * fbytes, plane_ptr(c, st.outplanes[l]), c->st_d2h)) != BVC_OK)
+                        return rc;
+            }
+            for (size_t l = 0; l < nfr; l++) pending_copy[st.outplanes[l]] = (int)si;
             CK(cudaEventRecord(ev_copied[si], c->st_d2h));
         }
     }
-    if (frames_out && !steps.empty()) CK(cudaStreamWaitEvent(c->st, ev_copied[steps.size() - 1], 0));
+    if (!pred_only && !steps.empty()) CK(cudaStreamWaitEvent(c->st, ev_dec[steps.size() - 1], 0));
+    if (frames_out && !steps.empty() && !pred_only) CK(cudaStreamWaitEvent(c->st, ev_copied[steps.size() - 1], 0));
+    if (!steps.empty()) CK(cudaStreamWaitEvent(c->st, ev_tok[steps.size() - 1], 0));
     CK(cudaMemcpyAsync(&err, c->d_overflow, sizeof err, cudaMemcpyDeviceToHost, c->st));
     if (levels_out) CK(cudaMemcpyAsync(levels_out, d_levels, (size_t)n * g.W * g.H * sizeof(int16_t), cudaMemcpyDeviceToHost, c->st));
     std::vector<int4> hmv;
@@ -1229,7 +1303,8 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     }
     if (qp_out) CK(cudaMemcpyAsync(qp_out, d_qp, (size_t)n * g.bh * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    if (err) return fail(c, BVC_ERR_INVALID, "malformed stream (missing prediction symbols, bad intra mode or motion vector out of range)");
+    if (err) return fail(c, BVC_ERR_INVALID, "malformed stream (exp-Golomb code cut short or too long, a coefficient stream without one EOB-terminated run "
+                               "per block, missing prediction symbols, bad intra mode or motion vector out of range)");
     if (pred_out)
         for (int f = 0; f < n; f++)
             for (size_t b = 0; b < nb; b++) {

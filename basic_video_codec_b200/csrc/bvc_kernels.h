@@ -204,6 +204,9 @@ struct DecArgs {
     const long long* coef_sym0;    // [nframes] first symbol of the frame's coefficient stream
     const int* blk_start;          // [nframes][nblk+1] first symbol of every block, relative to coef_sym0
     int16_t* levels_out;           // [nframes][H][W] or null
+    const uint8_t* frame_ok;       // [nframes] 0 = the frame's coefficient stream is malformed: leave the frame alone
+    uint32_t* top_mail;            // I frames: [lanes][bh][bw][bs] bottom rows handed down, pixel | epoch << 8 (see tq_iframe_kernel)
+    uint32_t epoch;
     int* progress;                 // I frames: [lanes][bh] wavefront counters (zeroed)
     int* ticket;                   // I frames: start-order ticket counter (see TqArgs::ticket)
     int* err_flag;
@@ -211,14 +214,19 @@ struct DecArgs {
     int frac;
 };
 int eg_chunk_bits();
-cudaError_t launch_eg_tokenize_spec(const uint8_t* data, const EgStream* streams, int nstreams, const int* chunk_stream,
-                                    long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab, uint8_t* entry_tab,
-                                    int* symbase, int* eobbase, int* err_flag, cudaStream_t st);
-cudaError_t launch_eg_tokenize_emit(const uint8_t* data, const EgStream* streams, const int* chunk_stream, long long nchunks,
-                                    const uint8_t* entry_tab, const int* symbase, const int* eobbase, int16_t* syms, int* blk_start,
-                                    int nblk, cudaStream_t st);
-cudaError_t launch_pred_decode(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags, int nframes, int4* mv_all,
-                               int32_t* modes_all, int32_t* qp_all, int bw, int bh, int base_qp, int with_ref, int* err_flag,
+// Tokenizing runs step by step (the streams of the frames one decode step needs): chunks [chunk_begin, chunk_begin + nchunks)
+// of the chunk tables, streams stream_list[0 .. nstreams)
+cudaError_t launch_eg_tokenize_spec(const uint8_t* data, EgStream* streams, const int* stream_list, int nstreams, const int* chunk_stream,
+                                    long long chunk_begin, long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab,
+                                    uint8_t* entry_tab, int* symbase, int* eobbase, int* err_flag, cudaStream_t st);
+cudaError_t launch_eg_chunk_map(const EgStream* streams, int nstreams, int* chunk_stream, cudaStream_t st);
+cudaError_t launch_eg_offsets(EgStream* streams, const int* stream_list, int nstreams, long long slab_base, long long* coef_sym0,
+                              uint8_t* frame_ok, int nblk, int pred_only, int* err_flag, cudaStream_t st);
+cudaError_t launch_eg_tokenize_emit(const uint8_t* data, const EgStream* streams, const int* chunk_stream, long long chunk_begin,
+                                    long long nchunks, const uint8_t* entry_tab, const int* symbase, const int* eobbase, int16_t* syms,
+                                    int* blk_start, int nblk, cudaStream_t st);
+cudaError_t launch_pred_decode(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags, const int* frame_list, int nframes,
+                               int4* mv_all, int32_t* modes_all, int32_t* qp_all, int bw, int bh, int base_qp, int with_ref, int* err_flag,
                                cudaStream_t st);
 cudaError_t launch_dec_pframe(const DecArgs& a, int lanes, cudaStream_t st);
 cudaError_t launch_dec_iframe(const DecArgs& a, int lanes, cudaStream_t st);

@@ -62,13 +62,14 @@ __device__ __forceinline__ int eg_step(const uint32_t* sm, int p, long long rem,
 // what a walk does at a position does not depend on where it came from.  So every position is decoded once -- 16 per
 // lane -- into a table (length, EOB flag, or how the walk ends there), and the 32 walks just follow the table.
 __global__ void __launch_bounds__(128) eg_spec_kernel(const uint8_t* data, const EgStream* streams, const int* chunk_stream,
-                                                      long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab) {
+                                                      long long chunk_begin, long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab,
+                                                      uint8_t* neob_tab) {
     __shared__ uint32_t sm[4][EG_STAGE_WORDS + 1];
     // per position: bits 0-4 code length (1..31, always odd); bit 5 EOB marker; 0x40 = end of stream, 0x80 = malformed
     __shared__ uint8_t tab[4][EG_CHUNK_BITS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gc = (long long)blockIdx.x * 4 + warp;
-    if (gc >= nchunks) return;
+    const long long gc = chunk_begin + (long long)blockIdx.x * 4 + warp;   // chunks [chunk_begin, chunk_begin + nchunks): one step's streams
+    if (gc >= chunk_begin + nchunks) return;
     const EgStream st = streams[chunk_stream[gc]];
     const long long bit0 = (gc - st.chunk0) * EG_CHUNK_BITS;
     if (lane < EG_STAGE_WORDS) sm[warp][lane] = stage_word(data, st.byte0 + (bit0 >> 3), lane);
@@ -96,14 +97,22 @@ __global__ void __launch_bounds__(128) eg_spec_kernel(const uint8_t* data, const
     neob_tab[gc * 32 + lane] = (uint8_t)neob;
 }
 
+// chunk -> stream map, built on the device from the streams' chunk ranges (1.2 M entries for the headline clip: as a host
+// array it cost a fill and a 5 MB pageable upload in front of everything else).  One CTA per stream.
+__global__ void __launch_bounds__(256) eg_chunk_map_kernel(const EgStream* streams, int* chunk_stream) {
+    const EgStream st = streams[blockIdx.x];
+    const long long nch = (st.nbits + EG_CHUNK_BITS - 1) / EG_CHUNK_BITS;
+    for (long long c = threadIdx.x; c < nch; c += blockDim.x) chunk_stream[st.chunk0 + c] = (int)blockIdx.x;
+}
+
 constexpr int CHAIN_TILE = 128;
-__global__ void __launch_bounds__(128) eg_chain_kernel(EgStream* streams, const uint8_t* exit_tab, const uint16_t* nsym_tab,
-                                                       const uint8_t* neob_tab, uint8_t* entry_tab, int* symbase, int* eobbase,
-                                                       int* err_flag) {
+__global__ void __launch_bounds__(128) eg_chain_kernel(EgStream* streams, const int* stream_list, const uint8_t* exit_tab,
+                                                       const uint16_t* nsym_tab, const uint8_t* neob_tab, uint8_t* entry_tab, int* symbase,
+                                                       int* eobbase, int* err_flag) {
     __shared__ uint32_t s_exit[CHAIN_TILE * 8];
     __shared__ uint32_t s_nsym[CHAIN_TILE * 16];
     __shared__ uint32_t s_neob[CHAIN_TILE * 8];
-    EgStream& st = streams[blockIdx.x];
+    EgStream& st = streams[stream_list[blockIdx.x]];
     const long long nch = (st.nbits + EG_CHUNK_BITS - 1) / EG_CHUNK_BITS;
     int e = 0, S = 0, E = 0;
     bool bad = false;
@@ -141,12 +150,33 @@ __global__ void __launch_bounds__(128) eg_chain_kernel(EgStream* streams, const 
     }
 }
 
+// Where the symbols of one step's streams go: consecutive runs in the step's slab of the symbol ring, in list order.  The
+// counts come from the chain pass, so the host never has to see them (no round trip between tokenizing and decoding).  A
+// coefficient stream must hold exactly one EOB-terminated run per block (the reference's decoder would run out of symbols);
+// frames that do not are marked so that the rebuild kernels leave them alone.
+__global__ void eg_offsets_kernel(EgStream* streams, const int* stream_list, int n, long long slab_base, long long* coef_sym0,
+                                  uint8_t* frame_ok, int nblk, int pred_only, int* err_flag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long off = slab_base;
+    for (int i = 0; i < n; i++) {
+        EgStream& s = streams[stream_list[i]];
+        s.sym0 = off;
+        off += s.nsym;
+        if (s.kind == 1) {
+            coef_sym0[s.frame] = s.sym0;
+            const bool ok = s.neob == nblk;
+            frame_ok[s.frame] = ok ? 1 : 0;
+            if (!ok && !pred_only) atomicExch(err_flag, 1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) eg_emit_kernel(const uint8_t* data, const EgStream* streams, const int* chunk_stream,
-                                                      long long nchunks, const uint8_t* entry_tab, const int* symbase,
-                                                      const int* eobbase, int16_t* syms, int* blk_start, int nblk) {
+                                                      long long chunk_begin, long long nchunks, const uint8_t* entry_tab,
+                                                      const int* symbase, const int* eobbase, int16_t* syms, int* blk_start, int nblk) {
     __shared__ uint32_t sm[128 * EG_STAGE_WORDS];
-    const long long gc = (long long)blockIdx.x * 128 + threadIdx.x;
-    if (gc >= nchunks) return;
+    const long long gc = chunk_begin + (long long)blockIdx.x * 128 + threadIdx.x;
+    if (gc >= chunk_begin + nchunks) return;
     const EgStream st = streams[chunk_stream[gc]];
     const long long bit0 = (gc - st.chunk0) * EG_CHUNK_BITS;
     uint32_t* my = sm + threadIdx.x * EG_STAGE_WORDS;
@@ -172,10 +202,10 @@ __global__ void __launch_bounds__(128) eg_emit_kernel(const uint8_t* data, const
 // ---------------------------------------------------------------------------------------------
 // D4: prediction data of one frame.  Symbol layout per block row: EG(qp - base), then per block spb symbols.
 __global__ void __launch_bounds__(256) pred_decode_kernel(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags,
-                                                          int4* mv_all, int32_t* modes_all, int32_t* qp_all, int bw, int bh,
-                                                          int base_qp, int with_ref, int* err_flag) {
+                                                          const int* frame_list, int4* mv_all, int32_t* modes_all, int32_t* qp_all,
+                                                          int bw, int bh, int base_qp, int with_ref, int* err_flag) {
     __shared__ int wsum[3][9];
-    const int f = blockIdx.x, tid = threadIdx.x, nblk = bw * bh;
+    const int f = frame_list[blockIdx.x], tid = threadIdx.x, nblk = bw * bh;
     const EgStream st = streams[2 * f];             // stream 2f = prediction data, 2f+1 = coefficients
     const int16_t* s = syms + st.sym0;
     const bool intra = intra_flags[f] != 0;
@@ -260,7 +290,8 @@ __device__ __forceinline__ void rle_to_tile(const DecArgs& a, int f, int b, cons
 // second half of tq_warp (the encoder's reconstruction), so decode(encode(x)) == the encoder's reconstruction bit for bit.
 template <int BS>
 __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lane, bool valid, int qp, uint8_t* recon, int rec_pitch,
-                                                        int16_t* levels, int lev_pitch, uint8_t* last_col = nullptr) {
+                                                        int16_t* levels, int lev_pitch, uint8_t* last_col = nullptr,
+                                                        uint32_t* mail_row = nullptr, uint32_t mail_tag = 0) {
     const int q = lane / BS, x = lane % BS, u = x;
     double a[BS], r[BS];
     const bool su = (u == 0) || (2 * u == BS);
@@ -301,6 +332,18 @@ __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lan
         }
         store_row_words<BS>(recon + (size_t)y * rec_pitch, ow);
         if (last_col) last_col[q * BS + y] = (uint8_t)(ow[BS / 4 - 1] >> 24);   // right column for the next block of the row
+        // bottom row for the block below: every pixel as a tagged word the consumer polls (see tq_iframe_kernel)
+        if (mail_row && y == BS - 1) {
+#pragma unroll
+            for (int i = 0; i < BS; i += 4) {
+                uint4 v;
+                v.x = ((ow[i >> 2]) & 255u) | mail_tag;
+                v.y = ((ow[i >> 2] >> 8) & 255u) | mail_tag;
+                v.z = ((ow[i >> 2] >> 16) & 255u) | mail_tag;
+                v.w = (ow[i >> 2] >> 24) | mail_tag;
+                __stcg(reinterpret_cast<uint4*>(mail_row + i), v);
+            }
+        }
     }
     __syncwarp();
 }
@@ -332,6 +375,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4) dec_pframe_kernel(DecArgs a
     WarpTile<BS>& t = sm.w[warp];
     const FrameLane& L = a.lanes[blockIdx.y];
     const int f = L.slot;
+    if (!a.frame_ok[f]) return;   // malformed coefficient stream (the call fails): its block table cannot be trusted
     const int q = lane / BS, x = lane % BS;
     const int b = (blockIdx.x * DEC_WARPS + warp) * NBW + q;
     const bool valid = b < a.nblk;
@@ -367,8 +411,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4) dec_pframe_kernel(DecArgs a
     dequant_idct_recon_warp<BS>(t, lane, valid, qp, recon, a.ref_pitch, lev, a.W);
 }
 
-// D6: I frames.  Same wavefront as tq_iframe_kernel (one warp per block row of NBW different frames, rows chained
-// through progress counters), with the mode read from the stream instead of decided.
+// D6: I frames.  Same wavefront as tq_iframe_kernel (one warp per block row of NBW different frames; a block's bottom row
+// is handed to the row below through epoch-tagged mailbox words, the right column through shared memory), with the mode
+// read from the stream instead of decided.
 template <int BS>
 __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
     constexpr int NBW = 32 / BS;
@@ -387,33 +432,32 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
     const int by = tk / ngrp, grp = tk % ngrp;
     const int q = lane / BS, x = lane % BS;
     const int fl_raw = grp * NBW + q;
-    const bool valid = fl_raw < lanes;
-    const int fl = valid ? fl_raw : lanes - 1;
+    const bool in_range = fl_raw < lanes;
+    const int fl = in_range ? fl_raw : lanes - 1;
     const FrameLane& L = a.lanes[fl];
     const int f = L.slot;
+    const bool valid = in_range && a.frame_ok[f];   // a malformed frame (the call fails) is left alone, all its rows alike
     const int oy = by * BS;
     WarpTile<BS>& t = sm.t;
     uint8_t* recon_plane = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes;
     const int qp = a.qp_all[(size_t)f * a.bh + by];
-    volatile int* prog_up = (by > 0) ? a.progress + (size_t)fl * a.bh + (by - 1) : nullptr;
-    int* prog_me = a.progress + (size_t)fl * a.bh + by;
-    int seen = 0;   // progress of the row above as last read: re-read only when it does not cover the block (see tq_iframe_kernel)
+    const volatile uint32_t* mail_up = a.top_mail + (((size_t)fl * a.bh + by) * a.bw) * BS + x;
+    uint32_t* mail_dn = (by + 1 < a.bh && valid) ? a.top_mail + (((size_t)fl * a.bh + by + 1) * a.bw) * BS : nullptr;
+    const uint32_t tag = a.epoch << 8;
     for (int bx = 0; bx < a.bw; bx++) {
         const int ox = bx * BS, b = by * a.bw + bx;
         zero_lev<BS>(t, lane);
         __syncwarp();
         if (valid && x == 0) rle_to_tile<BS>(a, f, b, sm.zz, &t.lev[q][0][0]);
         const int mode = a.modes_all[(size_t)f * a.nblk + b];
-        bool polled = false;
-        if (by > 0 && valid && x == 0 && seen < bx + 1) {
-            polled = true;
-            while ((seen = *prog_up) < bx + 1) {}   // pure spin: __nanosleep(20) sleeps for about a microsecond, a fifth of a block
-        }
-        if (__any_sync(0xffffffffu, polled)) __threadfence();
-        __syncwarp();
         // find_intra_predict_block IFrame.py:175-213: mode 0 -> pred[r][c] = recon[oy+c][ox-1] (the right column this warp's
-        // previous block left in shared memory); mode 1 -> recon[oy-1][ox+r] (from the plane, written by another SM)
-        const int tv = (oy > 0) ? (int)__ldcg(recon_plane + (size_t)(oy - 1) * a.ref_pitch + ox + x) : 128;
+        // previous block left in shared memory); mode 1 -> recon[oy-1][ox+r] (this lane's mailbox word, posted by the row above)
+        int tv = 128;
+        if (oy > 0 && valid) {
+            uint32_t v = mail_up[bx * BS];
+            while ((v & 0xffffff00u) != tag) v = mail_up[bx * BS];   // pure spin: __nanosleep(20) sleeps for about a microsecond
+            tv = (int)(v & 255u);
+        }
         if (ox == 0) sm.left[q][x] = 128;
         __syncwarp();
         uint32_t pw[BS / 4];
@@ -422,10 +466,8 @@ __global__ void __launch_bounds__(32) dec_iframe_kernel(DecArgs a, int lanes) {
         store_row_words<BS>(&t.pred[q][x][0], pw);
         __syncwarp();
         int16_t* lev = a.levels_out ? a.levels_out + ((size_t)f * a.H + oy) * a.W + ox : nullptr;
-        dequant_idct_recon_warp<BS>(t, lane, valid, qp, recon_plane + (size_t)oy * a.ref_pitch + ox, a.ref_pitch, lev, a.W, &sm.left[0][0]);
-        __threadfence();
-        __syncwarp();
-        if (valid && x == 0) atomicExch(prog_me, bx + 1);
+        dequant_idct_recon_warp<BS>(t, lane, valid, qp, recon_plane + (size_t)oy * a.ref_pitch + ox, a.ref_pitch, lev, a.W, &sm.left[0][0],
+                                    mail_dn ? mail_dn + bx * BS : nullptr, tag);
     }
 }
 
@@ -462,25 +504,34 @@ cudaError_t launch_dec_i(const DecArgs& a, int lanes, cudaStream_t st) {
 
 int eg_chunk_bits() { return EG_CHUNK_BITS; }
 
-cudaError_t launch_eg_tokenize_spec(const uint8_t* data, const EgStream* streams, int nstreams, const int* chunk_stream,
-                                    long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab, uint8_t* entry_tab,
-                                    int* symbase, int* eobbase, int* err_flag, cudaStream_t st) {
-    if (nchunks > 0) eg_spec_kernel<<<(unsigned)((nchunks + 3) / 4), 128, 0, st>>>(data, streams, chunk_stream, nchunks, exit_tab, nsym_tab, neob_tab);
+cudaError_t launch_eg_tokenize_spec(const uint8_t* data, EgStream* streams, const int* stream_list, int nstreams, const int* chunk_stream,
+                                    long long chunk_begin, long long nchunks, uint8_t* exit_tab, uint16_t* nsym_tab, uint8_t* neob_tab,
+                                    uint8_t* entry_tab, int* symbase, int* eobbase, int* err_flag, cudaStream_t st) {
+    if (nchunks > 0) eg_spec_kernel<<<(unsigned)((nchunks + 3) / 4), 128, 0, st>>>(data, streams, chunk_stream, chunk_begin, nchunks, exit_tab, nsym_tab, neob_tab);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    eg_chain_kernel<<<nstreams, 128, 0, st>>>(const_cast<EgStream*>(streams), exit_tab, nsym_tab, neob_tab, entry_tab, symbase, eobbase, err_flag);
+    if (nstreams > 0) eg_chain_kernel<<<nstreams, 128, 0, st>>>(streams, stream_list, exit_tab, nsym_tab, neob_tab, entry_tab, symbase, eobbase, err_flag);
     return cudaGetLastError();
 }
-cudaError_t launch_eg_tokenize_emit(const uint8_t* data, const EgStream* streams, const int* chunk_stream, long long nchunks,
-                                    const uint8_t* entry_tab, const int* symbase, const int* eobbase, int16_t* syms, int* blk_start,
-                                    int nblk, cudaStream_t st) {
-    if (nchunks > 0) eg_emit_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(data, streams, chunk_stream, nchunks, entry_tab, symbase, eobbase, syms, blk_start, nblk);
+cudaError_t launch_eg_chunk_map(const EgStream* streams, int nstreams, int* chunk_stream, cudaStream_t st) {
+    if (nstreams > 0) eg_chunk_map_kernel<<<nstreams, 256, 0, st>>>(streams, chunk_stream);
     return cudaGetLastError();
 }
-cudaError_t launch_pred_decode(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags, int nframes, int4* mv_all,
-                               int32_t* modes_all, int32_t* qp_all, int bw, int bh, int base_qp, int with_ref, int* err_flag,
+cudaError_t launch_eg_offsets(EgStream* streams, const int* stream_list, int nstreams, long long slab_base, long long* coef_sym0,
+                              uint8_t* frame_ok, int nblk, int pred_only, int* err_flag, cudaStream_t st) {
+    eg_offsets_kernel<<<1, 32, 0, st>>>(streams, stream_list, nstreams, slab_base, coef_sym0, frame_ok, nblk, pred_only, err_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_eg_tokenize_emit(const uint8_t* data, const EgStream* streams, const int* chunk_stream, long long chunk_begin,
+                                    long long nchunks, const uint8_t* entry_tab, const int* symbase, const int* eobbase, int16_t* syms,
+                                    int* blk_start, int nblk, cudaStream_t st) {
+    if (nchunks > 0) eg_emit_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, st>>>(data, streams, chunk_stream, chunk_begin, nchunks, entry_tab, symbase, eobbase, syms, blk_start, nblk);
+    return cudaGetLastError();
+}
+cudaError_t launch_pred_decode(const EgStream* streams, const int16_t* syms, const uint8_t* intra_flags, const int* frame_list, int nframes,
+                               int4* mv_all, int32_t* modes_all, int32_t* qp_all, int bw, int bh, int base_qp, int with_ref, int* err_flag,
                                cudaStream_t st) {
-    pred_decode_kernel<<<nframes, 256, 0, st>>>(streams, syms, intra_flags, mv_all, modes_all, qp_all, bw, bh, base_qp, with_ref, err_flag);
+    if (nframes > 0) pred_decode_kernel<<<nframes, 256, 0, st>>>(streams, syms, intra_flags, frame_list, mv_all, modes_all, qp_all, bw, bh, base_qp, with_ref, err_flag);
     return cudaGetLastError();
 }
 cudaError_t launch_dec_pframe(const DecArgs& a, int lanes, cudaStream_t st) {
