@@ -295,8 +295,24 @@ class Context:
         self._check_buffer(out, 6, "out")
         self._check_buffer(recon, frames.size, "recon")
         ln = C.c_size_t(0)
-        self._check(self._L.bvc_encode_clip(self._h, _p(frames), frames.shape[0], _p(out), out.size, C.byref(ln), _p(recon)))
+        self._check(self._repeat_if_enlarged(lambda: self._L.bvc_encode_clip(self._h, _p(frames), frames.shape[0], _p(out), out.size,
+                                                                             C.byref(ln), _p(recon))))
         return int(ln.value)
+
+    def _repeat_if_enlarged(self, call):
+        """Content that codes more bits than the library's staging buffers were sized for makes a clip call fail with
+        BVC_ERR_NOMEM after the library has enlarged the buffer in question ("repeat the call"): do that, a few times at most
+        (the two reservations can each be found too small once)."""
+        rc = call()
+        for _ in range(3):
+            if rc != BVC_ERR_NOMEM:
+                break
+            msg = self._L.bvc_last_error(self._h)
+            if b"staging" in msg:
+                rc = call()
+            else:
+                break
+        return rc
 
     # ---- decoder ---------------------------------------------------------------------------------
     def decode_clip(self, data, max_frames, details=False, out=None):
@@ -355,7 +371,7 @@ class Context:
             out = np.empty(nframes * self.W * self.H // 2 + (1 << 20), np.uint8)
         self._check_buffer(out, 6, "out")
         ln = C.c_size_t(0)
-        self._check(self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None))
+        self._check(self._repeat_if_enlarged(lambda: self._L.bvc_encode_clip_resident(self._h, int(nframes), _p(out), out.size, C.byref(ln), None)))
         return out, int(ln.value)
 
     def set_rate_control(self, rc_flag, frame_bit_budget=0.0, table=None):
@@ -381,7 +397,7 @@ class Context:
             frames = self._check_clip(frames)
             nframes = frames.shape[0]
         for _ in range(2):
-            rc = self._L.bvc_encode_clip_device(self._h, _p(frames), int(nframes), int(cap_hint), C.byref(ln))
+            rc = self._repeat_if_enlarged(lambda: self._L.bvc_encode_clip_device(self._h, _p(frames), int(nframes), int(cap_hint), C.byref(ln)))
             if rc == BVC_ERR_NOMEM and int(ln.value) > cap_hint:
                 cap_hint = int(ln.value)
                 continue

@@ -1418,8 +1418,8 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
     // the staging of a wave is cut into one region per container part (lane group, see below); no region needs to hold
     // more than the caller's buffer does
     const int NG = std::max(1, std::min(c->ngroups, G));
-    const size_t frag_total = std::min(frag_worst, std::max(c->frag_min, wave_frames * ((size_t)g.W * g.H / 8) + ((size_t)1 << 20)));
-    const size_t region = std::min((out_cap + 255) & ~(size_t)255, (frag_total / NG + 256) & ~(size_t)255);
+    const size_t frag_total = std::min(frag_worst, std::max(c->frag_min, wave_frames * ((size_t)g.W * g.H / 8)));
+    const size_t region = std::min((out_cap + 255) & ~(size_t)255, (frag_total / NG + ((size_t)1 << 20) + 256) & ~(size_t)255);
     if ((rc = ensure_fragments(c, region * NG, nwaves > 1 ? 2 : 1)) != BVC_OK) return rc;
     if (keep_on_device && (rc = ensure_container(c, out_cap)) != BVC_OK) return rc;
     const int per = (G + NG - 1) / NG;

@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=20, help="GOPs encoded in lock-step per GPU")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-decode", action="store_true")
+    ap.add_argument("--skip-4k", action="store_true", help="N = 8: leave out the BASELINE configs[4] block")
     ap.add_argument("--skip-full", action="store_true", help="reference arm: leave out the full-config step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -454,6 +455,18 @@ def main():
                          "the timed steps overlap kernel tails across lane groups",
         "bitstream_bytes_per_step": int(nbytes),
     }
+
+    # ---- BASELINE configs[4] (4K, 64 GOPs, r=64, 4 references, "whole 8 x B200 box"): measured when the whole box is there ----
+    if world == 8 and not args.skip_4k:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("run_c4_8gpu", os.path.join(ROOT, "profiles", "run_c4_8gpu.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            c5 = mod.measure(rank, world, local_rank)
+        except Exception as e:   # a secondary figure, not a reason to lose the line -- but every rank must take the same path
+            c5 = {"error": repr(e)}
+        line["config5_4k_whole_box"] = c5
 
     if rank == 0 and world == 1 and not args.skip_cpu:
         # in a subprocess: this process maps libbvc_b200.so only
