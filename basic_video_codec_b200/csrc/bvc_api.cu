@@ -77,7 +77,10 @@ struct bvc_ctx {
     int8_t *d_resid_mc = nullptr, *d_resid_nomc = nullptr;
     uint32_t* d_blk_bits = nullptr;
     int blk_words = 0;
-    long long *d_coef_off = nullptr, *d_row_bits = nullptr, *d_pred_row_off = nullptr, *d_cmp = nullptr;
+    long long *d_coef_off = nullptr, *d_row_bits = nullptr, *d_cmp = nullptr;
+    int32_t* d_pred_off = nullptr;                                // stream assembly scratch, see PackArgs
+    long long *d_tile_tot = nullptr, *d_tile_base = nullptr;
+    int pack_tiles_n = 0;
     // stream arena: one slot per frame of a clip call (slot 0 for the frame-level calls)
     uint32_t *d_coef_stream = nullptr, *d_pred_stream = nullptr;
     long long *d_frame_bits = nullptr, *d_frame_off = nullptr;
@@ -288,8 +291,11 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_resid_mc, (size_t)g.W * g.H));
         CK(dalloc(&c->d_resid_nomc, (size_t)g.W * g.H));
         CK(dalloc(&c->d_coef_off, L * (nb + 1)));
+        c->pack_tiles_n = pack_tiles(g.nblk);
+        CK(dalloc(&c->d_pred_off, L * nb));
+        CK(dalloc(&c->d_tile_tot, L * (size_t)(c->pack_tiles_n + 1) * 2));
+        CK(dalloc(&c->d_tile_base, L * (size_t)(c->pack_tiles_n + 1) * 2));
         CK(dalloc(&c->d_row_bits, L * g.bh));
-        CK(dalloc(&c->d_pred_row_off, L * (g.bh + 1)));
         CK(dalloc(&c->d_cmp, L));
         CK(dalloc(&c->d_rowbits, 1));
         CK(dalloc(&c->d_progress, L * g.bh));
@@ -335,7 +341,8 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->in_pool); cudaFree(c->ref_pool); cudaFree(c->d_mv); cudaFree(c->d_modes); cudaFree(c->d_isad);
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
-    cudaFree(c->d_pred_row_off); cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_top_mail); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_pred_off); cudaFree(c->d_tile_tot); cudaFree(c->d_tile_base);
+    cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_top_mail); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container); cudaFree(c->d_frag[0]); cudaFree(c->d_frag[1]);
@@ -594,9 +601,11 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     pk.mv = t.mv; pk.modes = t.modes; pk.qp_rows = t.qp_rows;
     pk.blk_bits = t.blk_bits; pk.blk_nbits = t.blk_nbits; pk.blk_words = c->blk_words;
     pk.coef_off = c->d_coef_off + L0 * (nb + 1);
+    pk.pred_off = c->d_pred_off + L0 * nb; pk.tiles = c->pack_tiles_n;
+    pk.tile_tot = c->d_tile_tot + L0 * (size_t)(c->pack_tiles_n + 1) * 2; pk.tile_base = c->d_tile_base + L0 * (size_t)(c->pack_tiles_n + 1) * 2;
     pk.lanes = t.lanes;
     pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
-    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh; pk.pred_row_off = c->d_pred_row_off + L0 * (g.bh + 1);
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits + L0 * g.bh;
     pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words; pk.slot_overflow = c->d_overflow + 1;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = sp.intra; pk.with_ref = c->p.nref_frames > 1;
@@ -655,13 +664,13 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         if (sp.intra && !rc_rows) { CK(launch_tq_ientropy(t, nl, st_pack)); c->launches += 1; }
         CK(launch_pack(pk, nl, st_pack));
         CK(cudaEventRecord(ev_pack_done, st_pack));
-        c->launches += 2;
+        c->launches += c->pack_tiles_n > 1 ? 3 : 2;
         return BVC_OK;
     }
     const int ep = tick(c, st_post);
     CK(launch_pack(pk, nl, st_post));
     span(c, BVC_K_PACK, ep, tick(c, st_post));
-    c->launches += 2;
+    c->launches += c->pack_tiles_n > 1 ? 3 : 2;
     return BVC_OK;
 }
 static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api) {
@@ -863,8 +872,9 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
     pk.blk_bits = c->d_blk_bits; pk.blk_nbits = c->d_blk_nbits; pk.blk_words = c->blk_words;
     pk.coef_off = c->d_coef_off; pk.lanes = c->d_fr_lanes;
+    pk.pred_off = c->d_pred_off; pk.tiles = c->pack_tiles_n; pk.tile_tot = c->d_tile_tot; pk.tile_base = c->d_tile_base;
     pk.coef_stream = c->d_coef_stream; pk.pred_stream = c->d_pred_stream;
-    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits; pk.pred_row_off = c->d_pred_row_off;
+    pk.frame_bits = c->d_frame_bits; pk.row_bits = c->d_row_bits;
     pk.coef_cap_words = c->coef_cap_words; pk.pred_cap_words = c->pred_cap_words; pk.slot_overflow = c->d_overflow + 1;
     pk.bw = g.bw; pk.bh = g.bh; pk.nblk = g.nblk; pk.base_qp = c->p.qp;
     pk.intra = intra; pk.with_ref = c->p.nref_frames > 1;
@@ -915,7 +925,7 @@ extern "C" int bvc_frame_end(bvc_ctx* c, bvc_frame_out* out) {
     TqArgs t; PackArgs pk;
     fill_row_args(c, t, pk, c->row_intra);
     CK(launch_pack(pk, 1, c->st));
-    c->launches += 2;
+    c->launches += c->pack_tiles_n > 1 ? 3 : 2;
     c->row_open = false;
     return frame_collect(c, out, c->row_intra, c->row_nref, c->row_fl, false, nullptr, nullptr, nullptr);
 }

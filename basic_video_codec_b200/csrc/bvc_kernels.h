@@ -145,13 +145,16 @@ struct PackArgs {
     const uint32_t* blk_bits;
     const int32_t* blk_nbits;
     int blk_words;
-    long long* coef_off;             // device [lanes][nblk+1]  exclusive bit offsets (out)
+    long long* coef_off;             // device [lanes][nblk+1] scratch: bit offset of every block's string inside its tile
+    int32_t* pred_off;               // device [lanes][nblk] scratch: the same for its prediction symbols
+    long long* tile_tot;             // device [lanes][tiles+1][2] scratch: (coefficient, prediction) bits per tile of 1024 blocks
+    long long* tile_base;            // device [lanes][tiles+1][2] scratch: exclusive scan of tile_tot, frame totals in entry `tiles`
+    int tiles;                       // pack_tiles(nblk)
     const FrameLane* lanes;        // device [lanes] (slot = where this frame's streams go)
     uint32_t* coef_stream;         // device [slots][coef_cap_words]
     uint32_t* pred_stream;         // device [slots][pred_cap_words]
     long long* frame_bits;           // device [slots][2] = (pred_bits, coef_bits) (out)
     long long* row_bits;             // device [lanes][bh] (out) bits_per_row
-    long long* pred_row_off;         // device [lanes][bh+1] scratch: prediction-stream offset of every row start
     size_t coef_cap_words, pred_cap_words;
     int* slot_overflow;            // device flag: a frame's stream does not fit its slot (may be null)
     int bw, bh, nblk;
@@ -159,6 +162,7 @@ struct PackArgs {
     int intra;                     // 1: modes, 0: motion vectors
     int with_ref;                  // nRefFrames > 1: code the reference index difference
 };
+int pack_tiles(int nblk);
 cudaError_t launch_pack(const PackArgs& a, int lanes, cudaStream_t st);
 // bits the reference accounts to one block row (PFrame.py:76-83): coefficient bits of its blocks + its
 // prediction symbols (row QP symbol included).  out: device long long[lanes].
