@@ -314,10 +314,22 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                         const size_t blk = (size_t)(by0 + yy) * a.bw + bx0 + b;
                         smap = a.sad_map + ((((size_t)lane * a.max_refs + r) * a.nphase + ph) * a.nblk + blk) * (size_t)a.map_stride + (dx + R);
                     }
-                    const uint32_t* rowp = colp + ((yy - yy0) * BS + m0) * wpitch;
-                    int mbase = m0 - (BS - 1);
+                    // Vertical offsets outside the plane are masked through utab, but sliding over them costs as much as over
+                    // valid ones (top and bottom block rows: up to half of the 2R+1 offsets, 2.2 % of a 1080p r=32 frame).  A
+                    // main thread therefore starts at the first offset that can be valid and runs only as many steady bodies as
+                    // the valid span needs (warp-uniform: mlo / mhi depend on the block row only); a segment of the extra warps
+                    // that lies outside the span is skipped.
+                    int m0y = m0, nm = 0;
+                    if (!is_extra) {
+                        nm = max(0, (max(mhi - mlo, 0) + BS - 1) / BS - 1);
+                        nm = min(nm, nmid);
+                        m0y = max(0, min(mlo, 2 * Rv - BS * (nm + 1)));
+                    } else if (m0 + BS < mlo || m0 > mhi) {
+                        continue;
+                    }
+                    const uint32_t* rowp = colp + ((yy - yy0) * BS + m0y) * wpitch;
+                    int mbase = m0y - (BS - 1);
                     const uint32_t* ut = &utab[yy][0] + BS + mbase;
-                    const int nm = is_extra ? 0 : nmid;
                     me_body<BS, BODY_FIRST, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                     rowp += BS * wpitch;
                     mbase += BS;

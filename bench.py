@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
 CLIP_SEED = 1080
-# DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r1_ncu_*.csv)
-ME_TRAFFIC_BYTES_PER_LANE = (41.834240e6 + 0.472576e6) / 10       # 10-lane launch (two lane groups)
+# DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r2_ncu_me_kernel.csv, r1_ncu_tq_kernel.csv)
+ME_TRAFFIC_BYTES_PER_LANE = (41.836032e6 + 0.075008e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
 TQ_TRAFFIC_BYTES_PER_LANE = (43.469568e6 + 3.402240e6) / 10
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
@@ -431,7 +431,7 @@ def main():
             "per_rank_peak": [p / 1e12 for p in pk_all] if world > 1 else None,
             "whole_step_frac": (whole_step_px / (dt / args.steps)) / peak_px,
             "traffic": ME_TRAFFIC_BYTES_PER_LANE * args.lanes,
-            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 10-lane launch / 10 (profiles/r1_ncu_me_kernel.csv); "
+            "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 10-lane launch / 10 (profiles/r2_ncu_me_kernel.csv); "
                               "algorithmic: 2 planes of 2.09 MB per lane",
             "algorithmic_bytes": 2 * W * H * args.lanes + 16 * (W // BS) * (H // BS) * args.lanes,
             "launch_ms": me_avg_s * 1e3, "launches": me_n,
