@@ -275,7 +275,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
-        if (const char* e = getenv("BVC_IQUAD")) c->iquad = atoi(e) != 0;
+        if (const char* e = getenv("BVC_IQUAD")) c->iquad = std::max(0, std::min(2, atoi(e)));
         if (const char* e = getenv("BVC_TQ_CTAS")) c->tq_cta_cap = std::max(0, atoi(e));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
         c->ref_planes = L * c->slots * c->pps;

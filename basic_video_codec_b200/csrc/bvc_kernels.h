@@ -124,7 +124,7 @@ struct TqArgs {
                                    // order in which CTAs actually start, so a row never waits for a CTA that is not resident
     int row_begin, row_count;      // block rows to encode in this launch (0, bh = whole frame); the row-by-row
                                    // rate-control loop (Frame.get_rc_qp, Frame.py:168-188) launches one row at a time
-    int quad;                      // I frames, BS >= 8: four warps per block pair (tq_iframe_quad_kernel) instead of one
+    int quad;                      // I frames, BS >= 8: four warps per block pair (tq_iframe_quad_kernel) instead of one (2: always)
     int cta_cap;                   // P frames: at most this many CTAs, each looping over work units (0 = one CTA per unit)
 };
 cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st);

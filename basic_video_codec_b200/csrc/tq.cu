@@ -392,7 +392,8 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st, bool with_entr
         // Four warps per block pair shorten the dependent chain (one 16x16 block step 4.8 -> 2.9 us), but the rows of a frame
         // run in lock step, so every CTA of an SM is in the same pass at the same time: beyond about two CTAs per SM the passes
         // queue for the SM's fp64 pipe and shared memory and the gain is gone (20 lanes of 1080p: 0.94 against 0.91 ms per I
-        // step; 3 lanes: 0.54 against 1.11, profiles/r2_iframe_quad.jsonl).
+        // step; 3 lanes: 0.54 against 1.11, profiles/r2_iframe_quad.jsonl).  8x8 blocks (80 registers, less work per pass)
+        // gain at any size: 20 lanes 1.04 against 1.19-1.35 ms.
         static int sms_dev[BVC_MAX_DEVICES] = {};
         int& sms = sms_dev[current_device_slot()];
         if (sms == 0) {
@@ -400,7 +401,7 @@ cudaError_t launch_i(const TqArgs& a, int lanes, cudaStream_t st, bool with_entr
             cudaGetDevice(&dev);
             if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
         }
-        if (a.quad && a.row_count * ngrp <= 2 * sms) tq_iframe_quad_kernel<BS><<<a.row_count * ngrp, 128, sizeof(QuadTile<BS>) + NBW * BS + 32, st>>>(a, lanes);
+        if (a.quad == 2 || (a.quad && (BS == 8 || a.row_count * ngrp <= 2 * sms))) tq_iframe_quad_kernel<BS><<<a.row_count * ngrp, 128, sizeof(QuadTile<BS>) + NBW * BS + 32, st>>>(a, lanes);
         else tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);
     } else {
         tq_iframe_kernel<BS><<<a.row_count * ngrp, 32, smem, st>>>(a, lanes);

@@ -23,7 +23,7 @@ for bs, r, qp in ((16, 4, 4), (8, 2, 3)):
         frames = base[:n]
         out = np.empty(n * W * H, np.uint8)
         ref = None
-        for quad in (0, 1):
+        for quad in (0, 1, 2):   # 2 = four warps whatever the number of CTAs in flight
             os.environ["BVC_IQUAD"] = str(quad)
             with bvc.Context(W, H, bs, r, qp, 1, False, False, IP, device=0, max_lanes=lanes) as ctx:
                 ctx.clip_upload(frames)
