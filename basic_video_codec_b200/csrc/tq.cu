@@ -50,6 +50,32 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
     }
 }
 
+// Mode decision of the intra wavefront, IFrame.py:184-195, from registers: lane (q, r) holds row r of the current block
+// (cw), the block's left column as a row (lw, the same for every lane of the block) and its own top pixel tv.
+//   mode 0 ("horizontal"): pred[r][c] = left[c]  -> this lane's share of the SAD is sum_c (cur[r][c] - left[c]) mod 256
+//   mode 1 ("vertical"):   pred[r][c] = top[r]   ->                              sum_c (cur[r][c] - top[r]) mod 256
+// In-frame predictors are uint8, so cur - pred wraps mod 256 (:189-190); border predictors are int64 128: a true absolute
+// difference.  Per-byte SIMD: __vsub4 wraps, __vsadu4(v, 0) sums four bytes.  The sums over the block's lanes (integer,
+// any order) follow with shuffles; same totals as the reference's per-pixel loop.
+template <int BS>
+__device__ __forceinline__ void intra_mode_sads(const uint32_t (&cw)[BS / 4], const uint32_t (&lw)[BS / 4], int tv, bool has_left, bool has_top,
+                                                int& sh, int& sv) {
+    const uint32_t tw = (uint32_t)tv * 0x01010101u;
+    uint32_t h = 0, v = 0;
+#pragma unroll
+    for (int j = 0; j < BS / 4; j++) {
+        h += has_left ? __vsadu4(__vsub4(cw[j], lw[j]), 0u) : __vsadu4(cw[j], 0x80808080u);
+        v += has_top ? __vsadu4(__vsub4(cw[j], tw), 0u) : __vsadu4(cw[j], 0x80808080u);
+    }
+    sh = (int)h;
+    sv = (int)v;
+#pragma unroll
+    for (int d = 1; d < BS; d <<= 1) {
+        sh += __shfl_xor_sync(0xffffffffu, sh, d);
+        sv += __shfl_xor_sync(0xffffffffu, sv, d);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // I frames: block (bx,by) needs the reconstructed right column of (bx-1,by) and bottom row of
 // (bx,by-1) (IFrame.py:184-213) => anti-diagonal wavefront.  One warp (= one CTA) walks one block row
@@ -111,32 +137,20 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
             tv = (int)(v & 255u);
         }
         __syncwarp();
-        const int lv = (ox > 0) ? (int)sm.left[q][x] : 128;
         if (ox == 0) sm.left[q][x] = 128;
         sm.top[q][x] = (uint8_t)tv;
-        store_row_words<BS>(&t.cur[q][x][0], cw);
         __syncwarp();
-        // mode decision, IFrame.py:184-195.  In-frame predictors are uint8, so cur - pred wraps mod 256
-        // (:189-190); border predictors are int64 128, a true absolute difference.
-        int sh = 0, sv = 0;
+        uint32_t lw[BS / 4];
 #pragma unroll
-        for (int i = 0; i < BS; i++) {
-            const int ch = t.cur[q][i][x];  // column x against left[x]  (mode 0: pred[r][c] = left[c])
-            sh += (ox > 0) ? ((ch - lv) & 255) : abs(ch - 128);
-            const int cv = t.cur[q][x][i];  // row x against top[x]      (mode 1: pred[r][c] = top[r])
-            sv += (oy > 0) ? ((cv - tv) & 255) : abs(cv - 128);
-        }
-#pragma unroll
-        for (int d = 1; d < BS; d <<= 1) {
-            sh += __shfl_xor_sync(0xffffffffu, sh, d);
-            sv += __shfl_xor_sync(0xffffffffu, sv, d);
-        }
+        for (int i = 0; i < BS / 4; i++) lw[i] = reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i];
+        int sh, sv;
+        intra_mode_sads<BS>(cw, lw, tv, ox > 0, oy > 0, sh, sv);
         const int mode = (sh < sv) ? 0 : 1;  // tie -> vertical, IFrame.py:192-195
         {
             // mode 0: row x of pred = left[0..BS-1]; mode 1: row x = top[x] replicated
             uint32_t pw[BS / 4];
 #pragma unroll
-            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i] : (uint32_t)tv * 0x01010101u;
+            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? lw[i] : (uint32_t)tv * 0x01010101u;
             stage_row<BS>(t, q, x, cw, pw);
         }
         if (valid && x == 0) {
@@ -213,29 +227,19 @@ __global__ void __launch_bounds__(128) tq_iframe_quad_kernel(TqArgs a, int lanes
                 while ((v & 0xffffff00u) != tag) v = mail_up[bx * BS];
                 tv = (int)(v & 255u);
             }
-            const int lv = (ox > 0) ? (int)sm.left[q][x] : 128;   // written by this warp at the end of the previous block
             __syncwarp();
-            if (ox == 0) sm.left[q][x] = 128;
-            store_row_words<BS>(&t.cur[q][x][0], cw);
+            if (ox == 0) sm.left[q][x] = 128;   // else written by this warp at the end of the previous block
             __syncwarp();
-            // mode decision, IFrame.py:184-195 (see tq_iframe_kernel)
-            int sh = 0, sv = 0;
+            uint32_t lw[BS / 4];
 #pragma unroll
-            for (int i = 0; i < BS; i++) {
-                const int ch = t.cur[q][i][x];
-                sh += (ox > 0) ? ((ch - lv) & 255) : abs(ch - 128);
-                const int cv = t.cur[q][x][i];
-                sv += (oy > 0) ? ((cv - tv) & 255) : abs(cv - 128);
-            }
-#pragma unroll
-            for (int d = 1; d < BS; d <<= 1) {
-                sh += __shfl_xor_sync(0xffffffffu, sh, d);
-                sv += __shfl_xor_sync(0xffffffffu, sv, d);
-            }
+            for (int i = 0; i < BS / 4; i++) lw[i] = reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i];
+            // mode decision, IFrame.py:184-195 (see intra_mode_sads)
+            int sh, sv;
+            intra_mode_sads<BS>(cw, lw, tv, ox > 0, oy > 0, sh, sv);
             const int mode = (sh < sv) ? 0 : 1;
             uint32_t pw[BS / 4];
 #pragma unroll
-            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? reinterpret_cast<const uint32_t*>(&sm.left[q][0])[i] : (uint32_t)tv * 0x01010101u;
+            for (int i = 0; i < BS / 4; i++) pw[i] = mode == 0 ? lw[i] : (uint32_t)tv * 0x01010101u;
             stage_row<BS>(t, q, x, cw, pw);
             if (valid && x == 0) {
                 a.modes[(size_t)fl * a.nblk + by * a.bw + bx] = mode;
