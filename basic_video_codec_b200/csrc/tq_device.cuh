@@ -91,6 +91,17 @@ __device__ __forceinline__ double int_to_double(int n) {   // exact for any int3
     return __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)n)), 4503601774854144.0);
 }
 __device__ __forceinline__ double pow2_neg(int s) { return __hiloint2double((1023 - s) << 20, 0); }
+// Quantise and rescale in one go: np.round(coef / 2^s) (dct.py:35-37, half to even; the division is exact) and level * 2^s
+// (dct.py:40-42).  1.5 * 2^(52+s) + coef rounds coef to the nearest multiple of 2^s, ties to the even multiple -- the same
+// rounding as rint(coef * 2^-s), because scaling by a power of two commutes with round-to-nearest -- the low mantissa word
+// of the sum is the level in two's complement, and subtracting the constant again leaves level * 2^s exactly.
+// magic_hi = 0x43380000 + (s << 20).  Two fp64 additions instead of multiply + add + subtract (+ a multiply to rescale).
+__device__ __forceinline__ double quant_rescale(double coef, int magic_hi, int& level) {
+    const double M = __hiloint2double(magic_hi, 0);
+    const double m = __dadd_rn(coef, M);
+    level = __double2loint(m);
+    return __dsub_rn(m, M);
+}
 __device__ __forceinline__ double pow2_pos(int s) { return __hiloint2double((1023 + s) << 20, 0); }
 
 struct TqOut {
@@ -203,11 +214,9 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         // quantize_block :35-37 = round half to even of coef * 2^-s (exact scaling)
         const int s = qp + min(max(u + v - (BS - 2), 0), 2);
         int li;
-        const double lq = rint_magic(__dmul_rn(coef, pow2_neg(s)), li);
+        const double resc = quant_rescale(coef, 0x43380000 + (s << 20), li);
         lv[v] = (short)li;
-        // rescale_block dct.py:40-42 is exact, so (lq * 2^s) * w == lq * (w * 2^s) with one rounding
-        const double wq = __hiloint2double(__double2hiint(w) + (s << 20), __double2loint(w));
-        a[v] = __dmul_rn(lq, wq);
+        a[v] = __dmul_rn(resc, w);   // rescale_block dct.py:40-42 is exact: (level * 2^s) * w, one rounding
     }
     {
         uint32_t pk[BS / 2];
@@ -348,10 +357,9 @@ __device__ __forceinline__ void quad_f2(QuadTile<BS>& t, int q, int x, int qp) {
         const double coef = __dmul_rn(acc, w);
         const int sh = qp + min(max(u + v - (BS - 2), 0), 2);
         int li;
-        const double lq = rint_magic(__dmul_rn(coef, pow2_neg(sh)), li);
+        const double resc = quant_rescale(coef, 0x43380000 + (sh << 20), li);
         lv[k] = (short)li;
-        const double wq = __hiloint2double(__double2hiint(w) + (sh << 20), __double2loint(w));
-        t.B[q][u][v] = __dmul_rn(lq, wq);
+        t.B[q][u][v] = __dmul_rn(resc, w);
     }
     uint32_t* ls = reinterpret_cast<uint32_t*>(&t.lev[q][u][WQ * UW]);
 #pragma unroll
