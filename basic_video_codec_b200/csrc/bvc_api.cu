@@ -95,7 +95,6 @@ struct bvc_ctx {
     void* h_totals = nullptr;         // pinned: per-wave fragment sizes and overflow flags
     size_t h_totals_cap = 0;
     size_t slot_bytes = 0;            // bvc_set_stream_slot_bytes: 0 = default
-    int* d_progress = nullptr;
     uint32_t* d_top_mail = nullptr;   // [max_lanes][bh][bw][bs]: bottom rows handed down the I-frame wavefront (tq_iframe_kernel)
     uint32_t epoch = 0;               // tag of the last I frame's mailbox entries
     int* d_ticket = nullptr;      // [max_lanes]: start-order counters of the wavefront kernels, one per lane group in flight
@@ -113,7 +112,7 @@ struct bvc_ctx {
     int fastme_direct = 0;  // bvc_set_fastme_direct: 0 auto (window walk / transfer tables), 1 direct evaluation, 2 SAD map + serial walk,
                             // 3 window walk, 4 SAD map + transfer tables
     DBuf dec_in, dec_streams, dec_chunk_stream, dec_exit, dec_nsym, dec_neob, dec_entry, dec_symbase, dec_eobbase, dec_intra,
-        dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_progress, dec_frame_ok, dec_step_frames,
+        dec_mv, dec_modes, dec_qp, dec_blk_start, dec_sym0, dec_syms, dec_levels, dec_lanes, dec_frame_ok, dec_step_frames,
         dec_step_streams;
 
     // host staging
@@ -298,7 +297,6 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         CK(dalloc(&c->d_row_bits, L * g.bh));
         CK(dalloc(&c->d_cmp, L));
         CK(dalloc(&c->d_rowbits, 1));
-        CK(dalloc(&c->d_progress, L * g.bh));
         CK(dalloc(&c->d_ticket, L));
         CK(dalloc(&c->d_top_mail, L * nb * bs));
         CK(cudaMemset(c->d_top_mail, 0, L * nb * bs * sizeof(uint32_t)));   // epoch 0 = never posted
@@ -342,14 +340,14 @@ extern "C" void bvc_destroy(bvc_ctx* c) {
     cudaFree(c->d_qp_rows); cudaFree(c->d_blk_nbits); cudaFree(c->d_blk_bits); cudaFree(c->d_levels);
     cudaFree(c->d_resid_mc); cudaFree(c->d_resid_nomc); cudaFree(c->d_coef_off); cudaFree(c->d_row_bits);
     cudaFree(c->d_pred_off); cudaFree(c->d_tile_tot); cudaFree(c->d_tile_base);
-    cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_progress); cudaFree(c->d_ticket); cudaFree(c->d_top_mail); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
+    cudaFree(c->d_cmp); cudaFree(c->d_rowbits); cudaFree(c->d_ticket); cudaFree(c->d_top_mail); cudaFree(c->d_rc_remaining); cudaFree(c->d_me_lanes);
     cudaFree(c->d_fr_lanes); cudaFree(c->d_hp_src); cudaFree(c->d_hp_dst);
     cudaFree(c->d_coef_stream); cudaFree(c->d_pred_stream); cudaFree(c->d_frame_bits); cudaFree(c->d_frame_off);
     cudaFree(c->d_overflow); cudaFree(c->d_container); cudaFree(c->d_frag[0]); cudaFree(c->d_frag[1]);
     if (c->h_totals) cudaFreeHost(c->h_totals);
     for (bvc_ctx::DBuf* b : {&c->dec_in, &c->dec_streams, &c->dec_chunk_stream, &c->dec_exit, &c->dec_nsym, &c->dec_neob, &c->dec_entry,
                              &c->dec_symbase, &c->dec_eobbase, &c->dec_intra, &c->dec_mv, &c->dec_modes, &c->dec_qp, &c->dec_blk_start,
-                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_progress, &c->dec_frame_ok, &c->dec_step_frames,
+                             &c->dec_sym0, &c->dec_syms, &c->dec_levels, &c->dec_lanes, &c->dec_frame_ok, &c->dec_step_frames,
                              &c->dec_step_streams, &c->sad_map, &c->fastme_tab})
         cudaFree(b->p);
     if (c->h_desc) cudaFreeHost(c->h_desc);
@@ -585,7 +583,7 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
     t.resid_nomc = frame_api ? c->d_resid_nomc : nullptr;
     t.blk_bits = c->d_blk_bits + L0 * nb * c->blk_words; t.blk_nbits = c->d_blk_nbits + L0 * nb; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
-    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress + L0 * g.bh; t.ticket = c->d_ticket + L0;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.ticket = c->d_ticket + L0;
     t.top_mail = c->d_top_mail + L0 * nb * g.bs;
     if (sp.intra) { c->epoch = (c->epoch % 0xFFFFFEu) + 1; t.epoch = c->epoch; }   // one epoch per I frame (all its rows, also row by row)
     t.row_begin = 0; t.row_count = g.bh;
@@ -866,7 +864,7 @@ static void fill_row_args(bvc_ctx* c, TqArgs& t, PackArgs& pk, bool intra) {
     t.levels = c->d_levels; t.resid_mc = c->d_resid_mc; t.resid_nomc = c->d_resid_nomc;
     t.blk_bits = c->d_blk_bits; t.blk_nbits = c->d_blk_nbits; t.blk_words = c->blk_words;
     t.W = g.W; t.H = g.H; t.bs = g.bs; t.bw = g.bw; t.bh = g.bh; t.nblk = g.nblk;
-    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.progress = c->d_progress; t.ticket = c->d_ticket;
+    t.frac = c->p.frac_me; t.multi_ref = c->p.nref_frames > 1; t.ticket = c->d_ticket;
     t.top_mail = c->d_top_mail; t.epoch = c->epoch; t.quad = c->iquad;
     pk = PackArgs{};
     pk.mv = c->d_mv; pk.modes = c->d_modes; pk.qp_rows = c->d_qp_rows;
@@ -1122,7 +1120,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     uint8_t *d_in, *d_exit, *d_neob, *d_entry, *d_intra, *d_frame_ok;
     uint16_t* d_nsym;
     EgStream* d_streams;
-    int *d_chunk_stream, *d_symbase, *d_eobbase, *d_blk_start, *d_progress, *d_step_frames, *d_step_streams;
+    int *d_chunk_stream, *d_symbase, *d_eobbase, *d_blk_start, *d_step_frames, *d_step_streams;
     int4* d_mv;
     int32_t *d_modes, *d_qp;
     long long* d_sym0;
@@ -1135,7 +1133,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
         (rc = dbuf(c, c->dec_eobbase, (size_t)nchunks, &d_eobbase)) || (rc = dbuf(c, c->dec_intra, (size_t)n, &d_intra)) ||
         (rc = dbuf(c, c->dec_mv, (size_t)n * nb, &d_mv)) || (rc = dbuf(c, c->dec_modes, (size_t)n * nb, &d_modes)) ||
         (rc = dbuf(c, c->dec_qp, (size_t)n * g.bh, &d_qp)) || (rc = dbuf(c, c->dec_blk_start, (size_t)n * (nb + 1), &d_blk_start)) ||
-        (rc = dbuf(c, c->dec_sym0, (size_t)n, &d_sym0)) || (rc = dbuf(c, c->dec_progress, (size_t)c->max_lanes * g.bh, &d_progress)) ||
+        (rc = dbuf(c, c->dec_sym0, (size_t)n, &d_sym0)) ||
         (rc = dbuf(c, c->dec_frame_ok, (size_t)n, &d_frame_ok)) || (rc = dbuf(c, c->dec_step_frames, step_frames.size(), &d_step_frames)) ||
         (rc = dbuf(c, c->dec_step_streams, step_streams.size(), &d_step_streams)) ||
         (rc = dbuf(c, c->dec_syms, (size_t)slab_syms * SLABS + 8, &d_syms)) || (rc = dbuf(c, c->dec_lanes, frl.size(), &d_lanes)))
@@ -1255,7 +1253,7 @@ static int decode_impl(bvc_ctx* c, const uint8_t* data, size_t len, int max_fram
     DecArgs a{};
     a.ref_base = c->ref_pool; a.ref_plane_bytes = g.plane_bytes; a.ref_pitch = g.pitch;
     a.mv_all = d_mv; a.modes_all = d_modes; a.qp_all = d_qp; a.syms = d_syms; a.coef_sym0 = d_sym0; a.blk_start = d_blk_start;
-    a.levels_out = d_levels; a.progress = d_progress; a.ticket = c->d_ticket; a.err_flag = c->d_overflow;
+    a.levels_out = d_levels; a.ticket = c->d_ticket; a.err_flag = c->d_overflow;
     a.W = g.W; a.H = g.H; a.bs = g.bs; a.bw = g.bw; a.bh = g.bh; a.nblk = g.nblk; a.frac = c->p.frac_me;
     a.frame_ok = d_frame_ok; a.top_mail = c->d_top_mail;
     // Decoded planes go back on their own stream so that the download of step s overlaps the kernels of step s+1 (the

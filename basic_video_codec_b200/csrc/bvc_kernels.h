@@ -116,7 +116,6 @@ struct TqArgs {
     int W, H, bs, bw, bh, nblk;
     int frac;                      // MVs in half-pel units, pred from phase planes
     int multi_ref;                 // nRefFrames > 1: pred from refs[mv.ref] else refs[0]
-    int* progress;                 // I frames: device [lanes][bh] wavefront progress counters (zeroed)
     uint32_t* top_mail;            // I frames: device [lanes][bh][bw][bs] mailboxes: bottom row of the block above, every pixel
                                    // as pixel | epoch << 8 (see tq_iframe_kernel)
     uint32_t epoch;                // I frames: tag of this frame's mailbox entries (1 .. 2^24-1, never the previous frame's)
@@ -211,7 +210,6 @@ struct DecArgs {
     const uint8_t* frame_ok;       // [nframes] 0 = the frame's coefficient stream is malformed: leave the frame alone
     uint32_t* top_mail;            // I frames: [lanes][bh][bw][bs] bottom rows handed down, pixel | epoch << 8 (see tq_iframe_kernel)
     uint32_t epoch;
-    int* progress;                 // I frames: [lanes][bh] wavefront counters (zeroed)
     int* ticket;                   // I frames: start-order ticket counter (see TqArgs::ticket)
     int* err_flag;
     int W, H, bs, bw, bh, nblk;

@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         WarpTile<BS> t;
         uint8_t zz[BS * BS];
         __align__(16) uint8_t left[NBW][BS];
-        __align__(16) uint8_t top[NBW][BS];
     };
     ISmem& sm = *reinterpret_cast<ISmem*>(smraw);
     const int lane = threadIdx.x;
@@ -138,7 +137,6 @@ __global__ void __launch_bounds__(32) tq_iframe_kernel(TqArgs a, int lanes) {
         }
         __syncwarp();
         if (ox == 0) sm.left[q][x] = 128;
-        sm.top[q][x] = (uint8_t)tv;
         __syncwarp();
         uint32_t lw[BS / 4];
 #pragma unroll
