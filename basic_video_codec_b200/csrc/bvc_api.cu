@@ -1597,7 +1597,7 @@ static int encode_clip_impl(bvc_ctx* c, const uint8_t* host_frames, int nframes,
         h_total[pi] = 0; h_over[2 * pi] = h_over[2 * pi + 1] = 0;
         if (n == 0) return BVC_OK;
         cudaStream_t ps = part_stream(gi);   // behind the group's last stream assembly; the next wave's assembly follows on the same stream
-        if (w >= 2) CK(cudaStreamWaitEvent(ps, ev_frag_free[pi - 2 * NG], 0));   // staging buffer w & 1 has been copied out
+        if (w >= 2 && ev_frag_free[pi - 2 * NG]) CK(cudaStreamWaitEvent(ps, ev_frag_free[pi - 2 * NG], 0));   // staging buffer w & 1 has been copied out
         const size_t first = (size_t)gi * per * IP;   // first frame slot of the part (a multiple of I_Period)
         ContainerArgs ca{};
         ca.frame_bits = c->d_frame_bits + 2 * first;

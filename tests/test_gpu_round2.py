@@ -265,3 +265,38 @@ def test_small_output_buffer_and_small_stream_slots_are_reported_not_overrun():
         assert ctx.encode_clip(frames)[0] == want             # retries with the worst-case slot
         ctx.set_stream_slot_bytes(0)
         assert ctx.encode_clip(frames)[0] == want
+
+
+def test_unbalanced_lane_groups_overflow_their_staging_region_and_the_call_is_repeated():
+    """The container of a wave is staged in one region per lane group, sized from an estimate.  Two noisy GOPs in the first
+    group and two flat ones in the second: the first part outgrows its region, the library enlarges the staging and asks for
+    the call to be repeated (BVC_ERR_NOMEM, "staging"); the binding does that and ends with the oracle's stream -- through
+    the host-buffer call, the resident call and the device-resident container of the sharded path."""
+    ob = _ob()
+    W, H, bs, r, qp, ip = 640, 480, 16, 2, 0, 6
+    rng = np.random.default_rng(11)
+    noisy = rng.integers(0, 256, size=(2 * ip, H, W), dtype=np.uint8)
+    flat = np.full((2 * ip, H, W), 128, np.uint8)
+    frames = np.ascontiguousarray(np.concatenate([noisy, flat]))
+    n = frames.shape[0]
+    want, _ = ob.encode_clip(ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip), frames, want_recon=False, nthreads=8)
+    assert len(want) > 2 * (n * W * H // 8 // 2 + (1 << 20))      # the first part alone is larger than two default regions
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=4) as ctx:
+        ctx.set_lane_groups(2)
+        assert ctx.encode_clip(frames)[0] == want
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=4) as ctx:
+        ctx.set_lane_groups(2)
+        ctx.set_stream_slot_bytes(W * H * 4)                       # 32 bits per pixel: only the staging is too small now
+        out = np.empty(2 * len(want), np.uint8)
+        ln = ctx.encode_clip_into(frames, out)
+        assert bytes(out[:ln]) == want
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=4) as ctx:
+        ctx.set_lane_groups(2)
+        ctx.set_stream_slot_bytes(W * H * 4)
+        ctx.clip_upload(frames)
+        out, ln = ctx.encode_clip_resident(n, np.empty(2 * len(want), np.uint8))
+        assert bytes(out[:ln]) == want
+        ln2 = ctx.encode_clip_device(None, n, cap_hint=2 * len(want))
+        got = np.empty(ln2, np.uint8)
+        ctx.container_download(got, 0, 0, ln2)
+        assert bytes(got) == want
