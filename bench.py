@@ -464,6 +464,10 @@ def main():
                      "peak_source": "measured in this run (bvc_measure_peaks, dependent-free fma.rn.f64 chains)"},
         },
         "decoder": decoder,
+        # latency-bound kernel (no roofline fraction, time per diagonal of the anti-diagonal wavefront)
+        "intra_wavefront": {"ms_per_I_step": kt_acc["tq_i"][0] / KSTEPS, "diagonals": (W // BS) + (H // BS) - 1,
+                            "us_per_diagonal": kt_acc["tq_i"][0] / KSTEPS * 1e3 / ((W // BS) + (H // BS) - 1),
+                            "note": f"{args.lanes} I frames in one launch (one warp per block pair at this lane count) + their entropy-coding kernel"},
         "kernel_ms_per_step": {k: v[0] / KSTEPS for k, v in kt_acc.items()},
         "kernel_timing": f"{KSTEPS} extra passes with one lane group (kernels serialised on one stream, {serial_ms:.2f} ms per pass); "
                          "the timed steps overlap kernel tails across lane groups",
