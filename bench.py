@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
 CLIP_SEED = 1080
 # DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r2_ncu_me_kernel.csv, r1_ncu_tq_kernel.csv)
-ME_TRAFFIC_BYTES_PER_LANE = (41.836032e6 + 0.075008e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
+ME_TRAFFIC_BYTES_PER_LANE = (41.837056e6 + 0.160256e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
 TQ_TRAFFIC_BYTES_PER_LANE = (43.469568e6 + 3.402240e6) / 10
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
