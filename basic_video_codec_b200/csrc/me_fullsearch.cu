@@ -94,6 +94,7 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
                                         int mbase, const uint32_t* utab_m, int mlo, int mhi, int mvy0, int sc, uint32_t tthr,
                                         uint32_t one, const KeyCfg kc, uint32_t& best, uint32_t& bestm, uint16_t* smap, int n1) {
     constexpr int WPR = BS / 4;
+    uint32_t pend = 0xFFFFFFFFu;
 #pragma unroll
     for (int t = 0; t < BS; t++) {
         uint32_t w[WPR];
@@ -120,7 +121,12 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
             const int slot = (t + 1) & (BS - 1);
             if (PACKED) {
                 const uint32_t u = utab_m[t];   // utab_m = utab + mbase (per thread)
-                best = min(best, imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr)));
+                const uint32_t key = imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr));
+                // two finished candidates per ALU-pipe instruction (VIMNMX3): the steady and ramp-down bodies finish one
+                // candidate per row, so even rows park their key and odd rows fold both into the running minimum
+                if (MODE == BODY_FIRST) best = min(best, key);
+                else if ((t & 1) == 0) pend = key;
+                else best = __vimin3_u32(best, pend, key);
                 if (SADMAP && !(u >> 31)) smap[(mbase + t) * n1] = (uint16_t)acc[slot];
             } else {
                 const int m = mbase + t;
