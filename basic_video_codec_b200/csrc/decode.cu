@@ -301,7 +301,7 @@ __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lan
     for (int v = 0; v < BS; v++) {
         const bool sv = (v == 0) || (2 * v == BS);
         const double w = sv ? w_sp : w_nm;
-        const int s = qp + min(max(u + v - (BS - 2), 0), 2);
+        const int s = qp + __vimin_s32_relu(u + v - (BS - 2), 2);
         const short lv = t.lev[q][u][v];
         if (levels && valid) levels[(size_t)u * lev_pitch + v] = lv;
         const double wq = __hiloint2double(__double2hiint(w) + (s << 20), __double2loint(w));
@@ -327,7 +327,7 @@ __device__ __forceinline__ void dequant_idct_recon_warp(WarpTile<BS>& t, int lan
         for (int i = 0; i < BS; i++) {
             const int pb = (int)((pw[i >> 2] >> (8 * (i & 3))) & 255u);
             const int v = (int)(short)(int)rint(__dadd_rn(r[i], (double)pb));
-            const uint32_t c8 = (uint32_t)min(max(v, 0), 255);
+            const uint32_t c8 = (uint32_t)__vimin_s32_relu(v, 255);
             if ((i & 3) == 0) ow[i >> 2] = c8; else ow[i >> 2] |= c8 << (8 * (i & 3));
         }
         store_row_words<BS>(recon + (size_t)y * rec_pitch, ow);

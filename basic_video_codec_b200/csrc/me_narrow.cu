@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(NarrowCfg<BS, R>::THREADS, NarrowCfg<BS, R>::M
             }
             const int mvx = a.sc * dx + px;
             const uint32_t tthr = (uint32_t)abs(mvx) << KEY_MBITS;
-            uint32_t best = 0xFFFFFFFFu;
+            uint32_t best = 0xFFFFFFFFu, pend = 0xFFFFFFFFu;
             const int oy2 = (tp.by0 + yy) * BS;
 #pragma unroll
             for (int m = 0; m < NM; m++) {
@@ -275,7 +275,10 @@ __global__ void __launch_bounds__(NarrowCfg<BS, R>::THREADS, NarrowCfg<BS, R>::M
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u_plus_t) : "r"(one), "r"(u), "r"(tthr));
                 uint32_t key;
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(acc[m]), "r"(scale), "r"(u_plus_t));
-                best = min(best, key);
+                // two candidates per ALU-pipe instruction (VIMNMX3); NM = 2R + 1 is odd, the last one goes alone
+                if ((m & 1) == 0 && m + 1 < NM) pend = key;
+                else if (m & 1) best = __vimin3_u32(best, pend, key);
+                else best = min(best, key);
             }
             if (best < 0x80000000u) {
                 const uint32_t m = best & ((1u << KEY_MBITS) - 1u);

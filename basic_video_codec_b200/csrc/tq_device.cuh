@@ -212,7 +212,7 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
         if (DBG && o.coef_out && valid) o.coef_out[u * BS + v] = coef;
         // generate_quantization_matrix dct.py:21-32: shift s = qp + {0,1,2} for u+v <,=,> BS-1;
         // quantize_block :35-37 = round half to even of coef * 2^-s (exact scaling)
-        const int s = qp + min(max(u + v - (BS - 2), 0), 2);
+        const int s = qp + __vimin_s32_relu(u + v - (BS - 2), 2);
         int li;
         const double resc = quant_rescale(coef, 0x43380000 + (s << 20), li);
         lv[v] = (short)li;
@@ -262,7 +262,7 @@ __device__ __forceinline__ void tq_warp(WarpTile<BS>& t, int lane, bool valid, i
             int vi;
             rint_magic(__dadd_rn(r[i], int_to_double(pb)), vi);
             const int v = (int)(short)vi;
-            const uint32_t c8 = (uint32_t)min(max(v, 0), 255);
+            const uint32_t c8 = (uint32_t)__vimin_s32_relu(v, 255);
             if ((i & 3) == 0) ow[i >> 2] = c8; else ow[i >> 2] |= c8 << (8 * (i & 3));
             if (DBG && o.idct_out) o.idct_out[y * BS + i] = r[i];
             // PFrame.py:39,63: float64 idct residual stored into an int8 plane (C cast: truncate, wrap)
@@ -355,7 +355,7 @@ __device__ __forceinline__ void quad_f2(QuadTile<BS>& t, int q, int x, int qp) {
         const bool sv = (v == 0) || (2 * v == BS);
         const double w = sv ? w_sp : w_nm;
         const double coef = __dmul_rn(acc, w);
-        const int sh = qp + min(max(u + v - (BS - 2), 0), 2);
+        const int sh = qp + __vimin_s32_relu(u + v - (BS - 2), 2);
         int li;
         const double resc = quant_rescale(coef, 0x43380000 + (sh << 20), li);
         lv[k] = (short)li;
@@ -404,8 +404,8 @@ __device__ __forceinline__ void quad_i2(QuadTile<BS>& t, int q, int x) {
         int v0, v1;
         rint_magic(__dadd_rn(r0, int_to_double((int)t.pred[q][y][i0])), v0);
         rint_magic(__dadd_rn(r1, int_to_double((int)t.pred[q][y][BS - 1 - i0])), v1);
-        t.rec[q][y][i0] = (uint8_t)min(max((int)(short)v0, 0), 255);
-        t.rec[q][y][BS - 1 - i0] = (uint8_t)min(max((int)(short)v1, 0), 255);
+        t.rec[q][y][i0] = (uint8_t)__vimin_s32_relu((int)(short)v0, 255);
+        t.rec[q][y][BS - 1 - i0] = (uint8_t)__vimin_s32_relu((int)(short)v1, 255);
     }
 }
 #define BVC_QUAD_DISPATCH(fn, warp, ...)                     \
