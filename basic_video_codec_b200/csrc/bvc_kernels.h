@@ -125,6 +125,8 @@ struct TqArgs {
                                    // rate-control loop (Frame.get_rc_qp, Frame.py:168-188) launches one row at a time
     int quad;                      // I frames, BS >= 8: four warps per block pair (tq_iframe_quad_kernel) instead of one (2: always)
     int cta_cap;                   // P frames: at most this many CTAs, each looping over work units (0 = one CTA per unit)
+    uint32_t ux_magic, ux_shift;   // P frames: division by the work units per lane / by bw (filled in by launch_tq_pframe)
+    uint32_t bw_magic, bw_shift;
 };
 cudaError_t launch_tq_pframe(const TqArgs& a, int lanes, cudaStream_t st);
 // with_entropy = false: the wavefront only (levels stay in a.levels); launch_tq_ientropy codes them later, on any stream

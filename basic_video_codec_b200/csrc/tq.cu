@@ -15,6 +15,13 @@ namespace {
 
 constexpr int TQ_WARPS = 4;
 
+// q = (mulhi(x, magic) + x) >> shift == x / d for every x < 2^31 (fast_div in tq_device.cuh)
+static void fast_div_constants(uint32_t d, uint32_t& magic, uint32_t& shift) {
+    shift = 0;
+    while ((1u << shift) < d) shift++;
+    magic = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << shift) - d)) / d + 1);
+}
+
 template <int BS>
 struct TqCtaSmem {
     WarpTile<BS> w[TQ_WARPS];
@@ -28,25 +35,86 @@ struct TqCtaSmem {
 // frees until it has no CTA left to place -- an uncapped grid evicts the search 1:1.  Capped at about one search CTA's
 // registers per SM (3 CTAs), the transform (fp64 pipe / issue bound) runs beside one search CTA per SM (ALU pipe bound,
 // which alone still reaches 86 % of the two-CTA rate), so most of its time disappears under the search.
+template <int BS>
+__device__ __forceinline__ PTask pframe_task(const TqArgs& a, int u, int units_x, int warp, int q) {
+    constexpr int NBW = 32 / BS;
+    PTask k;
+    k.fl = (int)fast_div((uint32_t)u, a.ux_magic, a.ux_shift);
+    const int ux = u - k.fl * units_x;
+    const int blk_end = (a.row_begin + a.row_count) * a.bw;
+    const int b = a.row_begin * a.bw + (ux * TQ_WARPS + warp) * NBW + q;
+    k.valid = b < blk_end;
+    k.b = k.valid ? b : blk_end - 1;
+    const int by = (int)fast_div((uint32_t)k.b, a.bw_magic, a.bw_shift);
+    k.oy = by * BS;
+    k.ox = (k.b - by * a.bw) * BS;
+    return k;
+}
+
 template <int BS, bool DBG>
 __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, int units_x, int units) {
-    constexpr int NBW = 32 / BS;
+    static_assert(sizeof(EntScratch<BS>) <= sizeof(WarpTile<BS>::buf), "entropy scratch must fit the fp64 exchange buffer");
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     build_zigzag<BS>(sm.zz, threadIdx.x, blockDim.x);
     __syncthreads();
     WarpTile<BS>& t = sm.w[warp];
-    const int q = lane / BS;
-    const int blk_begin = a.row_begin * a.bw, blk_end = (a.row_begin + a.row_count) * a.bw;
+    EntScratch<BS>& es = *reinterpret_cast<EntScratch<BS>*>(&t.buf[0][0][0]);
+    const int q = lane / BS, x = lane % BS;
+    int u = blockIdx.x;
+    if (u >= units) return;
+    PTask k = pframe_task<BS>(a, u, units_x, warp, q);
+    PRows<BS> rows;
+    pframe_fetch_rows<BS>(a, k, x, a.mv[(size_t)k.fl * a.nblk + k.b], rows);
 #pragma unroll 1
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int fl = u / units_x, ux = u - fl * units_x;
-        const int b = blk_begin + (ux * TQ_WARPS + warp) * NBW + q;
-        const bool valid = b < blk_end;
-        const int bb = valid ? b : blk_end - 1;
-        tq_pframe_warp<BS, DBG>(a, fl, t, sm.zz, lane, bb, valid, a.mv[(size_t)fl * a.nblk + bb]);
-        __syncwarp();   // the tile is this warp's alone, but the next unit restages it
+    for (;;) {
+        {   // stage the rows fetched one task ago
+            uint32_t pw[BS / 4];
+#pragma unroll
+            for (int i = 0; i < BS / 4; i++) pw[i] = __funnelshift_r(rows.raw[i], rows.raw[i + 1], rows.sh);
+            stage_row<BS>(t, q, x, rows.cw, pw);
+        }
+        if (DBG && a.resid_nomc && k.valid) {
+            // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
+            const FrameLane& L = a.lanes[k.fl];
+            const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(k.oy + x) * a.ref_pitch + k.ox;
+            int8_t* d = a.resid_nomc + ((size_t)k.fl * a.H + k.oy + x) * a.W + k.ox;
+#pragma unroll
+            for (int i = 0; i < BS; i++) d[i] = (int8_t)((int)t.cur[q][x][i] - (int)r0[i]);
+        }
+        __syncwarp();
+        {
+            TqOut o;
+            o.levels = a.levels ? a.levels + ((size_t)k.fl * a.H + k.oy) * a.W + k.ox : nullptr;
+            o.lev_pitch = a.W;
+            o.recon = a.ref_base + (size_t)a.lanes[k.fl].out_plane * a.ref_plane_bytes + (size_t)k.oy * a.ref_pitch + k.ox;
+            o.rec_pitch = a.ref_pitch;
+            o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)k.fl * a.H + k.oy) * a.W + k.ox : nullptr;
+            o.resid_pitch = a.W;
+            o.idct_out = nullptr;
+            o.coef_out = nullptr;
+            const int qp = a.qp_rows[(size_t)k.fl * a.bh + k.oy / BS];
+            tq_warp<BS, DBG>(t, lane, k.valid, qp, o, nullptr, nullptr, false);
+        }
+        // next task: its motion vector travels behind the event pass, its pixel rows behind the coding pass
+        const int u2 = u + gridDim.x;
+        const bool more = u2 < units;
+        PTask k2 = k;
+        int4 mv2 = make_int4(0, 0, 0, 0);
+        if (more) {
+            k2 = pframe_task<BS>(a, u2, units_x, warp, q);
+            mv2 = ldg_int4_keep(a.mv + (size_t)k2.fl * a.nblk + k2.b);
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, k.valid);
+        const int E = entropy_tile_events<BS>(t, es, sm.zz, lane, vmask);
+        if (more) pframe_fetch_rows<BS>(a, k2, x, mv2, rows);
+        entropy_tile_code<BS>(es, E, lane);
+        const size_t bi = (size_t)k.fl * a.nblk + k.b;
+        entropy_tile_store<BS>(es, lane, k.valid, a.blk_bits + bi * a.blk_words, a.blk_nbits + bi);
+        if (!more) break;
+        k = k2;
+        u = u2;
     }
 }
 
@@ -359,7 +427,10 @@ cudaError_t launch_pd(const TqArgs& a, int lanes, cudaStream_t st) {
     const int nb = a.row_count * a.bw;
     const int units_x = (nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), units = units_x * lanes;
     const int grid = a.cta_cap > 0 ? std::min(units, a.cta_cap) : units;
-    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(a, units_x, units);
+    TqArgs b = a;
+    fast_div_constants((uint32_t)units_x, b.ux_magic, b.ux_shift);
+    fast_div_constants((uint32_t)a.bw, b.bw_magic, b.bw_shift);
+    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(b, units_x, units);
     return cudaGetLastError();
 }
 template <int BS>

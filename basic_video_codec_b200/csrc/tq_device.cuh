@@ -595,66 +595,195 @@ __device__ __forceinline__ int entropy_block_warp(const int16_t* lev, const uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// One warp task of the P-frame path: NBW blocks (lane -> block `b` of lane group `fl`, motion vector `mv`; lanes of
-// the same block pass the same values; !valid lanes pass any in-range block and produce nothing).  Stages current and
-// predicted pixels, forms the residual, transforms / quantises / reconstructs and entropy-codes the blocks
-// (PFrame.process_block PFrame.py:99-125,230-249; Frame.py:61-75,190-202).
-template <int BS, bool DBG = true>
-__device__ __forceinline__ void tq_pframe_warp(const TqArgs& a, int fl, WarpTile<BS>& t, const uint8_t* zz, int lane, int b, bool valid,
-                                               int4 mv) {
-    constexpr int NBW = 32 / BS;
-    const FrameLane& L = a.lanes[fl];
+// Entropy coding of ALL blocks of a warp tile in one go (P-frame path).  entropy_block_warp above walks one block at a
+// time: its dependent chain (ballots -> event selection -> scan -> shared-memory atomics -> copy) is paid per block and
+// the end-of-block marker is a divergent extra.  Here the emitting positions ("events": run starts and non-zero values,
+// scan order) of every block of the tile are first compacted into ONE list -- each block closed by a terminator event
+// that carries the end-of-block marker and, being a run start at position N, also ends the block's last run -- and then
+// lane j codes event j: a tile of sparse blocks (two 16x16 blocks with <= 30 events in all, the usual case after
+// quantisation) takes a single pass, the bit offsets restart at every terminator (segmented scan), and the copy to the
+// per-block bit strings runs for all blocks at once (lane group q = block q).
+// The scratch lives in the tile's fp64 exchange buffer, which is idle while the levels are coded.
+constexpr uint32_t EV_NZ = 1u << 12, EV_ST = 1u << 13, EV_EOB = 1u << 14;   // bits 0-8 position, 9-11 block, 16-31 level
+template <int BS>
+struct EntScratch {
+    static constexpr int NBW = 32 / BS, N = BS * BS, WCAP = blk_words_for<BS>() + 4;
+    uint32_t bits[NBW][WCAP];
+    uint32_t ev[NBW * (N + 1)];
+    int nbits[NBW];
+};
+
+// Phase A: event list of the tile's valid blocks (vmask = ballot of the lanes' `valid`), bit strings zeroed.
+// Returns the number of events (warp-uniform).
+template <int BS>
+__device__ __forceinline__ int entropy_tile_events(const WarpTile<BS>& t, EntScratch<BS>& es, const uint8_t* zz, int lane, uint32_t vmask) {
+    constexpr int NBW = 32 / BS, N = BS * BS;
+    constexpr int NI = N >= 32 ? N / 32 : 1;
+    constexpr int AL = N >= 32 ? 32 : N;
+    constexpr uint32_t ALMASK = AL == 32 ? 0xffffffffu : ((1u << AL) - 1u);
+    const bool act = lane < AL;
+    const uint32_t lt = (1u << lane) - 1u;
+    int zp[NI];   // this lane's zig-zag positions: the same for every block and every tile
+#pragma unroll
+    for (int i = 0; i < NI; i++) zp[i] = act ? (int)zz[i * AL + lane] : 0;
+    int E = 0;
+#pragma unroll 1
+    for (int q = 0; q < NBW; q++) {
+        if (!((vmask >> (q * BS)) & 1u)) continue;
+        const int16_t* lev = &t.lev[q][0][0];
+        uint32_t top = 0;
+        int nnz = 0;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int c = act ? (int)lev[zp[i]] : 0;
+            const uint32_t M = __ballot_sync(0xffffffffu, c != 0);
+            // a run starts where the non-zero state flips; position 0 always starts one
+            const uint32_t carry = (i == 0) ? ((~M) & 1u) : top;
+            const uint32_t S = (M ^ ((M << 1) | carry)) & ALMASK;
+            const uint32_t EV = S | M;
+            if ((EV >> lane) & 1u)
+                es.ev[E + __popc(EV & lt)] = ((uint32_t)c << 16) | (uint32_t)(i * AL + lane) | ((uint32_t)q << 9) |
+                                             (((M >> lane) & 1u) ? EV_NZ : 0u) | (((S >> lane) & 1u) ? EV_ST : 0u);
+            E += __popc(EV);
+            nnz += __popc(M);
+            top = (M >> (AL - 1)) & 1u;
+        }
+        if (lane == 0) es.ev[E] = (uint32_t)N | ((uint32_t)q << 9) | EV_ST | EV_EOB;
+        E++;
+        // zero what the block can need: <= 31 bits per value, <= 19 per run header, <= 2*nnz+1 runs, 27 for the end marker
+        const int wmax = min(EntScratch<BS>::WCAP, ((69 * nnz + 46 + 31) >> 5) + 2);
+        for (int w = lane; w < wmax; w += 32) es.bits[q][w] = 0;
+    }
+    __syncwarp();
+    return E;
+}
+
+// Phase B: lane j codes event j (32 events per pass); Frame.py:61-75, entropy_encoder.py:8-29,65-88.
+template <int BS>
+__device__ __forceinline__ void entropy_tile_code(EntScratch<BS>& es, int E, int lane) {
+    constexpr int N = BS * BS;
+    const uint32_t lt = (1u << lane) - 1u;
+    int carry_bits = 0;   // bits already written for the block that is open at the start of the pass
+#pragma unroll 1
+    for (int base = 0; base < E; base += 32) {
+        const uint32_t w = (base + lane < E) ? es.ev[base + lane] : 0u;
+        const int p = (int)(w & 511u), q = (int)((w >> 9) & 7u);
+        const bool isnz = w & EV_NZ, st = w & EV_ST, eob = w & EV_EOB;
+        // a run ends where the next one starts (the terminator is a start at position N)
+        const uint32_t later = __ballot_sync(0xffffffffu, st) & ~((2u << lane) - 1u);
+        int pn = __shfl_sync(0xffffffffu, p, later ? __ffs(later) - 1 : 0);
+        if (st && !eob && !later) {   // dense tiles only: the next start lies in a later pass
+            int k = base + 32;
+            while (!(es.ev[k] & EV_ST)) k++;
+            pn = (int)(es.ev[k] & 511u);
+        }
+        unsigned long long cd = 0;
+        int ln = 0;
+        if (eob) {
+            cd = eg_code(BVC_EOB_MARKER);   // Frame.py:75
+            ln = 27;
+        } else if (st) {
+            const int runlen = pn - p;
+            const uint32_t e = eg_code(isnz ? -runlen : (pn == N ? 0 : runlen));
+            ln = eg_len_of_code(e);
+            cd = e;
+        }
+        if (isnz) {
+            const uint32_t e = eg_code((int)w >> 16);
+            const int l2 = eg_len_of_code(e);
+            cd = (cd << l2) | e;
+            ln += l2;
+        }
+        int incl = ln;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        // bit offsets restart after every terminator
+        const uint32_t eobb = __ballot_sync(0xffffffffu, eob);
+        const uint32_t prior = eobb & lt;
+        const int corr = __shfl_sync(0xffffffffu, incl, prior ? 31 - __clz(prior) : 0);
+        const int off = prior ? (incl - ln - corr) : (carry_bits + incl - ln);
+        if (ln) put_bits_smem(es.bits[q], off, cd, ln);
+        if (eob) es.nbits[q] = off + 27;
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        const int last = __shfl_sync(0xffffffffu, incl, eobb ? 31 - __clz(eobb) : 0);
+        carry_bits = eobb ? tot - last : carry_bits + tot;
+    }
+    __syncwarp();
+}
+
+// Phase C: every lane group copies its block's bit string (lane = (q, x)); `gout` / `nbits_out` belong to the lane's block.
+template <int BS>
+__device__ __forceinline__ void entropy_tile_store(const EntScratch<BS>& es, int lane, bool valid, uint32_t* gout, int32_t* nbits_out) {
     const int q = lane / BS, x = lane % BS;
-    const int bx = b % a.bw, by = b / a.bw;
-    const int ox = bx * BS, oy = by * BS;
-    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(oy + x) * a.cur_pitch + ox;
-    // find_mv_predicted_block PFrame.py:230-244: refs[mv[2]] only when more than one reference is present
-    const int k = (L.nref > 1) ? mv.z : 0;
-    int plane = L.ref_plane[k];
+    const int nb = valid ? es.nbits[q] : 0;
+    const int nwords = (nb + 31) >> 5;
+    for (int w = x; w < nwords; w += BS) gout[w] = es.bits[q][w];
+    if (valid && x == 0) *nbits_out = nb;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// P-frame path, one warp task = NBW blocks (lane -> block `b` of lane group `fl`; lanes of one block hold the same values;
+// !valid lanes name any in-range block and produce nothing): PFrame.process_block PFrame.py:99-125,230-249;
+// Frame.py:61-75,190-202.  The task's pixel rows are fetched into registers one task ahead (PRows), behind the entropy
+// coding of the task before, so the two dependent global round trips (motion vector -> predicted row) are off the
+// critical path.
+// Division by a launch constant (x < 2^31): q = (mulhi(x, magic) + x) >> shift.
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic, uint32_t shift) { return (__umulhi(x, magic) + x) >> shift; }
+
+template <int BS>
+struct PRows {
+    uint32_t cw[BS / 4];       // current row
+    uint32_t raw[BS / 4 + 1];  // aligned words covering the predicted row
+    uint32_t sh;               // its byte offset in raw[0], times 8
+};
+struct PTask {
+    int fl, b, oy, ox;   // lane group, block, block origin
+    bool valid;
+};
+
+// Loads that stay where they are issued (asm volatile): the rows of the NEXT task are requested ahead of the entropy phase
+// of the current one and consumed after it.
+__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int BS>
+__device__ __forceinline__ void ldg_row_keep(const uint8_t* p, uint32_t (&w)[BS / 4]) {
+    if constexpr (BS == 16) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+    else if constexpr (BS == 8) asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    else asm volatile("ld.global.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+}
+__device__ __forceinline__ int4 ldg_int4_keep(const int4* p) {
+    int4 v;
+    asm volatile("ld.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// find_mv_predicted_block PFrame.py:230-244 (refs[mv[2]] only when more than one reference is present) + the current row
+template <int BS>
+__device__ __forceinline__ void pframe_fetch_rows(const TqArgs& a, const PTask& k, int x, int4 mv, PRows<BS>& r) {
+    const FrameLane& L = a.lanes[k.fl];
+    const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(k.oy + x) * a.cur_pitch + k.ox;
+    const int kref = (L.nref > 1) ? mv.z : 0;
+    int plane = L.ref_plane[kref];
     int dx = mv.x, dy = mv.y;
     if (a.frac) {  // half-pel MV = integer offset on one of the four phase planes
         plane += (mv.x & 1) | ((mv.y & 1) << 1);
         dx = mv.x >> 1;
         dy = mv.y >> 1;
     }
-    const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(oy + dy + x) * a.ref_pitch + (ox + dx);
-    {
-        uint32_t cw[BS / 4], pw[BS / 4];
-        load_row_aligned<BS>(cur, cw);
-        load_row_unaligned<BS>(pr, pw);
-        stage_row<BS>(t, q, x, cw, pw);
-    }
-    if (DBG && a.resid_nomc && valid) {
-        // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
-        const uint8_t* r0 = a.ref_base + (size_t)L.ref_plane[0] * a.ref_plane_bytes + (size_t)(oy + x) * a.ref_pitch + ox;
-        int8_t* d = a.resid_nomc + ((size_t)fl * a.H + oy + x) * a.W + ox;
+    const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(k.oy + dy + x) * a.ref_pitch + (k.ox + dx);
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(pr);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+    r.sh = (uint32_t)(ad & 3) * 8;
+    ldg_row_keep<BS>(cur, r.cw);
 #pragma unroll
-        for (int i = 0; i < BS; i++) d[i] = (int8_t)((int)cur[i] - (int)r0[i]);
-    }
-    __syncwarp();
-
-    TqOut o;
-    o.levels = a.levels ? a.levels + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
-    o.lev_pitch = a.W;
-    o.recon = a.ref_base + (size_t)L.out_plane * a.ref_plane_bytes + (size_t)oy * a.ref_pitch + ox;
-    o.rec_pitch = a.ref_pitch;
-    o.resid_mc = a.resid_mc ? a.resid_mc + ((size_t)fl * a.H + oy) * a.W + ox : nullptr;
-    o.resid_pitch = a.W;
-    o.idct_out = nullptr;
-    o.coef_out = nullptr;
-    const int qp = a.qp_rows[(size_t)fl * a.bh + by];
-    tq_warp<BS, DBG>(t, lane, valid, qp, o, nullptr, nullptr, false);
-
-    // entropy-code the warp's blocks one after the other
-#pragma unroll 1
-    for (int qq = 0; qq < NBW; qq++) {
-        const int b2 = __shfl_sync(0xffffffffu, b, qq * BS);
-        const int v2 = __shfl_sync(0xffffffffu, (int)valid, qq * BS);
-        if (!v2) continue;
-        uint32_t* gout = a.blk_bits + ((size_t)fl * a.nblk + b2) * a.blk_words;
-        const int nb = entropy_block_warp<BS>(&t.lev[qq][0][0], zz, t.bits, lane, gout);
-        if (lane == 0) a.blk_nbits[(size_t)fl * a.nblk + b2] = nb;
-    }
+    for (int i = 0; i <= BS / 4; i++) r.raw[i] = ldg_keep(base + i);
 }
 
 }  // namespace bvc
