@@ -35,14 +35,15 @@ struct TqCtaSmem {
 // frees until it has no CTA left to place -- an uncapped grid evicts the search 1:1.  Capped at about one search CTA's
 // registers per SM (3 CTAs), the transform (fp64 pipe / issue bound) runs beside one search CTA per SM (ALU pipe bound,
 // which alone still reaches 86 % of the two-CTA rate), so most of its time disappears under the search.
+// Warp task wt of a launch: lane group fl = wt / tasks_per_lane, blocks (wt % tasks_per_lane) * NBW + q of the launch's rows.
 template <int BS>
-__device__ __forceinline__ PTask pframe_task(const TqArgs& a, int u, int units_x, int warp, int q) {
+__device__ __forceinline__ PTask pframe_task(const TqArgs& a, int wt, int tasks_per_lane, int q) {
     constexpr int NBW = 32 / BS;
     PTask k;
-    k.fl = (int)fast_div((uint32_t)u, a.ux_magic, a.ux_shift);
-    const int ux = u - k.fl * units_x;
+    k.fl = (int)fast_div((uint32_t)wt, a.ux_magic, a.ux_shift);
+    const int rem = wt - k.fl * tasks_per_lane;
     const int blk_end = (a.row_begin + a.row_count) * a.bw;
-    const int b = a.row_begin * a.bw + (ux * TQ_WARPS + warp) * NBW + q;
+    const int b = a.row_begin * a.bw + rem * NBW + q;
     k.valid = b < blk_end;
     k.b = k.valid ? b : blk_end - 1;
     const int by = (int)fast_div((uint32_t)k.b, a.bw_magic, a.bw_shift);
@@ -51,8 +52,13 @@ __device__ __forceinline__ PTask pframe_task(const TqArgs& a, int u, int units_x
     return k;
 }
 
+// Persistent grid (at most the resident CTAs of the GPU): every warp walks warp tasks on its own -- no CTA barrier after
+// the zig-zag table -- the first one from its position in the grid, the following ones from a ticket counter (a.ticket, left
+// at zero again by the warp that draws the last ticket), so the launch balances itself whatever the other kernels on the
+// GPU do.  The ticket is drawn before the transform and read after it; the next task's motion vector is requested before
+// the event pass of the entropy coder and its pixel rows before the coding pass, so no global round trip is exposed.
 template <int BS, bool DBG>
-__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, int units_x, int units) {
+__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, int tasks_per_lane, int ntasks) {
     static_assert(sizeof(EntScratch<BS>) <= sizeof(WarpTile<BS>::buf), "entropy scratch must fit the fp64 exchange buffer");
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);
@@ -62,13 +68,16 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
     WarpTile<BS>& t = sm.w[warp];
     EntScratch<BS>& es = *reinterpret_cast<EntScratch<BS>*>(&t.buf[0][0][0]);
     const int q = lane / BS, x = lane % BS;
-    int u = blockIdx.x;
-    if (u >= units) return;
-    PTask k = pframe_task<BS>(a, u, units_x, warp, q);
+    const int nwarps = (int)gridDim.x * TQ_WARPS;
+    int wt = (int)blockIdx.x * TQ_WARPS + warp;
+    if (wt >= ntasks) return;
+    PTask k = pframe_task<BS>(a, wt, tasks_per_lane, q);
     PRows<BS> rows;
     pframe_fetch_rows<BS>(a, k, x, a.mv[(size_t)k.fl * a.nblk + k.b], rows);
 #pragma unroll 1
     for (;;) {
+        int tk = 0;
+        if (lane == 0) tk = atomicAdd(a.ticket, 1);
         {   // stage the rows fetched one task ago
             uint32_t pw[BS / 4];
 #pragma unroll
@@ -97,13 +106,14 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
             const int qp = a.qp_rows[(size_t)k.fl * a.bh + k.oy / BS];
             tq_warp<BS, DBG>(t, lane, k.valid, qp, o, nullptr, nullptr, false);
         }
-        // next task: its motion vector travels behind the event pass, its pixel rows behind the coding pass
-        const int u2 = u + gridDim.x;
-        const bool more = u2 < units;
+        // tickets 0 .. ntasks-1 are drawn in all (ntasks - nwarps good ones, one bad one per warp): the last puts the counter back
+        if (lane == 0 && tk == ntasks - 1) atomicExch(a.ticket, 0);
+        const int wt2 = nwarps + __shfl_sync(0xffffffffu, tk, 0);
+        const bool more = wt2 < ntasks;
         PTask k2 = k;
         int4 mv2 = make_int4(0, 0, 0, 0);
         if (more) {
-            k2 = pframe_task<BS>(a, u2, units_x, warp, q);
+            k2 = pframe_task<BS>(a, wt2, tasks_per_lane, q);
             mv2 = ldg_int4_keep(a.mv + (size_t)k2.fl * a.nblk + k2.b);
         }
         const uint32_t vmask = __ballot_sync(0xffffffffu, k.valid);
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
         entropy_tile_store<BS>(es, lane, k.valid, a.blk_bits + bi * a.blk_words, a.blk_nbits + bi);
         if (!more) break;
         k = k2;
-        u = u2;
+        wt = wt2;
     }
 }
 
@@ -426,11 +436,24 @@ cudaError_t launch_pd(const TqArgs& a, int lanes, cudaStream_t st) {
     }
     const int nb = a.row_count * a.bw;
     const int units_x = (nb + TQ_WARPS * NBW - 1) / (TQ_WARPS * NBW), units = units_x * lanes;
-    const int grid = a.cta_cap > 0 ? std::min(units, a.cta_cap) : units;
+    // persistent grid: the CTAs that can be resident at once (6 per SM), each warp drawing tasks until none is left
+    static int slots_dev[BVC_MAX_DEVICES] = {};
+    int& slots = slots_dev[current_device_slot()];
+    if (slots == 0) {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tq_pframe_kernel<BS, DBG>, TQ_WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        slots = per_sm * sms;
+    }
+    if (!a.ticket) return cudaErrorInvalidValue;   // the task counter (zero between launches)
+    int grid = std::min(units, slots);
+    if (a.cta_cap > 0) grid = std::min(grid, a.cta_cap);
     TqArgs b = a;
-    fast_div_constants((uint32_t)units_x, b.ux_magic, b.ux_shift);
+    const int tasks_per_lane = units_x * TQ_WARPS;
+    fast_div_constants((uint32_t)tasks_per_lane, b.ux_magic, b.ux_shift);
     fast_div_constants((uint32_t)a.bw, b.bw_magic, b.bw_shift);
-    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(b, units_x, units);
+    tq_pframe_kernel<BS, DBG><<<grid, TQ_WARPS * 32, smem, st>>>(b, tasks_per_lane, units * TQ_WARPS);
     return cudaGetLastError();
 }
 template <int BS>
