@@ -72,18 +72,12 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
     int wt = (int)blockIdx.x * TQ_WARPS + warp;
     if (wt >= ntasks) return;
     PTask k = pframe_task<BS>(a, wt, tasks_per_lane, q);
-    PRows<BS> rows;
-    pframe_fetch_rows<BS>(a, k, x, a.mv[(size_t)k.fl * a.nblk + k.b], rows);
+    uint32_t sh = pframe_request_rows<BS>(a, t, k, q, x, a.mv[(size_t)k.fl * a.nblk + k.b]);
 #pragma unroll 1
     for (;;) {
         int tk = 0;
-        if (lane == 0) tk = atomicAdd(a.ticket, 1);
-        {   // stage the rows fetched one task ago
-            uint32_t pw[BS / 4];
-#pragma unroll
-            for (int i = 0; i < BS / 4; i++) pw[i] = __funnelshift_r(rows.raw[i], rows.raw[i + 1], rows.sh);
-            stage_row<BS>(t, q, x, rows.cw, pw);
-        }
+        if (lane == 0) tk = ticket_draw(a.ticket);
+        pframe_stage_rows<BS>(t, q, x, sh);
         if (DBG && a.resid_nomc && k.valid) {
             // PFrame.py:40,64,103,116: int16(cur) - int16(refs[0]) stored into an int8 plane
             const FrameLane& L = a.lanes[k.fl];
@@ -114,11 +108,11 @@ __global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, i
         int4 mv2 = make_int4(0, 0, 0, 0);
         if (more) {
             k2 = pframe_task<BS>(a, wt2, tasks_per_lane, q);
-            mv2 = ldg_int4_keep(a.mv + (size_t)k2.fl * a.nblk + k2.b);
+            mv2 = ldg_mv_keep(a.mv + (size_t)k2.fl * a.nblk + k2.b);
         }
         const uint32_t vmask = __ballot_sync(0xffffffffu, k.valid);
         const int E = entropy_tile_events<BS>(t, es, sm.zz, lane, vmask);
-        if (more) pframe_fetch_rows<BS>(a, k2, x, mv2, rows);
+        if (more) sh = pframe_request_rows<BS>(a, t, k2, q, x, mv2);
         entropy_tile_code<BS>(es, E, lane);
         const size_t bi = (size_t)k.fl * a.nblk + k.b;
         entropy_tile_store<BS>(es, lane, k.valid, a.blk_bits + bi * a.blk_words, a.blk_nbits + bi);

@@ -734,39 +734,46 @@ __device__ __forceinline__ void entropy_tile_store(const EntScratch<BS>& es, int
 // Division by a launch constant (x < 2^31): q = (mulhi(x, magic) + x) >> shift.
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic, uint32_t shift) { return (__umulhi(x, magic) + x) >> shift; }
 
-template <int BS>
-struct PRows {
-    uint32_t cw[BS / 4];       // current row
-    uint32_t raw[BS / 4 + 1];  // aligned words covering the predicted row
-    uint32_t sh;               // its byte offset in raw[0], times 8
-};
 struct PTask {
     int fl, b, oy, ox;   // lane group, block, block origin
     bool valid;
 };
 
-// Loads that stay where they are issued (asm volatile): the rows of the NEXT task are requested ahead of the entropy phase
-// of the current one and consumed after it.
-__device__ __forceinline__ uint32_t ldg_keep(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+// Asynchronous global -> shared copies (LDGSTS): the rows of the NEXT task travel into tile regions that are idle while
+// the current task's levels are coded, without occupying registers or a scoreboard.
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 template <int BS>
-__device__ __forceinline__ void ldg_row_keep(const uint8_t* p, uint32_t (&w)[BS / 4]) {
-    if constexpr (BS == 16) asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
-    else if constexpr (BS == 8) asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
-    else asm volatile("ld.global.u32 %0, [%1];" : "=r"(w[0]) : "l"(p));
+__device__ __forceinline__ void cp_async_row(void* dst, const void* src) {   // BS bytes, BS-byte aligned
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    if constexpr (BS == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else if constexpr (BS == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
-__device__ __forceinline__ int4 ldg_int4_keep(const int4* p) {
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// motion vector without its fourth component (the SAD): a destination register nobody reads would be reused at once and
+// the write-after-write hazard would stall the warp until the load lands
+__device__ __forceinline__ int4 ldg_mv_keep(const int4* p) {
     int4 v;
-    asm volatile("ld.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    asm volatile("ld.global.s32 %0, [%1+8];" : "=r"(v.z) : "l"(p));
+    v.w = 0;
+    return v;
+}
+// one ticket of the task counter; asm so that the compiler neither aggregates it across the warp nor waits for it early
+__device__ __forceinline__ int ticket_draw(int* counter) {
+    int v;
+    asm volatile("atom.global.add.s32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
     return v;
 }
 
-// find_mv_predicted_block PFrame.py:230-244 (refs[mv[2]] only when more than one reference is present) + the current row
+// Request the pixel rows of task k (lane x = row x of its block): the current row goes straight to t.cur[q][x], the aligned
+// words covering the predicted row (find_mv_predicted_block PFrame.py:230-244: refs[mv[2]] only when more than one
+// reference is present) to the lane's own slot in t.res, where pframe_stage_rows picks them up.  Returns the predicted
+// row's byte offset inside the slot.
 template <int BS>
-__device__ __forceinline__ void pframe_fetch_rows(const TqArgs& a, const PTask& k, int x, int4 mv, PRows<BS>& r) {
+__device__ __forceinline__ uint32_t pframe_request_rows(const TqArgs& a, WarpTile<BS>& t, const PTask& k, int q, int x, int4 mv) {
     const FrameLane& L = a.lanes[k.fl];
     const uint8_t* cur = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes + (size_t)(k.oy + x) * a.cur_pitch + k.ox;
     const int kref = (L.nref > 1) ? mv.z : 0;
@@ -778,12 +785,31 @@ __device__ __forceinline__ void pframe_fetch_rows(const TqArgs& a, const PTask& 
         dy = mv.y >> 1;
     }
     const uint8_t* pr = a.ref_base + (size_t)plane * a.ref_plane_bytes + (size_t)(k.oy + dy + x) * a.ref_pitch + (k.ox + dx);
+    // the BS predicted bytes lie in at most two aligned BS-byte chunks of the reference row: two wide copies into the lane's
+    // 2*BS-byte slot instead of BS/4+1 narrow ones (the second chunk is skipped when the row is aligned: it could lie
+    // beyond the pool)
     const uintptr_t ad = reinterpret_cast<uintptr_t>(pr);
-    const uint32_t* base = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
-    r.sh = (uint32_t)(ad & 3) * 8;
-    ldg_row_keep<BS>(cur, r.cw);
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(ad & ~(uintptr_t)(BS - 1));
+    cp_async_row<BS>(&t.cur[q][x][0], cur);
+    uint8_t* slot = reinterpret_cast<uint8_t*>(&t.res[q][x][0]);
+    cp_async_row<BS>(slot, base);
+    if (ad & (BS - 1)) cp_async_row<BS>(slot + BS, base + BS);
+    return (uint32_t)(ad & (BS - 1));
+}
+// ... and turn them into the staged tile rows (cur, pred, residual) once they have arrived
+template <int BS>
+__device__ __forceinline__ void pframe_stage_rows(WarpTile<BS>& t, int q, int x, uint32_t off) {   // off = byte offset of the row in its slot
+    cp_async_wait_all();
+    uint32_t cw[BS / 4], raw[BS / 4 + 1], pw[BS / 4];
+    load_row_aligned<BS>(&t.cur[q][x][0], cw);
+    const uint32_t* rp = reinterpret_cast<const uint32_t*>(&t.res[q][x][0]) + (off >> 2);
+    const uint32_t sh = (off & 3u) * 8u;
 #pragma unroll
-    for (int i = 0; i <= BS / 4; i++) r.raw[i] = ldg_keep(base + i);
+    for (int i = 0; i < BS / 4; i++) raw[i] = rp[i];
+    raw[BS / 4] = sh ? rp[BS / 4] : 0u;   // an aligned row ends with its last word (the slot may end there too)
+#pragma unroll
+    for (int i = 0; i < BS / 4; i++) pw[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+    stage_row<BS>(t, q, x, cw, pw);
 }
 
 }  // namespace bvc
