@@ -69,6 +69,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+// the same, pinned in program order relative to volatile loads (software-pipelined search bodies)
+__device__ __forceinline__ uint32_t sad4_keep(uint32_t a, uint32_t b, uint32_t acc) {
+    uint32_t d;
+    asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

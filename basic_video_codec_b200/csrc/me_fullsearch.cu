@@ -89,19 +89,32 @@ __device__ __forceinline__ uint32_t imad_u32(uint32_t a, uint32_t b, uint32_t c)
 //            (FMA pipe) and ONE ALU-pipe instruction (VIMNMX); no compare, select or branch.
 //   general: per-thread arithmetic (used only when SAD | L1 | m does not fit 31 bits).
 //   SADMAP : additionally store the SAD of every in-range candidate to smap[m * n1] (FastME's look-up table).
-template <int BS, int MODE, bool PACKED, bool SADMAP>
+template <int BS, int MODE, bool PACKED, bool SADMAP, bool PIPE>
 __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)[BS], const uint32_t* rowp, int wpitch,
                                         int mbase, const uint32_t* utab_m, int mlo, int mhi, int mvy0, int sc, uint32_t tthr,
                                         uint32_t one, const KeyCfg kc, uint32_t& best, uint32_t& bestm, uint16_t* smap, int n1) {
     constexpr int WPR = BS / 4;
     uint32_t pend = 0xFFFFFFFFu;
+    // Window words are requested one word ahead of their use (PIPE, constant pitch only): volatile loads and volatile
+    // VABSDIFF4s keep the interleaving written here, so a warp meets the shared-memory latency once per body instead of
+    // once per word (left to itself ptxas sinks every LDS to just in front of its first use).
+    const volatile uint32_t* vrow = rowp;
+    uint32_t wcur = 0;
+    if (PIPE) wcur = vrow[0];
 #pragma unroll
     for (int t = 0; t < BS; t++) {
         uint32_t w[WPR];
+        if (!PIPE) {
 #pragma unroll
-        for (int j = 0; j < WPR; j++) w[j] = rowp[t * wpitch + j];
+            for (int j = 0; j < WPR; j++) w[j] = rowp[t * wpitch + j];
+        }
 #pragma unroll
         for (int wi = 0; wi < WPR; wi++) {
+            uint32_t wnext = 0;
+            if (PIPE) {
+                w[wi] = wcur;
+                if (!(t == BS - 1 && wi == WPR - 1)) wnext = vrow[(wi + 1 < WPR) ? (t * wpitch + wi + 1) : ((t + 1) * wpitch)];
+            }
 #pragma unroll
             for (int j = 0; j < BS; j++) {
                 // candidate offset m = y - j; FIRST body: m >= 0 <=> j <= t; LAST body: m <= 2R <=> j >= t
@@ -111,17 +124,20 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
                 if (on) {
                     const int slot = (t - j) & (BS - 1);
                     // first word of a fresh candidate (j == 0, wi == 0) starts from zero: no reset needed
-                    acc[slot] = sad4(w[wi], cur.w[j][wi], (j == 0 && wi == 0) ? 0u : acc[slot]);
+                    const uint32_t c0 = (j == 0 && wi == 0) ? 0u : acc[slot];
+                    acc[slot] = PIPE ? sad4_keep(w[wi], cur.w[j][wi], c0) : sad4(w[wi], cur.w[j][wi], c0);
                 }
             }
+            if (PIPE) wcur = wnext;
         }
         // the candidate whose last row (j = BS-1) was just added is complete
         const bool completes = (MODE != BODY_FIRST) || (t == BS - 1);
         if (completes) {
             const int slot = (t + 1) & (BS - 1);
             if (PACKED) {
+                // the thread's own |mvx| term is the same for all of its candidates: it joins the winner after the bodies
                 const uint32_t u = utab_m[t];   // utab_m = utab + mbase (per thread)
-                const uint32_t key = imad_u32(acc[slot], kc.scale, imad_u32(one, u, tthr));
+                const uint32_t key = imad_u32(acc[slot], kc.scale, u);
                 // two finished candidates per ALU-pipe instruction (VIMNMX3): the steady and ramp-down bodies finish one
                 // candidate per row, so even rows park their key and odd rows fold both into the running minimum
                 if (MODE == BODY_FIRST) best = min(best, key);
@@ -150,11 +166,15 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
 // WPC: window pitch in words when it is known at compile time (the headline shapes), 0 = read it from the arguments.
 // With a constant pitch every LDS of an unrolled body takes an immediate offset from one base register: no address
 // arithmetic (VIADD, ALU pipe) between the VABSDIFF4s.
+// Registers: 96 let two CTAs of up to 341 threads share an SM.  The two constant-pitch shapes run 256 threads, so two CTAs
+// fit at 128 registers: the spare ones are what lets ptxas keep the window loads a whole word ahead of their use (me_body,
+// PIPE); at 96 it sinks a quarter of them back to just in front of their first use.
 template <int BS, int NB, int NBY, bool PACKED, bool SADMAP, int WPC>
-__global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
+__global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constant__ CUtensorMap ref_map, MeArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ unsigned long long sbest[NBY][NB];
+    __shared__ int xjob;   // extra jobs handed out so far (all windows of the CTA)
     __shared__ uint32_t utab[NBY][2 * 128 + 1 + 2 * BS];   // per-pass candidate tables, indexed by m + BS
 
     const int tid = threadIdx.x;
@@ -192,27 +212,12 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     uint8_t* scur = smem + 4 * (size_t)copy_stride;   // [NBY*BS][NB*BS] current pixels of the CTA's blocks
 
     const int nmain = NB * 2 * R;
-    const int xbase = (nmain + 31) & ~31;     // first thread of the extra warps
     const int nseg = (2 * Rv + 1 + BS) / (BS + 1);
-    const bool is_extra = tid >= xbase;
-    int b, dx, m0 = 0, yye = 0;
-    bool active;
-    if (!is_extra) {
-        b = tid / (2 * R);
-        dx = tid - b * 2 * R - R;
-        active = tid < nmain;
-    } else {
-        const int e = tid - xbase;
-        yye = e / (NB * nseg);
-        const int e2 = e - yye * NB * nseg;
-        b = e2 / nseg;
-        const int seg = e2 - b * nseg;
-        dx = R;
-        m0 = min(seg * (BS + 1), 2 * Rv - BS);  // overlapping the previous segment is harmless for an argmin
-        active = yye >= yy0 && yye < yy1;
-    }
-    active = active && (bx0 + b < a.bw);
-    const int ox = (bx0 + b) * BS;
+    // Jobs of a warp: first its main job (one candidate column per thread, every block row of the CTA); then, as long as
+    // there are any left, "extra" jobs of 32 segments of the last columns, drawn from a shared-memory counter -- whichever
+    // warps finish their main job first take them, so no warp sits at the closing barrier while work is left.
+    const int nxjobs = (NB * NBY * nseg + 31) >> 5;
+    const int wlane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -223,6 +228,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
         tma_load_3d(smem, &ref_map, &bar, bx0 * BS - R - a.win_lm, wy0, L.ref_plane[r_begin]);
     }
     for (int i = tid; i < NB * NBY; i += blockDim.x) sbest[i / NB][i % NB] = ~0ull;
+    if (tid == 0) xjob = 0;
     {   // stage the current blocks (NB*BS x NBY*BS bytes) in shared memory, 16 B per thread-iteration
         const uint8_t* cp = a.cur_base + (size_t)L.cur_plane * a.cur_plane_bytes;
         constexpr int VPR = NB * BS / 16 > 0 ? NB * BS / 16 : 1;   // 16-byte vectors per row
@@ -239,10 +245,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    // this thread's window column (left edge of the candidate) and the aligned copy it reads
-    const int X = a.win_lm + b * BS + dx + R;
     const int wpitch = WPC ? WPC : (WW >> 2);
-    const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2);
 
     uint32_t one;
     asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque 1 so `one*u + t` stays an IMAD
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
     kc.scale = 1u << (a.key_mbits + a.key_l1bits);
 
     uint32_t parity = 0;
+    int win = 0;   // windows searched so far
     const int nmid = (2 * Rv) / BS - 1;
 
     for (int r = r_begin; r < r_end; r++) {
@@ -295,11 +299,36 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
             }
             __syncthreads();
 
+            // every warp draws until it misses once, so a window uses nwarps + nxjobs tickets, the first nxjobs of them good
+            const int xbeg = win * (((int)blockDim.x >> 5) + nxjobs), xend = xbeg + nxjobs;
+            for (int job = -1;;) {
+            const bool is_extra = job >= 0;
+            int b, dx, m0 = 0, yye = 0;
+            bool active;
+            if (!is_extra) {
+                b = tid / (2 * R);
+                dx = tid - b * 2 * R - R;
+                active = tid < nmain;
+            } else {
+                const int e = (job - xbeg) * 32 + wlane;
+                yye = e / (NB * nseg);
+                const int e2 = e - yye * NB * nseg;
+                b = e2 / nseg;
+                const int seg = e2 - b * nseg;
+                dx = R;
+                m0 = min(seg * (BS + 1), 2 * Rv - BS);  // overlapping the previous segment is harmless for an argmin
+                active = yye >= yy0 && yye < yy1;     // (also false beyond the last segment: yye >= NBY)
+            }
+            active = active && (bx0 + b < a.bw);
+            const int ox = (bx0 + b) * BS;
+            // this thread's window column (left edge of the candidate) and the aligned copy it reads
+            const int X = a.win_lm + b * BS + dx + R;
+            const uint32_t* colp = reinterpret_cast<const uint32_t*>(smem + (size_t)(X & 3) * copy_stride) + (X >> 2);
             const int mvx = a.sc * dx + px;
             const bool xvalid = active && (ox + dx >= 0) && (ox + dx + BS <= a.W - px) && (dx <= R - px);
             if (xvalid) {
                 const uint32_t absmx = (uint32_t)abs(mvx);
-                const uint32_t tthr = PACKED ? (absmx << kc.mbits) : absmx;
+                const uint32_t tthr = PACKED ? 0u : absmx;   // packed keys take |mvx| after the bodies
                 const int mvy0 = py - a.sc * Rv;  // mvy = mvy0 + sc*m
                 // main threads: every block row of the CTA; extra threads: their one (row, segment)
                 const int yy_lo = is_extra ? yye : yy0, yy_hi = is_extra ? yye + 1 : yy1;
@@ -336,20 +365,21 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                     const uint32_t* rowp = colp + ((yy - yy0) * BS + m0y) * wpitch;
                     int mbase = m0y - (BS - 1);
                     const uint32_t* ut = &utab[yy][0] + BS + mbase;
-                    me_body<BS, BODY_FIRST, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
+                    me_body<BS, BODY_FIRST, PACKED, SADMAP, WPC != 0>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                     rowp += BS * wpitch;
                     mbase += BS;
                     ut += BS;
                     for (int i = 0; i < nm; i++) {
-                        me_body<BS, BODY_MID, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
+                        me_body<BS, BODY_MID, PACKED, SADMAP, WPC != 0>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                         rowp += BS * wpitch;
                         mbase += BS;
                         ut += BS;
                     }
-                    me_body<BS, BODY_LAST, PACKED, SADMAP>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
+                    me_body<BS, BODY_LAST, PACKED, SADMAP, WPC != 0>(cur, acc, rowp, wpitch, mbase, ut, mlo, mhi, mvy0, a.sc, tthr, one, kc, best, bestm, smap, n1);
                     if (PACKED ? (best < 0x80000000u) : (best != 0xFFFFFFFFu)) {
                         uint32_t hi;
                         if (PACKED) {
+                            best += absmx << kc.mbits;   // the L1 field holds |mvx| + |mvy| <= 2 * Rh: no carry into the SAD field
                             bestm = best & ((1u << kc.mbits) - 1u);
                             const uint32_t l1 = (best >> kc.mbits) & ((1u << a.key_l1bits) - 1u);
                             hi = ((best >> (kc.mbits + a.key_l1bits)) << 9) | l1;
@@ -362,6 +392,14 @@ __global__ void __launch_bounds__(544, 1) me_tiled_kernel(const __grid_constant_
                     }
                 }
             }
+            // next job of this warp
+            int nj = 0;
+            if (wlane == 0) nj = atomicAdd(&xjob, 1);
+            nj = __shfl_sync(0xffffffffu, nj, 0);
+            if (nj >= xend) break;
+            job = nj;
+            }
+            win++;
             __syncthreads();  // everyone is done with the window before the next TMA overwrites it
         }
     }
@@ -461,7 +499,8 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
     a.Rv = cfg.Rv;
     const int nmain = NB * 2 * R;
     const int nseg = (2 * a.Rv + 1 + BS) / (BS + 1);
-    const int threads = ((nmain + 31) & ~31) + ((NB * NBY * nseg + 31) & ~31);
+    (void)nseg;
+    const int threads = (nmain + 31) & ~31;   // the last columns are extra jobs of the same warps (see the kernel)
     a.win_pitch = cfg.win_pitch;
     a.win_lm = cfg.win_lm;
     a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
