@@ -175,7 +175,10 @@ __global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constan
     __shared__ uint64_t bar;
     __shared__ unsigned long long sbest[NBY][NB];
     __shared__ int xjob;   // extra jobs handed out so far (all windows of the CTA)
-    __shared__ uint32_t utab[NBY][2 * 128 + 1 + 2 * BS];   // per-pass candidate tables, indexed by m + BS
+    // per-pass candidate tables, indexed by m + BS (the constant-pitch shapes have Rv <= 64: with eight stacked rows two CTAs
+    // only fit an SM with the smaller table)
+    constexpr int UTN = (WPC ? 2 * 64 : 2 * 128) + 1 + 2 * BS;
+    __shared__ uint32_t utab[NBY][UTN];
 
     const int tid = threadIdx.x;
     const int R = a.R;        // horizontal range = the search range (plane units)
@@ -533,7 +536,7 @@ template <int BS, int NB, int NBY, bool PACKED, bool SADMAP>
 cudaError_t launch_tiled_pm(const CUtensorMap& map, MeArgs a, int lanes, cudaStream_t st) {
     // constant-pitch instantiations for the two headline shapes: 1080p r=32 (4x4 blocks, 128-byte window rows) and
     // 4K r=64 (2x2 blocks, 160-byte rows)
-    if constexpr (BS == 16 && PACKED && !SADMAP && ((NB == 4 && NBY == 4) || (NB == 2 && NBY == 2))) {
+    if constexpr (BS == 16 && PACKED && !SADMAP && ((NB == 4 && (NBY == 4 || NBY == 8)) || (NB == 2 && NBY == 2))) {
         constexpr int WP = (NB == 4) ? 32 : 40;
         if (me_tile_config(BS, a.R).win_pitch == WP * 4) return launch_tiled_pmw<BS, NB, NBY, PACKED, SADMAP, WP>(map, a, lanes, st);
     }
@@ -577,11 +580,15 @@ TileShape pick_shape(int bs, int R, int Rv) {
         for (int i = 0; i < 3; i++) {
             const int nb = c[i];
             const int pitch = ((lm + nb * bs + 2 * R + 15) / 16) * 16;
-            const int nbys[] = {4, 2, 1};
-            for (int j = 0; j < 3; j++) {
+            const int nbys[] = {8, 4, 2, 1};
+            for (int j = 0; j < 4; j++) {
                 const int nby = nbys[j];
+                // eight stacked rows (half as many CTA prologues, 24 instead of 32 window rows per block row) only where it
+                // was measured: the headline geometry
+                if (nby == 8 && !(bs == 16 && nb == 4 && R == 32)) continue;
                 const int rows = nby * bs + 2 * Rv;
-                const int threads = ((nb * 2 * R + 31) & ~31) + ((nb * nby * nseg + 31) & ~31);
+                // (selection still counts the former extra warps, so every other geometry keeps the shape it was measured with)
+                const int threads = ((nb * 2 * R + 31) & ~31) + (nby == 8 ? 0 : ((nb * nby * nseg + 31) & ~31));
                 const int smem = 4 * pitch * rows + nb * nby * bs * bs;
                 if (pitch > 256 || rows > 256) continue;
                 if (pass == 0 ? (threads <= 341 && smem <= 106 * 1024) : (threads <= 544 && smem <= 110 * 1024)) return {nb, nby};
@@ -619,6 +626,9 @@ MeTileCfg me_tile_config(int bs, int R) {
 
 template <int BS, int NB>
 static cudaError_t launch_by_nby(const MeTileCfg& cfg, const CUtensorMap& map, const MeArgs& a, int lanes, cudaStream_t st) {
+    if constexpr (BS == 16 && NB == 4) {
+        if (cfg.nby == 8) return launch_tiled<BS, NB, 8>(map, a, lanes, st);
+    }
     if (cfg.nby == 4) return launch_tiled<BS, NB, 4>(map, a, lanes, st);
     if (cfg.nby == 2) return launch_tiled<BS, NB, 2>(map, a, lanes, st);
     return launch_tiled<BS, NB, 1>(map, a, lanes, st);
