@@ -51,6 +51,7 @@ struct bvc_ctx {
     int ngroups = 2;
     int iquad = 1;        // I-frame wavefront with four warps per block pair (BVC_IQUAD=0: the one-warp kernel)
     int tq_cta_cap = 0;   // clip path with lane groups: CTAs of the P transform launch (0 = one per work unit), BVC_TQ_CTAS
+    int me_tall = 0;      // motion search: tall tile shape by launch size (0), always (BVC_ME_TALL=1), never (BVC_ME_TALL=-1)
     int tail_split = 1;   // motion search: tiles of the last, partly filled wave as one-row CTAs (BVC_TAIL_SPLIT=0 turns it off)
     cudaStream_t st_grp[BVC_MAX_GROUPS] = {}, st_post[BVC_MAX_GROUPS] = {};
     // st_pack: entropy coding of I levels + stream assembly.  Nothing of the next step's search needs them (it needs the
@@ -68,6 +69,8 @@ struct bvc_ctx {
     size_t ref_planes = 0;
     CUtensorMap ref_map{};
     bool have_map = false;
+    CUtensorMap ref_map_tall{};   // box of the tall tile shape (me_tile_config(.., true)), when the geometry has one
+    bool have_tall = false;
     CUtensorMap fw_map{};     // FastME window walk: box = fastme_window_box()
     bool have_fw_map = false;
 
@@ -200,6 +203,7 @@ static int encode_map(bvc_ctx* c, CUtensorMap* out, int box_w, int box_h, int bo
 
 static int make_ref_map(bvc_ctx* c) {
     c->have_map = false;
+    c->have_tall = false;
     c->have_fw_map = false;
     if (c->p.fast_me && c->g.bs % 4 == 0 && c->g.bs <= 32) {
         int bw = 0, bh = 0, bd = 1;
@@ -216,6 +220,12 @@ static int make_ref_map(bvc_ctx* c) {
     int rc = encode_map(c, &c->ref_map, cfg.win_pitch, cfg.rows);
     if (rc != BVC_OK) return rc;
     c->have_map = true;
+    const MeTileCfg tall = me_tile_config(c->g.bs, R, true);
+    if (!c->p.fast_me && cfg.tiled && tall.tiled && tall.nby != cfg.nby) {
+        rc = encode_map(c, &c->ref_map_tall, tall.win_pitch, tall.rows);
+        if (rc != BVC_OK) return rc;
+        c->have_tall = true;
+    }
     return BVC_OK;
 }
 
@@ -274,6 +284,7 @@ extern "C" int bvc_create(bvc_ctx** out, int device, const bvc_params* p, int ma
         }
         if (const char* e = getenv("BVC_LANE_GROUPS")) c->ngroups = std::max(1, std::min(BVC_MAX_GROUPS, atoi(e)));
         if (const char* e = getenv("BVC_TAIL_SPLIT")) c->tail_split = atoi(e) != 0;
+        if (const char* e = getenv("BVC_ME_TALL")) c->me_tall = atoi(e);
         if (const char* e = getenv("BVC_IQUAD")) c->iquad = std::max(0, std::min(2, atoi(e)));
         if (const char* e = getenv("BVC_TQ_CTAS")) c->tq_cta_cap = std::max(0, atoi(e));
         const size_t L = (size_t)max_lanes, nb = (size_t)g.nblk;
@@ -637,12 +648,14 @@ static int enqueue_step(bvc_ctx* c, const StepPlan& sp, bool frame_api, cudaStre
         m.Rh = c->p.search_range * m.sc;
         m.uniform_nref = sp.nref;
         m.tail_split = c->tail_split && st_post == st_me;   // with lane groups the other group's kernels fill the tail
+        m.tall_mode = c->me_tall;
         const int e0 = tick(c, st_me);
         if (c->p.fast_me) {
             int rcf = launch_fastme_any(c, m, nl, L0, st_me, sp.nl);
             if (rcf != BVC_OK) return rcf;
         } else {
-            CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, st_me));
+            CK(launch_me_fullsearch(c->have_map ? &c->ref_map : nullptr, m, nl, c->ref_pool, g.plane_bytes, g.pitch, st_me,
+                                    c->have_tall ? &c->ref_map_tall : nullptr));
         }
         const int e1 = tick(c, st_me);
         span(c, BVC_K_ME, e0, e1);

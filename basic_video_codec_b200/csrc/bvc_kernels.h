@@ -29,6 +29,7 @@ struct MeArgs {
     int Rv;                        // vertical range the tiled bodies walk (>= R, 2*Rv a multiple of bs); launcher
     int tiles_x, tiles_y, n_full;  // linear tile grid: CTAs [0, n_full) own whole tiles, the rest one block row each (launcher)
     int tail_split;                // 1: cut the tiles of the last, partly filled wave into one-row CTAs
+    int tall_mode;                 // tall tile shape: 0 = by launch size (launch_me_fullsearch), 1 = always, -1 = never
     int uniform_nref;              // > 0: every lane of the launch has this many references (no per-lane look-up in the kernels)
     int n_tiles;                   // narrow kernel: tiles_x * tiles_y * lanes, walked by a persistent grid (launcher)
     int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
@@ -49,12 +50,12 @@ struct MeTileCfg {
     int win_lm;     // left margin: window column of x0-R inside the 16-byte aligned box
     int Rv;         // vertical range walked (tiled kernel: R rounded up so that 2*Rv % bs == 0)
 };
-MeTileCfg me_tile_config(int bs, int R);
+MeTileCfg me_tile_config(int bs, int R, bool tall = false);   // tall: see pick_shape (me_fullsearch.cu)
 // narrow-range search (me_narrow.cu): 2R < bs, one thread per (block, candidate column), exact work
 MeTileCfg me_narrow_config(int bs, int R);
 cudaError_t launch_me_narrow(const CUtensorMap& ref_map, const MeArgs& args, int lanes, cudaStream_t st);
 cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
-                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st);
+                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st, const CUtensorMap* tall_map = nullptr);
 
 // ---- K4 FastME ---------------------------------------------------------------------------------
 cudaError_t launch_fastme(const MeArgs& a, int lanes, const uint8_t* ref_base, size_t ref_plane_bytes, int ref_pitch,

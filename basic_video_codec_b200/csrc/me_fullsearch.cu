@@ -506,7 +506,7 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
     const int threads = (nmain + 31) & ~31;   // the last columns are extra jobs of the same warps (see the kernel)
     a.win_pitch = cfg.win_pitch;
     a.win_lm = cfg.win_lm;
-    a.win_copy_bytes = ((cfg.win_pitch * cfg.rows + 127) / 128) * 128;
+    a.win_copy_bytes = ((cfg.win_pitch * (NBY * BS + 2 * cfg.Rv) + 127) / 128) * 128;   // (NBY may be the tall shape's)
     const size_t smem = 4 * (size_t)(a.win_copy_bytes + 32) + (size_t)NBY * BS * NB * BS + 16;
     static size_t configured_dev[BVC_MAX_DEVICES] = {};
     size_t& configured = configured_dev[current_device_slot()];
@@ -568,7 +568,7 @@ cudaError_t launch_tiled(const CUtensorMap& map, MeArgs a, int lanes, cudaStream
 // the same for every CTA) and NBY stacked.  Constraints: <= 544 threads, TMA box <= 256 x 256, four window copies
 // <= 110 KB; shapes that let two CTAs share an SM are preferred.
 struct TileShape { int nb, nby; };
-TileShape pick_shape(int bs, int R, int Rv) {
+TileShape pick_shape(int bs, int R, int Rv, bool tall) {
     const int cand16[] = {4, 2, 1}, cand8[] = {8, 4, 2}, cand4[] = {8, 4, 4};
     const int* c = bs == 16 ? cand16 : bs == 8 ? cand8 : cand4;
     const int lm = (16 - R % 16) % 16;
@@ -583,9 +583,10 @@ TileShape pick_shape(int bs, int R, int Rv) {
             const int nbys[] = {8, 4, 2, 1};
             for (int j = 0; j < 4; j++) {
                 const int nby = nbys[j];
-                // eight stacked rows (half as many CTA prologues, 24 instead of 32 window rows per block row) only where it
-                // was measured: the headline geometry
-                if (nby == 8 && !(bs == 16 && nb == 4 && R == 32)) continue;
+                // eight stacked rows (half as many CTA prologues, 24 instead of 32 window rows per block row): the "tall" shape
+                // of the headline geometry, taken by launches of at least four waves of such CTAs (launch_me_fullsearch) --
+                // with the two or three GOP lanes a rank has under strong scaling the smaller CTAs fill the GPU better
+                if (nby == 8 && !(tall && bs == 16 && nb == 4 && R == 32)) continue;
                 const int rows = nby * bs + 2 * Rv;
                 // (selection still counts the former extra warps, so every other geometry keeps the shape it was measured with)
                 const int threads = ((nb * 2 * R + 31) & ~31) + (nby == 8 ? 0 : ((nb * nby * nseg + 31) & ~31));
@@ -606,13 +607,13 @@ TileShape pick_shape(int bs, int R, int Rv) {
 //              multiple of BS) and the extra offsets are masked, so the executed / algorithmic VABSDIFF4 ratio is
 //              (2*Rv+1)/(2R+1) (1.0 for every BASELINE configuration)
 //   else     : the generic kernel (R = 0, windows beyond the TMA box limits)
-MeTileCfg me_tile_config(int bs, int R) {
+MeTileCfg me_tile_config(int bs, int R, bool tall) {
     MeTileCfg c{};
     if (!(bs == 4 || bs == 8 || bs == 16)) return c;
     if (R < 1) return c;
     if (2 * R < bs) return me_narrow_config(bs, R);
     const int Rv = (2 * R + bs - 1) / bs * bs / 2;
-    const TileShape t = pick_shape(bs, R, Rv);
+    const TileShape t = pick_shape(bs, R, Rv, tall);
     if (t.nb == 0) return c;
     c.tiled = true;
     c.Rv = Rv;
@@ -635,9 +636,14 @@ static cudaError_t launch_by_nby(const MeTileCfg& cfg, const CUtensorMap& map, c
 }
 
 cudaError_t launch_me_fullsearch(const CUtensorMap* ref_map, const MeArgs& args, int lanes, const uint8_t* ref_base,
-                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st) {
+                                 size_t ref_plane_bytes, int ref_pitch, cudaStream_t st, const CUtensorMap* tall_map) {
     MeArgs a = args;
-    const MeTileCfg cfg = me_tile_config(a.bs, a.R);
+    MeTileCfg cfg = me_tile_config(a.bs, a.R);
+    if (tall_map && cfg.tiled && !a.sad_map) {
+        const MeTileCfg tc = me_tile_config(a.bs, a.R, true);
+        const long long ctas = (long long)((a.bw + tc.nb - 1) / tc.nb) * ((a.bh + tc.nby - 1) / tc.nby) * lanes;
+        if (tc.tiled && tc.nby == 8 && a.tall_mode >= 0 && (a.tall_mode > 0 || ctas >= 4 * 296)) { cfg = tc; ref_map = tall_map; }
+    }
     if (cfg.narrow && ref_map && !a.sad_map) return launch_me_narrow(*ref_map, a, lanes, st);
     if (cfg.tiled && ref_map) {
         if (a.bs == 16) {

@@ -121,6 +121,27 @@ def test_tail_split_many_lanes_matches_oracle(monkeypatch):
         assert ctx.encode_clip(frames)[0] == want
 
 
+@pytest.mark.parametrize("tall,split", [("1", "1"), ("1", "0"), ("-1", "1")])
+def test_tall_search_tiles_match_oracle(tall, split, monkeypatch):
+    """i=16, r=32: the headline search shape and its tall variant (eight stacked block rows per CTA, taken by large
+    launches -- forced here with BVC_ME_TALL) on a frame whose 13 x 11 blocks fill neither the last tile column nor the
+    last tile row, 75 GOP lanes in one launch (300 tall tiles: one whole wave of 296 plus a split tail): stream and
+    reconstruction equal to the oracle's, every lane through the extra jobs of the last candidate column."""
+    ob = _ob()
+    W, H, bs, r, qp, ip, ngop = 208, 176, 16, 32, 3, 2, 75
+    base = synth.moving_clip(67, H, W, 8, step=7, clamp=40)
+    frames = np.ascontiguousarray(np.concatenate([np.roll(base[(2 * g) % 6: (2 * g) % 6 + 2], 3 * g, axis=2) for g in range(ngop)]))
+    cfg = ob.make_config(W, H, bs, r, qp, nref=1, i_period=ip)
+    want, want_recon = ob.encode_clip(cfg, frames)
+    monkeypatch.setenv("BVC_ME_TALL", tall)
+    monkeypatch.setenv("BVC_TAIL_SPLIT", split)
+    with _ctx(W, H, bs, r, qp, ip=ip, lanes=ngop) as ctx:
+        ctx.set_lane_groups(1)
+        data, recon = ctx.encode_clip(frames, want_recon=True)
+    assert data == want
+    assert np.array_equal(recon, want_recon)
+
+
 @pytest.mark.parametrize("bs", [8, 16])
 def test_iframe_quad_and_single_warp_wavefronts_match_oracle(bs, monkeypatch):
     """The I-frame wavefront with four warps per block pair (few CTAs in flight) and with one (BVC_IQUAD=0, and any launch of
