@@ -33,6 +33,8 @@ struct MeArgs {
     int uniform_nref;              // > 0: every lane of the launch has this many references (no per-lane look-up in the kernels)
     int n_tiles;                   // narrow kernel: tiles_x * tiles_y * lanes, walked by a persistent grid (launcher)
     int key_l1bits, key_mbits;     // packed argmin key layout (launcher)
+    // divisions by launch constants as multiply-high + shift (launcher): by tiles_x * tiles_y, by tiles_x, by 2R
+    uint32_t perz_magic, perz_shift, tx_magic, tx_shift, r2_magic, r2_shift;
     // SAD map (FastME): when non-null the tiled kernel stores the SAD of every in-range candidate instead of reducing
     // them: uint16 [lane][ref][phase][blk][map_stride >= (2R+1)^2] (row = vertical offset + R, column = horizontal offset + R),
     // pre-filled with 0xFFFF = "leaves the plane".  max_refs = the ref stride (nRefFrames).

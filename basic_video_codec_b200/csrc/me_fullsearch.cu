@@ -66,6 +66,25 @@ __device__ __forceinline__ void load_cur(CurBlock<BS>& c, const uint8_t* p, int 
 
 enum { BODY_FIRST = 0, BODY_MID = 1, BODY_LAST = 2 };
 
+// A CTA that starts while its SM's other CTA is in the bodies gets the ALU pipe only when that one leaves it idle, so every
+// ALU-pipe instruction of the prologue (shifts, compares, the integer-division sequences) stretches the time until this CTA's
+// warps reach their own bodies and the SM has four searching warps per scheduler again.  The prologue therefore does its
+// arithmetic on the FMA pipe where it can: divisions by launch constants as multiply-high + shift, the byte-shifted window
+// copies as multiply-high + multiply-add.
+__device__ __forceinline__ uint32_t div_magic(uint32_t x, uint32_t magic, uint32_t shift) { return (__umulhi(x, magic) + x) >> shift; }
+static void div_magic_constants(uint32_t d, uint32_t& magic, uint32_t& shift) {   // exact for x < 2^31
+    shift = 0;
+    while ((1u << shift) < d) shift++;
+    magic = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << shift) - d)) / d + 1);
+}
+// (lo >> s) | (hi << (32 - s)) for s = 8, 16, 24 with k = 1 << (32 - s) in a register: mul.hi + mad.lo, both on the FMA pipe
+__device__ __forceinline__ uint32_t funnel_fma(uint32_t lo, uint32_t hi, uint32_t k) {
+    uint32_t t, r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(t) : "r"(lo), "r"(k));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(k), "r"(t));
+    return r;
+}
+
 // Per-pass constants of the per-thread argmin.
 //   PACKED : key = SAD << (l1bits+mbits) | L1 << mbits | m   -- one IMAD + one VIMNMX per candidate;
 //            usable when the three fields fit 32 bits (always for the headline configurations).
@@ -197,8 +216,8 @@ __global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constan
         yy1 = yy0 + 1;
     }
     const int per_z = a.tiles_x * a.tiles_y;
-    const int z = tile / per_z, t2 = tile - z * per_z;
-    const int ty = t2 / a.tiles_x, tx = t2 - ty * a.tiles_x;
+    const int z = (int)div_magic((uint32_t)tile, a.perz_magic, a.perz_shift), t2 = tile - z * per_z;
+    const int ty = (int)div_magic((uint32_t)t2, a.tx_magic, a.tx_shift), tx = t2 - ty * a.tiles_x;
     const int bx0 = tx * NB;
     const int by0 = ty * NBY;
     const int rows = (yy1 - yy0) * BS + 2 * Rv;       // window rows this CTA reads (the TMA box always has NBY*BS + 2*Rv)
@@ -270,15 +289,19 @@ __global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constan
             }
             if (PACKED) {
                 // utab[yy][m + BS]: L1 contribution and index of vertical offset m, bit 31 = outside the plane or the range
+                // one table column per thread (its |mvy| term once), all block rows of the CTA: no division, few compares
                 const int per = 2 * Rv + 1 + 2 * BS;
-                for (int i = tid; i < NBY * per; i += blockDim.x) {
-                    const int yy = i / per, ii = i - yy * per;
-                    const int oy = (by0 + yy) * BS;
-                    const int mlo = max(Rv - R, Rv - oy);
-                    const int mhi = min(Rv + R - py, a.H - py - BS - oy + Rv);
+                for (int ii = tid; ii < per; ii += blockDim.x) {
                     const int m = ii - BS;
                     const uint32_t amvy = (uint32_t)abs(py - a.sc * Rv + a.sc * m);
-                    utab[yy][ii] = (m >= mlo && m <= mhi) ? ((amvy << kc.mbits) | (uint32_t)m) : 0x80000000u;
+                    const uint32_t ent = (amvy << kc.mbits) | (uint32_t)m;
+#pragma unroll
+                    for (int yy = 0; yy < NBY; yy++) {
+                        const int oy = (by0 + yy) * BS;
+                        const int mlo = max(Rv - R, Rv - oy);
+                        const int mhi = min(Rv + R - py, a.H - py - BS - oy + Rv);
+                        utab[yy][ii] = (m >= mlo && m <= mhi) ? ent : 0x80000000u;
+                    }
                 }
             }
             mbar_wait(&bar, parity);
@@ -289,15 +312,19 @@ __global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constan
                 uint32_t* c2 = reinterpret_cast<uint32_t*>(smem + 2 * (size_t)copy_stride);
                 uint32_t* c3 = reinterpret_cast<uint32_t*>(smem + 3 * (size_t)copy_stride);
                 const int nq = (WW * rows) >> 4;   // 16-byte groups (WW is a multiple of 16)
+                uint32_t k8, k16, k24;   // opaque, so that the multiplications are not turned back into shifts
+                asm volatile("mov.u32 %0, 0x01000000;" : "=r"(k8));
+                asm volatile("mov.u32 %0, 0x00010000;" : "=r"(k16));
+                asm volatile("mov.u32 %0, 0x00000100;" : "=r"(k24));
                 for (int g4 = tid; g4 < nq; g4 += blockDim.x) {
                     const uint4 v = reinterpret_cast<const uint4*>(c0)[g4];
                     const uint32_t nx = c0[4 * g4 + 4];   // first word of the next group (the 32-byte gap after the last one)
-                    reinterpret_cast<uint4*>(c1)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 8), __funnelshift_r(v.y, v.z, 8),
-                                                                  __funnelshift_r(v.z, v.w, 8), __funnelshift_r(v.w, nx, 8));
-                    reinterpret_cast<uint4*>(c2)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16),
-                                                                  __funnelshift_r(v.z, v.w, 16), __funnelshift_r(v.w, nx, 16));
-                    reinterpret_cast<uint4*>(c3)[g4] = make_uint4(__funnelshift_r(v.x, v.y, 24), __funnelshift_r(v.y, v.z, 24),
-                                                                  __funnelshift_r(v.z, v.w, 24), __funnelshift_r(v.w, nx, 24));
+                    reinterpret_cast<uint4*>(c1)[g4] = make_uint4(funnel_fma(v.x, v.y, k8), funnel_fma(v.y, v.z, k8),
+                                                                  funnel_fma(v.z, v.w, k8), funnel_fma(v.w, nx, k8));
+                    reinterpret_cast<uint4*>(c2)[g4] = make_uint4(funnel_fma(v.x, v.y, k16), funnel_fma(v.y, v.z, k16),
+                                                                  funnel_fma(v.z, v.w, k16), funnel_fma(v.w, nx, k16));
+                    reinterpret_cast<uint4*>(c3)[g4] = make_uint4(funnel_fma(v.x, v.y, k24), funnel_fma(v.y, v.z, k24),
+                                                                  funnel_fma(v.z, v.w, k24), funnel_fma(v.w, nx, k24));
                 }
             }
             __syncthreads();
@@ -309,7 +336,7 @@ __global__ void __maxnreg__(WPC ? 128 : 96) me_tiled_kernel(const __grid_constan
             int b, dx, m0 = 0, yye = 0;
             bool active;
             if (!is_extra) {
-                b = tid / (2 * R);
+                b = (int)div_magic((uint32_t)tid, a.r2_magic, a.r2_shift);
                 dx = tid - b * 2 * R - R;
                 active = tid < nmain;
             } else {
@@ -520,6 +547,9 @@ cudaError_t launch_tiled_pmw(const CUtensorMap& map, MeArgs a, int lanes, cudaSt
     }
     a.tiles_x = (a.bw + NB - 1) / NB;
     a.tiles_y = (a.bh + NBY - 1) / NBY;
+    div_magic_constants((uint32_t)(a.tiles_x * a.tiles_y), a.perz_magic, a.perz_shift);
+    div_magic_constants((uint32_t)a.tiles_x, a.tx_magic, a.tx_shift);
+    div_magic_constants((uint32_t)(2 * R), a.r2_magic, a.r2_shift);
     const long long total = (long long)a.tiles_x * a.tiles_y * (SADMAP ? lanes * a.max_refs : lanes);
     // whole waves of full tiles, then the remaining tiles as NBY one-row CTAs each (see the kernel)
     static int slots_dev[BVC_MAX_DEVICES] = {};
