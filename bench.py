@@ -34,9 +34,10 @@ sys.path.insert(0, ROOT)
 
 W, H, BS, R, QP, IP, NFRAMES = 1920, 1088, 16, 32, 4, 30, 600
 CLIP_SEED = 1080
-# DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures (profiles/r2_ncu_me_kernel.csv, r1_ncu_tq_kernel.csv)
-ME_TRAFFIC_BYTES_PER_LANE = (41.837056e6 + 0.160256e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
-TQ_TRAFFIC_BYTES_PER_LANE = (43.469568e6 + 3.402240e6) / 10
+# DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures of the final build
+# (profiles/r2_ncu_me_kernel.csv, profiles/r2_ncu_tq_kernel.csv: dram__bytes_read.sum + dram__bytes_write.sum of a 10-lane launch)
+ME_TRAFFIC_BYTES_PER_LANE = (41.839104e6 + 0.392704e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
+TQ_TRAFFIC_BYTES_PER_LANE = (43.457280e6 + 6.424832e6) / 10       # profiles/r2_ncu_tq_kernel.csv
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
 
@@ -435,7 +436,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "kernel": "me_tiled_kernel<16,4,4> (full-search SAD, VABSDIFF4.U8.ACC)", "bound": "int-simd",
+            "kernel": "me_tiled_kernel<16,4,8> (full-search SAD, VABSDIFF4.U8.ACC; 4 x 8 blocks per CTA, 4 x 4 in launches of fewer than four waves)", "bound": "int-simd",
             "achieved": achieved / 1e12, "peak": peak_px / 1e12, "unit": "Tpx-absdiff/s",
             "frac": achieved / peak_px,
             "peak_source": "measured in this run, right before the timed region: bvc_measure_peaks (dependent-free VABSDIFF4.U8.ACC "
