@@ -32,8 +32,11 @@
 //   * argmin: per thread one IMAD (FMA pipe) + one VIMNMX per candidate on a packed key
 //     (SAD | L1 | m); per pass merged with the full 64-bit key (SAD, L1, ref, mvy, mvx); per block a
 //     shared-memory 64-bit atomicMin.
-//   * the last candidate column (dx = +R) of every block would leave a warp 1/32 full; it is given to
-//     one extra warp that splits it into vertical segments, so lane utilisation stays ~98 %.
+//   * the last candidate column (dx = +R) of every block would leave a warp 1/32 full: it is split into vertical segments,
+//     and the segments are jobs of 32 that the CTA's warps draw from a counter once their own columns are done, so lane
+//     utilisation stays ~98 % without extra warps (256 threads per CTA leave 128 registers for two CTAs per SM).
+//   * window words are requested a whole word ahead of their use (software-pipelined bodies); the prologue of a CTA keeps
+//     off the ALU pipe, because a CTA that starts beside a searching CTA only gets that pipe's gaps.
 #include "bvc_common.cuh"
 #include "bvc_kernels.h"
 
@@ -173,15 +176,13 @@ __device__ __forceinline__ void me_body(const CurBlock<BS>& cur, uint32_t (&acc)
     }
 }
 
-// Tiled full-search kernel.  One CTA = NB x NBY blocks (NB side by side, NBY stacked); grid =
-// (ceil(bw/NB), ceil(bh/NBY), lanes).  Dynamic smem: the TMA window (NBY*BS+2R rows) + 3 shifted copies +
-// the CTA's current blocks.
-// Threads: NB*2R "main" threads, one per candidate column dx in [-R, R-1] of one block column; each slides
-// over all 2R+1 vertical offsets once per stacked block row (current block reloaded into registers from
-// shared memory).  The last column dx = +R of every block would leave a warp 1/32 full: it is split into
-// vertical segments of BS+1 candidates (ramp-up + ramp-down body only) and all NB*NBY*nseg segments are
-// packed into extra warps that run once per window, so lane utilisation stays ~98 % and -- with NBY
-// stacked rows per CTA -- the extra warps weigh little against the main warps of their SM sub-partition.
+// Tiled full-search kernel.  One CTA = NB x NBY blocks (NB side by side, NBY stacked); grid = tiles x lanes, linear.
+// Dynamic smem: the TMA window (NBY*BS+2R rows) + 3 shifted copies + the CTA's current blocks.
+// Threads: NB*2R, one per candidate column dx in [-R, R-1] of one block column; each slides over all 2R+1 vertical
+// offsets once per stacked block row (current block reloaded into registers from shared memory).  The last column
+// dx = +R of every block is split into vertical segments of BS+1 candidates (ramp-up + ramp-down body only); 32 segments
+// are one "extra job", and a warp that has finished its own columns draws extra jobs from a shared-memory counter until
+// none is left -- no warp waits at the closing barrier while work remains, and the CTA needs no extra warps.
 // WPC: window pitch in words when it is known at compile time (the headline shapes), 0 = read it from the arguments.
 // With a constant pitch every LDS of an unrolled body takes an immediate offset from one base register: no address
 // arithmetic (VIADD, ALU pipe) between the VABSDIFF4s.

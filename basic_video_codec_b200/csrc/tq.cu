@@ -29,12 +29,12 @@ struct TqCtaSmem {
 };
 
 // ---------------------------------------------------------------------------------------------
-// P frames: every block independent.  A work unit = TQ_WARPS*NBW consecutive blocks of one lane; grid = min(units, a.cta_cap)
-// CTAs, each looping over units.  The cap matters on the clip path: this kernel runs on a high-priority stream while the
-// other lane group's search is on the GPU, and the block scheduler hands a high-priority kernel *every* slot the search
-// frees until it has no CTA left to place -- an uncapped grid evicts the search 1:1.  Capped at about one search CTA's
-// registers per SM (3 CTAs), the transform (fp64 pipe / issue bound) runs beside one search CTA per SM (ALU pipe bound,
-// which alone still reaches 86 % of the two-CTA rate), so most of its time disappears under the search.
+// P frames: every block independent.  A warp task = NBW consecutive blocks of one lane; the grid is persistent (at most
+// the resident CTAs, optionally fewer: a.cta_cap) and its warps draw tasks from a ticket counter.  The cap was an experiment
+// on the clip path: this kernel runs on a high-priority stream while the other lane group's search is on the GPU, and the
+// block scheduler hands a high-priority kernel every slot the search frees -- capped at one search CTA's registers per SM the
+// transform would run *beside* a search CTA; measured slower at every cap (profiles/r2_experiments.md section 4), so the
+// default is no cap.
 // Warp task wt of a launch: lane group fl = wt / tasks_per_lane, blocks (wt % tasks_per_lane) * NBW + q of the launch's rows.
 template <int BS>
 __device__ __forceinline__ PTask pframe_task(const TqArgs& a, int wt, int tasks_per_lane, int q) {
