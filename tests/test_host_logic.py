@@ -116,3 +116,23 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=60, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_division_by_launch_constants_is_exact():
+    """The kernels divide by launch constants (tiles per lane, blocks per row, 2r) as multiply-high + add + shift
+    (csrc/me_fullsearch.cu div_magic_constants / div_magic, csrc/tq.cu fast_div_constants / fast_div).  Same arithmetic in
+    numpy: exact for every divisor the library can meet and every dividend below 2^31."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([np.arange(0, 70000, dtype=np.uint64), rng.integers(0, 2**31, 200000, dtype=np.uint64),
+                         np.array([2**31 - 1, 2**31 - 2], dtype=np.uint64)])
+    for d in list(range(1, 300)) + [510, 1020, 4080, 8160, 65535, 65536, 1 << 20, (1 << 20) + 7]:
+        shift = 0
+        while (1 << shift) < d:
+            shift += 1
+        magic = ((1 << 32) * ((1 << shift) - d)) // d + 1
+        assert magic < (1 << 32)
+        hi = (xs * np.uint64(magic)) >> np.uint64(32)
+        s = hi + xs
+        assert int(s.max()) < (1 << 32)          # the 32-bit addition in the kernel does not wrap
+        assert np.array_equal(s >> np.uint64(shift), xs // np.uint64(d)), d
