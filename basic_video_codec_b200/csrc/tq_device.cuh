@@ -728,9 +728,9 @@ __device__ __forceinline__ void entropy_tile_store(const EntScratch<BS>& es, int
 // ---------------------------------------------------------------------------------------------
 // P-frame path, one warp task = NBW blocks (lane -> block `b` of lane group `fl`; lanes of one block hold the same values;
 // !valid lanes name any in-range block and produce nothing): PFrame.process_block PFrame.py:99-125,230-249;
-// Frame.py:61-75,190-202.  The task's pixel rows are fetched into registers one task ahead (PRows), behind the entropy
-// coding of the task before, so the two dependent global round trips (motion vector -> predicted row) are off the
-// critical path.
+// Frame.py:61-75,190-202.  The task's pixel rows are requested one task ahead, behind the entropy coding of the task
+// before (pframe_request_rows / pframe_stage_rows), so the two dependent global round trips (motion vector -> predicted
+// row) are off the critical path.
 // Division by a launch constant (x < 2^31): q = (mulhi(x, magic) + x) >> shift.
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic, uint32_t shift) { return (__umulhi(x, magic) + x) >> shift; }
 
@@ -741,9 +741,6 @@ struct PTask {
 
 // Asynchronous global -> shared copies (LDGSTS): the rows of the NEXT task travel into tile regions that are idle while
 // the current task's levels are coded, without occupying registers or a scoreboard.
-__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
 template <int BS>
 __device__ __forceinline__ void cp_async_row(void* dst, const void* src) {   // BS bytes, BS-byte aligned
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
