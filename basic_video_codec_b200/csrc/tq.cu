@@ -58,7 +58,7 @@ __device__ __forceinline__ PTask pframe_task(const TqArgs& a, int wt, int tasks_
 // GPU do.  The ticket is drawn before the transform and read after it; the next task's motion vector is requested before
 // the event pass of the entropy coder and its pixel rows before the coding pass, so no global round trip is exposed.
 template <int BS, bool DBG>
-__global__ void __launch_bounds__(TQ_WARPS * 32, 6) tq_pframe_kernel(TqArgs a, int tasks_per_lane, int ntasks) {
+__global__ void __launch_bounds__(TQ_WARPS * 32, 4) tq_pframe_kernel(TqArgs a, int tasks_per_lane, int ntasks) {
     static_assert(sizeof(EntScratch<BS>) <= sizeof(WarpTile<BS>::buf), "entropy scratch must fit the fp64 exchange buffer");
     extern __shared__ __align__(16) uint8_t smraw[];
     TqCtaSmem<BS>& sm = *reinterpret_cast<TqCtaSmem<BS>*>(smraw);

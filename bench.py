@@ -37,7 +37,7 @@ CLIP_SEED = 1080
 # DRAM traffic per lane (one 1080p frame) of a launch, from the committed ncu --set full captures of the final build
 # (profiles/r2_ncu_me_kernel.csv, profiles/r2_ncu_tq_kernel.csv: dram__bytes_read.sum + dram__bytes_write.sum of a 10-lane launch)
 ME_TRAFFIC_BYTES_PER_LANE = (41.839104e6 + 0.392704e6) / 10       # 10-lane launch (two lane groups), profiles/r2_ncu_me_kernel.csv
-TQ_TRAFFIC_BYTES_PER_LANE = (43.457280e6 + 6.424832e6) / 10       # profiles/r2_ncu_tq_kernel.csv
+TQ_TRAFFIC_BYTES_PER_LANE = (43.462656e6 + 6.845440e6) / 10       # profiles/r2_ncu_tq_kernel.csv
 WORKLOAD = "synthetic 1920x1088 Y plane, 600 frames, i=16, r=32 full-search, I_Period=30, nRefFrames=1, QP=4 (BASELINE configs[3])"
 
 
